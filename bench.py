@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""bench.py — 2-opt move evaluations per second on the BASELINE.json headline workload.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+Workload (config.workload): synthetic uniform EUC_2D instance uni<n> (n = 100000, SURVEY.md §8(c) generator),
+nearest-neighbour start tour built on the GPU, best-improvement 2-opt with on-the-fly distances.
+One STEP = one best-improvement pass = all n(n-3)/2 move deltas evaluated + argmin + move applied.
+  value   = passes * n(n-3)/2 / device time, tour resident in HBM (CUDA events on the engine's stream)
+  e2e     = the same through the host-buffer C-ABI call tspb200_two_opt(): coordinates + tour uploaded from
+            pinned host memory, K passes, tour downloaded, wall clock around the call
+  N > 1   : the pair tiles are dealt round-robin over the ranks (strong scaling, same instance), one 8-byte
+            NCCL min-allreduce per pass selects the move; max over ranks of the device time.
+--impl reference times the reference's own CPU code (oracle/_ref: its calc_dist driven over rows of one
+best-improvement scan, all host threads) on the same instance and start tour.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "2opt_move_evals_per_sec"
+UNIT = "evals/s"
+FP32_INSTR_PER_EVAL = 18  # per-unit figure of the on-the-fly 2-opt roofline
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=100000)
+    ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tlo", action="store_true", help="also run to the local optimum and report time_to_local_optimum_s")
+    ap.add_argument("--rows-per-thread", type=int, default=0)
+    ap.add_argument("--tile-cols", type=int, default=0)
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.idx), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        # "under load": samples in the upper half of the observed range
+        hi = [x for x in sm if x >= 0.5 * max(sm)]
+        return {"sm_mhz": float(np.median(hi)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+def pinned(arr: np.ndarray) -> np.ndarray:
+    import torch
+    t = torch.empty(arr.shape, dtype=getattr(torch, str(arr.dtype)), pin_memory=torch.cuda.is_available())
+    out = t.numpy()
+    out[...] = arr
+    out_holder.append(t)
+    return out
+
+
+out_holder = []
+
+
+def cpu_baseline_sample(xy, succ, seconds_budget: float):
+    """Rows of ONE best-improvement scan on the host cores: the reference's compiled calc_dist when
+    oracle/_ref is present (kind "reference"), else the oracle port."""
+    from oracle.oracle import Oracle, RefLib, REF_SO
+    n = len(xy)
+    threads = os.cpu_count() or 1
+    if os.path.exists(REF_SO):
+        lib, kind = RefLib(), "reference"
+    else:
+        lib, kind = Oracle(), "port"
+    # calibrate on a few rows, then size the sample for the time budget
+    ev, sec, _ = lib.bi_scan_rows_mt(xy, 0, succ, 0, min(n - 1, 16 * threads), threads)
+    rate = ev / max(sec, 1e-6)
+    want = rate * seconds_budget
+    total_pairs = n * (n - 3) // 2
+    if want >= total_pairs:
+        rows = n - 1
+    else:  # rows r with r*n - r^2/2 ~= want
+        rows = int(n - np.sqrt(max(0.0, float(n) * n - 2.0 * want)))
+        rows = max(16 * threads, min(n - 1, rows))
+    ev, sec, _ = lib.bi_scan_rows_mt(xy, 0, succ, 0, rows, threads)
+    return {"value": ev / sec, "unit": UNIT, "cores": threads, "kind": kind,
+            "sample": f"rows [0,{rows}) of one best-improvement scan of uni{n} from the NN start = {ev} pair evaluations "
+                      f"in {sec:.2f} s; {'reference calc_dist (oracle/_ref)' if kind == 'reference' else 'oracle port'}, "
+                      f"{threads} threads, rows dealt in blocks of 16"}, rows
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference CPU implementation on the same workload (rank 0 only)."""
+    if rank != 0:
+        return
+    from oracle.oracle import Oracle
+    from tsp_optimization_b200.instances import uniform_instance
+    n = args.n
+    xy = uniform_instance(n)
+    succ = start_tour_cpu_or_cached(xy, n)
+    total = max(1, args.steps + args.warmup)
+    per_step = max(0.3, min(8.0, 150.0 / total))
+    base, rows = cpu_baseline_sample(xy, succ, per_step)
+    from oracle.oracle import RefLib, REF_SO
+    lib = RefLib() if os.path.exists(REF_SO) else Oracle()
+    threads = os.cpu_count() or 1
+    for _ in range(args.warmup):
+        lib.bi_scan_rows_mt(xy, 0, succ, 0, rows, threads)
+    ev_sum, sec_sum = 0, 0.0
+    for _ in range(args.steps):
+        ev, sec, _ = lib.bi_scan_rows_mt(xy, 0, succ, 0, rows, threads)
+        ev_sum += ev
+        sec_sum += sec
+    val = ev_sum / sec_sum
+    base["value"] = val
+    line = {"metric": METRIC, "value": val, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * sec_sum / max(1, args.steps), "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"uni{n} EUC_2D, NN start, best-improvement 2-opt scan (reference CPU code)", "n": n},
+            "cpu_baseline": base,
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def start_tour_cpu_or_cached(xy, n):
+    """NN start tour without a GPU (reference arm): cached on disk because greedy() is O(n^2) on the CPU."""
+    from oracle.oracle import Oracle
+    cache = os.path.join(ROOT, "gpurun_out", f"nn_uni{n}.npy")
+    if os.path.exists(cache):
+        return np.load(cache)
+    succ, _ = Oracle().nn_tour(xy, 0, 0)
+    try:
+        os.makedirs(os.path.dirname(cache), exist_ok=True)
+        np.save(cache, succ)
+    except OSError:
+        pass
+    return succ
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from tsp_optimization_b200 import BI, Engine
+    from tsp_optimization_b200.dist import attach_engine_comm, init_process_group_from_env
+    from tsp_optimization_b200.instances import uniform_instance
+
+    if world > 1:
+        init_process_group_from_env("nccl")
+    torch.cuda.set_device(local)
+    n = args.n
+    xy = uniform_instance(n)
+    pairs = n * (n - 3) // 2
+
+    eng = Engine(local)
+    if args.rows_per_thread:
+        eng.set_option("rows_per_thread", args.rows_per_thread)
+    if args.tile_cols:
+        eng.set_option("tile_cols", args.tile_cols)
+    eng.set_instance(xy, 0)
+    t0 = time.perf_counter()
+    succ0, nn_cost = eng.nn_tour(0)  # identical on every rank (deterministic)
+    nn_s = time.perf_counter() - t0
+    if rank == 0:
+        try:
+            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+            np.save(os.path.join(ROOT, "gpurun_out", f"nn_uni{n}.npy"), succ0)
+        except OSError:
+            pass
+    if world > 1:
+        attach_engine_comm(eng, rank, world)
+    eng.tour_upload(succ0)
+
+    flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- resident-tour timing: W warm-up passes, then exactly K timed passes --------------------------------
+    eng.bi_run(args.warmup)
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    gpu_ms, launches, moves = 0.0, 0, 0
+    wall0 = time.perf_counter()
+    if flush is None:
+        st = eng.bi_run(args.steps)
+        gpu_ms, launches, moves, done_passes = st.gpu_ms, st.launches, st.moves, st.passes
+    else:
+        done_passes = 0
+        for _ in range(args.steps):
+            flush.zero_()  # > L2 (126 MB): every step starts with a cold L2
+            torch.cuda.synchronize()
+            st = eng.bi_run(1)
+            gpu_ms += st.gpu_ms
+            launches += st.launches
+            moves += st.moves
+            done_passes += st.passes
+    barrier()
+    wall_s = time.perf_counter() - wall0
+    clocks = sampler.stop()
+    if world > 1:
+        t = torch.tensor([gpu_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        gpu_ms = float(t.item())
+    value = done_passes * pairs / (gpu_ms * 1e-3)
+
+    # ---- e2e: host buffers through the C-ABI, copies inside the timed region -------------------------------
+    h_xy = pinned(xy)
+    h_succ = pinned(succ0.astype(np.int32))
+    e2e_passes = max(1, args.steps)
+    eng.set_instance(h_xy, 0)           # warm-up of the same call sequence
+    eng.two_opt(BI, h_succ, 0.0, max_iters=2)
+    barrier()
+    w0 = time.perf_counter()
+    eng.set_instance(h_xy, 0)
+    s_out, obj_out, st_e, _ = eng.two_opt(BI, h_succ, 0.0, max_iters=e2e_passes)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - w0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_val = st_e.passes * pairs / e2e_s
+    h2d = 16 * n + 4 * n
+    d2h = 4 * n + 8
+
+    tlo = None
+    if args.tlo:
+        eng.set_instance(h_xy, 0)
+        barrier()
+        w0 = time.perf_counter()
+        s_out, obj_out, st_f, _ = eng.two_opt(BI, h_succ, 0.0)
+        tlo_s = time.perf_counter() - w0
+        tlo = {"time_to_local_optimum_s": tlo_s, "passes": st_f.passes, "moves": st_f.moves, "gpu_ms": st_f.gpu_ms,
+               "start_cost": nn_cost, "final_cost": obj_out, "evals_per_s": st_f.evals / (st_f.gpu_ms * 1e-3)}
+
+    if rank != 0:
+        eng.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks, peaks_src = measured_peaks()
+    sm_mhz = clocks.get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
+    num_sms = eng.info("num_sms")
+    peak_instr = num_sms * 128 * sm_mhz * 1e6  # FP32 lane-instructions / s at the clock seen under load
+    per_gpu = value / world
+    roofline = {"bound": "fp32_issue", "achieved": per_gpu * FP32_INSTR_PER_EVAL / 1e12, "peak": peak_instr / 1e12,
+                "unit": "T lane-instr/s", "frac": per_gpu * FP32_INSTR_PER_EVAL / peak_instr, "traffic": None,
+                "kernel": "bi_scan_kernel", "per_unit": f"{FP32_INSTR_PER_EVAL} FP32 lane-instructions per evaluated move (SURVEY.md §8d)",
+                "peak_source": f"{num_sms} SMs x 128 FP32 lanes x {sm_mhz:.0f} MHz (nvidia-smi median under load); "
+                               f"MEASURED_PEAKS.json ({peaks_src}) holds no FP32 figure",
+                "sqrt_bound_frac": per_gpu / (num_sms * 16 * sm_mhz * 1e6),
+                "note": "the kernel shares each distance between the two moves that use it, so it issues ~9 FP32 "
+                        "lane-instr and 1.125 MUFU.SQRT per move; sqrt_bound_frac = evals/s over the MUFU limit "
+                        "(16 sqrt/clk/SM, one sqrt per move)"}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": gpu_ms / max(1, done_passes), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"uni{n} EUC_2D (SURVEY.md §8c generator), GPU nearest-neighbour start, best-improvement "
+                                   f"2-opt passes with on-the-fly distances (BASELINE configs[3])",
+                       "n": n, "pairs_per_step": pairs, "rows_per_thread": eng.info("rows_per_thread"),
+                       "tile_cols": eng.info("tile_cols"), "grid": eng.info("grid_bi"), "tiles": eng.info("ntiles"),
+                       "sharding": "tiles round-robin over ranks + 8-byte NCCL min-allreduce per pass" if world > 1 else "single GPU",
+                       "l2": "flushed between timed steps (256 MB write)" if flush is not None else "not flushed (2.4 MB working set)",
+                       "nn_start_s": nn_s},
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d / e2e_passes, "d2h_bytes_per_step": d2h / e2e_passes,
+                    "passes": st_e.passes, "seconds": e2e_s,
+                    "call": "tspb200_set_instance + tspb200_two_opt(BI, host succ[], max_iters=steps)"},
+            "gpu_launches": int(launches), "moves_applied": int(moves), "wall_s": wall_s,
+            "clocks": clocks, "roofline": roofline}
+    if tlo:
+        line["time_to_local_optimum"] = tlo
+    if not args.no_cpu_baseline and world == 1:
+        base, _ = cpu_baseline_sample(xy, succ0, 15.0)
+        line["cpu_baseline"] = base
+    print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

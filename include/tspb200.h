@@ -1,0 +1,153 @@
+/*
+ * tspb200.h — C ABI of libtspb200.so, the B200 (sm_100a) engine for the TSP_Optimization hot path:
+ * TSPLIB distance evaluation and 2-opt neighbourhood evaluation / move application.
+ *
+ * Plain pointers and sizes only (no torch / CUDA types).  All functions return 0 on success and a
+ * non-zero TSPB200_E_* code on failure; tspb200_last_error() gives the message.  There is NO CPU
+ * fallback: without a CUDA device every compute entry point fails with TSPB200_E_CUDA.
+ *
+ * Reference interfaces replaced (paths relative to the reference repository):
+ *   calc_dist        include/distutil.h:137, src/distutil.c:73-92   -> tspb200_dist_matrix*, tspb200_tour_costs
+ *   alg_2opt         include/heuristics.h:82, src/heuristics.c:438  -> tspb200_two_opt(mode = TSPB200_FI)
+ *   alg_2opt_tabu    src/tabusearch.c:107 (no header)                -> tspb200_two_opt(mode = TSPB200_BI)
+ *   reverse_path     include/utility.h:334, src/utility.c:708        -> applied on the device inside two_opt
+ *   greedy           include/heuristics.h, src/heuristics.c:18       -> tspb200_nn_tour
+ *   fitness          src/genetic.c:51-60                             -> tspb200_tour_costs
+ * The reference-named drop-in symbols themselves (calc_dist, alg_2opt, alg_2opt_tabu, reverse_path on the
+ * reference's `instance` struct) live in libtspb200_dropin.so, see tspb200_dropin.h and INTEGRATION.md.
+ */
+#ifndef TSPB200_H
+#define TSPB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* weight types: numeric values of the reference enum (include/utility.h:45-52) */
+enum {
+    TSPB200_EUC_2D = 0,
+    TSPB200_MAX_2D = 1,
+    TSPB200_MAN_2D = 2,
+    TSPB200_CEIL_2D = 3,
+    TSPB200_GEO = 4,
+    TSPB200_ATT = 5
+};
+
+/* 2-opt modes */
+enum {
+    TSPB200_FI = 0, /* first improvement  == reference alg_2opt       (src/heuristics.c:438-502)  */
+    TSPB200_BI = 1  /* best improvement   == reference alg_2opt_tabu  (src/tabusearch.c:107-178), NULL tabu list */
+};
+
+/* error codes */
+enum {
+    TSPB200_OK = 0,
+    TSPB200_E_CUDA = 1,     /* CUDA runtime / no device                          */
+    TSPB200_E_ARG = 2,      /* bad argument (e.g. succ[] is not a single cycle)  */
+    TSPB200_E_STATE = 3,    /* call order (no instance / no tour uploaded)       */
+    TSPB200_E_NCCL = 4,     /* NCCL not loadable or a collective failed          */
+    TSPB200_E_UNSUPPORTED = 5,
+    TSPB200_E_DEVICE_CHECK = 6 /* a device-side consistency check failed         */
+};
+
+/* status of a 2-opt run, also the reference's return convention (include/heuristics.h:6-7) */
+enum {
+    TSPB200_LOCAL_OPTIMUM = 0,
+    TSPB200_TIME_LIMIT_EXCEEDED = 2, /* reference TIME_LIMIT_EXCEEDED */
+    TSPB200_STOPPED_BY_CAP = 3       /* max_passes / max_moves reached */
+};
+
+typedef struct tspb200_ctx tspb200_ctx;
+
+typedef struct {
+    int64_t passes;     /* BI: scans performed (incl. the terminating one); FI: sweeps               */
+    int64_t moves;      /* applied moves                                                             */
+    int64_t evals;      /* BI: passes * n(n-3)/2 (every non-adjacent pair is evaluated every scan);  */
+                        /* FI: linear pairs swept (upper bound of the reference's count)             */
+    int64_t launches;   /* kernel launches of OUR kernels inside the timed region                    */
+    int64_t obj_delta;  /* sum of the applied deltas                                                 */
+    double gpu_ms;      /* device time of the run, CUDA events on the engine's stream                */
+    double cost;        /* tour cost after the run (BI: recomputed from scratch; FI: obj_in + delta) */
+    int32_t status;     /* TSPB200_LOCAL_OPTIMUM / _TIME_LIMIT_EXCEEDED / _STOPPED_BY_CAP            */
+    int32_t path;       /* 0 = FP32 filter + FP64 exact (EUC/CEIL/ATT), 1 = exact on the fly, 2 = matrix lookup */
+} tspb200_stats;
+
+typedef struct {
+    int32_t i, j;   /* node indices i<j exactly as the reference enumerates them */
+    int64_t delta;
+} tspb200_move;
+
+/* ---- context ------------------------------------------------------------------------------------ */
+int tspb200_create(int device, tspb200_ctx **out);
+void tspb200_destroy(tspb200_ctx *ctx);
+const char *tspb200_last_error(const tspb200_ctx *ctx);
+/* Tuning / mode knobs. keys: "rows_per_thread" (2|4|8), "tile_cols" (even, 32..1024), "grid" (blocks),
+ * "force_path" (-1 auto, 0 fp32 filter, 1 exact on the fly, 2 matrix), "batch" (passes per host sync),
+ * "time_limit_ms" (<=0 unlimited; checked between launch batches). */
+int tspb200_set_option(tspb200_ctx *ctx, const char *key, int64_t value);
+int64_t tspb200_get_info(const tspb200_ctx *ctx, const char *key);
+
+/* ---- instance (reference: instance.nodes / num_nodes / weight_type, include/utility.h:146-160) ---- */
+/* xy = n interleaved (x,y) doubles, the layout of the reference's point[] (include/utility.h:126-129). */
+int tspb200_set_instance(tspb200_ctx *ctx, const double *xy, int n, int weight_type);
+
+/* ---- distance matrix: out[i*n + j] = (int32) calc_dist(i, j)  (src/distutil.c:73-92) --------------- */
+/* Builds the matrix in HBM (row pitch rounded up to 4 ints) and keeps it resident; a resident matrix is
+ * what "force_path" = 2 / the GEO path gather from. gpu_ms (may be NULL) = device time of the kernel. */
+int tspb200_dist_matrix_build(tspb200_ctx *ctx, double *gpu_ms);
+/* Copies the resident matrix to host memory as a dense n*n int32 array. */
+int tspb200_dist_matrix_get(tspb200_ctx *ctx, int32_t *out);
+/* One call, host buffers: build + copy back. */
+int tspb200_dist_matrix(tspb200_ctx *ctx, int32_t *out);
+int tspb200_dist_matrix_free(tspb200_ctx *ctx);
+
+/* ---- tours ---------------------------------------------------------------------------------------- */
+/* succ[k] = successor of node k == reference inst->solution.edges[k].j (include/utility.h:131-134). */
+int tspb200_tour_upload(tspb200_ctx *ctx, const int32_t *succ, int64_t log_cap);
+int tspb200_tour_download(tspb200_ctx *ctx, int32_t *succ, double *cost);
+int tspb200_tour_log(tspb200_ctx *ctx, tspb200_move *log, int64_t cap, int64_t *count);
+
+/* Runs on the RESIDENT tour (no host<->device tour traffic): max_passes / max_moves < 0 = until the
+ * local optimum. Repeated calls continue where the previous one stopped. */
+int tspb200_bi_run(tspb200_ctx *ctx, int64_t max_passes, tspb200_stats *st);
+int tspb200_fi_run(tspb200_ctx *ctx, int64_t max_moves, tspb200_stats *st);
+
+/* Host-buffer entry point (what the drop-in shims call): upload succ, run, download succ.
+ * *obj: FI reads it and adds the deltas (reference heuristics.c:486); BI overwrites it with the recomputed
+ * cost (reference tabusearch.c:168-172). log may be NULL. */
+int tspb200_two_opt(tspb200_ctx *ctx, int mode, int32_t *succ, double *obj, int64_t max_iters,
+                    tspb200_stats *st, tspb200_move *log, int64_t log_cap, int64_t *log_count);
+
+/* Batched 2-opt of `batch` independent tours of the same instance (GA offspring repair, multi-start,
+ * VNS / tabu restarts): one thread block per tour, tour state in shared memory, run to the local optimum.
+ * succ = batch*n successors (in/out), obj = batch doubles (in/out, same convention as tspb200_two_opt). */
+int tspb200_two_opt_batch(tspb200_ctx *ctx, int mode, int32_t *succ, double *obj, int batch, tspb200_stats *st);
+
+/* Nearest-neighbour tour from `start` (reference greedy(), src/heuristics.c:18-78). */
+int tspb200_nn_tour(tspb200_ctx *ctx, int start, int32_t *succ, double *cost);
+
+/* Costs of `batch` tours: as_order != 0 -> tours are visiting orders (GA chromosomes, genetic.c:51-60),
+ * else successor arrays. */
+int tspb200_tour_costs(tspb200_ctx *ctx, const int32_t *tours, int batch, int as_order, double *out);
+
+/* ---- multi-GPU (one process per GPU; the caller bootstraps the id, e.g. over torch.distributed) ---- */
+/* Neighbourhood sharding: with a communicator attached, tspb200_bi_run deals the pair tiles round-robin
+ * over the ranks and selects the move with ONE 8-byte NCCL min-allreduce per pass; every rank applies the
+ * same move to its own replica of the tour. */
+int tspb200_comm_unique_id(void *id128); /* 128 bytes out (ncclUniqueId), call on rank 0 */
+int tspb200_comm_init(tspb200_ctx *ctx, const void *id128, int rank, int world);
+int tspb200_comm_destroy(tspb200_ctx *ctx);
+
+/* ---- host-only helpers (no device needed) ----------------------------------------------------------- */
+/* Tile plan of the best-improvement scan for (n, R rows per thread, TJ columns per tile); R or TJ == 0 picks
+ * the shape the engine would pick for `slots` resident blocks and `world` ranks. row_start: ntr+1 prefix sums
+ * of tiles per tile-row; row_j0: first tile column per tile-row. Used by the CPU-side sharding tests. */
+int tspb200_debug_tile_plan(int n, int R, int TJ, int slots, int world, int *out_R, int *out_TJ, int *row_start,
+                            int *row_j0, int cap, int *ntr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TSPB200_H */

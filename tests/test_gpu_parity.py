@@ -1,0 +1,399 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Everything goes through the C ABI
+(libtspb200.so / libtspb200_dropin.so) and is compared bit-for-bit with the oracle (oracle/tsp_oracle.c,
+itself pinned to the compiled reference) and with the committed golden fixtures."""
+import ctypes as C
+import hashlib
+
+import numpy as np
+import pytest
+
+from tsp_optimization_b200 import engine as eng
+from tsp_optimization_b200.instances import is_tour, order_to_succ, random_tours, uniform_instance
+
+FI, BI = eng.FI, eng.BI
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+# ---- ctypes mirror of the reference `instance` (include/tspb200_dropin.h) ---------------------------------
+class _Method(C.Structure):
+    _fields_ = [("id", C.c_int), ("edge_type", C.c_int), ("name", C.c_char_p), ("use_cplex", C.c_int)]
+
+
+class _Params(C.Structure):
+    _fields_ = [("file_path", C.c_char_p), ("num_threads", C.c_int), ("time_limit", C.c_int), ("method", _Method),
+                ("verbose", C.c_int), ("integer_cost", C.c_int), ("seed", C.c_int), ("perf_prof", C.c_int),
+                ("callback_2opt", C.c_int)]
+
+
+class _Solution(C.Structure):
+    _fields_ = [("obj_best", C.c_double), ("edges", C.c_void_p), ("time_to_solve", C.c_double), ("xbest", C.c_void_p)]
+
+
+class _Instance(C.Structure):
+    _fields_ = [("params", _Params), ("name", C.c_char_p), ("comment", C.c_char_p), ("nodes", C.c_void_p),
+                ("num_nodes", C.c_int), ("weight_type", C.c_int), ("num_columns", C.c_long), ("ind", C.c_void_p),
+                ("thread_seeds", C.c_void_p), ("solution", _Solution)]
+
+
+class RefInstance:
+    """A reference-layout instance living in numpy buffers (what the reference's parser + TSP_heuc build)."""
+
+    def __init__(self, xy, wt, succ, obj=0.0):
+        assert C.sizeof(_Instance) == 152
+        self.xy = np.ascontiguousarray(xy, dtype=np.float64)
+        n = len(self.xy)
+        self.edges = np.empty((n, 2), dtype=np.int32)
+        self.edges[:, 0] = np.arange(n)
+        self.edges[:, 1] = succ
+        c = _Instance()
+        c.params.integer_cost = 1
+        c.params.perf_prof = 1
+        c.params.time_limit = 0
+        c.nodes = self.xy.ctypes.data
+        c.num_nodes = n
+        c.weight_type = wt
+        c.num_columns = n * (n - 1) // 2
+        c.solution.obj_best = obj
+        c.solution.edges = self.edges.ctypes.data
+        self.c = c
+
+    def succ(self):
+        return self.edges[:, 1].copy()
+
+    def set_succ_entry(self, k, v):
+        self.edges[k, 1] = v
+
+
+pytestmark = pytest.mark.gpu
+
+EUC = ["berlin52", "eil51", "pr299", "a280", "lin318", "rd400", "pcb442", "pr439", "d493", "u574", "rat575", "p654",
+       "d657", "u724", "rat783", "pr1002", "vm1084"]
+
+
+# ---- distance matrix ------------------------------------------------------------------------------------------
+def test_matrix_bit_exact_all_golden_instances(engine, instances, goldens, oracle):
+    """every (i,j) of every fixture instance == calc_dist (EUC_2D, CEIL_2D, ATT, GEO incl. the GEO diagonal 1)."""
+    for nm, (xy, wt) in sorted(instances.items()):
+        engine.set_instance(xy, wt)
+        m = engine.dist_matrix()
+        g = goldens["instances"][nm]
+        if sha(m) != g["matrix_sha256"]:
+            ref = oracle.dist_matrix(xy, wt)
+            bad = np.argwhere(m != ref)
+            pytest.fail(f"{nm}: {len(bad)} entries differ, first {bad[:5].tolist()} got {m[tuple(bad[0])]} want {ref[tuple(bad[0])]}")
+        assert int(m.sum(dtype=np.int64)) == g["matrix_sum"]
+    engine.dist_matrix_free()
+
+
+@pytest.mark.parametrize("wt", [0, 3, 5, 1, 2, 99])
+def test_matrix_random_coordinates(engine, oracle, wt):
+    rng = np.random.default_rng(100 + wt)
+    for n, hi, frac in [(257, 50, False), (1031, 10000, False), (700, 3000, True), (515, 1_400_000, False)]:
+        xy = rng.integers(0, hi, size=(n, 2)).astype(np.float64)
+        if frac:
+            xy += rng.integers(0, 1000, size=(n, 2)) / 1000.0  # not FP32-representable -> FP64 path
+        engine.set_instance(xy, wt)
+        m = engine.dist_matrix()
+        ref = oracle.dist_matrix(xy, wt)
+        assert (m == ref).all(), (wt, n, hi, np.argwhere(m != ref)[:3].tolist())
+    engine.dist_matrix_free()
+
+
+def test_matrix_adversarial_half_boundaries(engine, oracle):
+    """distances engineered to sit on / next to the .5 (EUC) and integer (CEIL, ATT) rounding boundaries."""
+    pts = [(0.0, 0.0)]
+    for k in range(1, 400):
+        pts.append((float(k), float(k + 1)))      # s = 2k^2+2k+1 : sqrt close to k*sqrt2 + .7
+        pts.append((0.0, float(k) + 0.5))          # exact .5
+        pts.append((3.0 * k, 4.0 * k))             # exact integers 5k
+    for k in range(1, 300):
+        s = k * k + k                              # sqrt(s) = k + .5 - 1/(8k): nearest approach from below
+        pts.append((float(s), 0.0))
+    xy = np.array(pts, dtype=np.float64)
+    xy2 = np.sqrt(np.abs(xy)) if False else xy
+    for wt in (0, 3, 5):
+        engine.set_instance(xy2, wt)
+        m = engine.dist_matrix()
+        ref = oracle.dist_matrix(xy2, wt)
+        assert (m == ref).all(), (wt, np.argwhere(m != ref)[:3].tolist())
+    engine.dist_matrix_free()
+
+
+def test_matrix_large_checksum_property(engine, oracle):
+    """n = 6000 (144 MB matrix): symmetry, zero diagonal, and 64 sampled rows == oracle."""
+    xy = uniform_instance(6000)
+    engine.set_instance(xy, 0)
+    m = engine.dist_matrix()
+    assert (m == m.T).all() and (np.diag(m) == 0).all()
+    rows = np.random.default_rng(1).integers(0, 6000, size=64)
+    for i in rows:
+        out = np.empty(6000, dtype=np.int32)
+        oracle.L.orc_dist_row(np.ascontiguousarray(xy), 6000, 0, int(i), out)
+        assert (m[i] == out).all()
+    engine.dist_matrix_free()
+
+
+# ---- 2-opt, single tour --------------------------------------------------------------------------------------
+def _check_bi(engine, oracle, xy, wt, succ0, max_passes=-1, force_path=-1):
+    engine.set_option("force_path", force_path)
+    engine.set_instance(xy, wt)
+    if force_path == 2 or (force_path == -1 and wt in (1, 2, 4)):
+        engine.dist_matrix_build()
+    s, obj, st, log = engine.two_opt(BI, succ0, 0.0, max_iters=max_passes, log_cap=100000)
+    os_, oobj, ost, olog = oracle.two_opt_bi(xy, wt, succ0, max_passes=max_passes, log_cap=100000)
+    assert log.tolist() == olog.tolist()
+    assert (s == os_).all() and obj == oobj
+    assert st.moves == ost.moves and st.passes == ost.passes and st.evals == ost.evals
+    engine.set_option("force_path", -1)
+    return st
+
+
+def _check_fi(engine, oracle, xy, wt, succ0, obj0, force_path=-1):
+    engine.set_option("force_path", force_path)
+    engine.set_instance(xy, wt)
+    if force_path == 2 or (force_path == -1 and wt in (1, 2, 4)):
+        engine.dist_matrix_build()
+    s, obj, st, log = engine.two_opt(FI, succ0, obj0, log_cap=100000)
+    os_, oobj, ost, olog = oracle.two_opt_fi(xy, wt, succ0, obj0, log_cap=100000)
+    assert log.tolist() == olog.tolist()
+    assert (s == os_).all() and obj == oobj
+    assert st.moves == ost.moves and st.passes == ost.passes
+    engine.set_option("force_path", -1)
+    return st
+
+
+def test_berlin52_known_answers(engine, oracle, instances, goldens):
+    xy, wt = instances["berlin52"]
+    succ, cost = oracle.nn_tour(xy, wt, 0)
+    engine.set_instance(xy, wt)
+    s, obj, st, log = engine.two_opt(BI, succ, 0.0, log_cap=100)
+    assert obj == 7842 and st.moves == 11 and st.evals == 15288
+    assert log.tolist() == goldens["instances"]["berlin52"]["bi_log"]
+    s, obj, st, log = engine.two_opt(FI, succ, cost, log_cap=100)
+    assert obj == 8083 and st.moves == 20 and st.passes == 5
+    assert log.tolist() == goldens["instances"]["berlin52"]["fi_log"]
+
+
+@pytest.mark.parametrize("nm", ["berlin52", "pr299", "att532", "dsj1000", "pr1002", "att48", "eil51"])
+def test_bi_grid_kernel_move_log_parity(engine, oracle, instances, nm):
+    xy, wt = instances[nm]
+    succ, _ = oracle.nn_tour(xy, wt, 0)
+    st = _check_bi(engine, oracle, xy, wt, succ)
+    assert st.path == 0 and st.status == 0
+
+
+@pytest.mark.parametrize("nm", ["gr666", "ulysses22", "burma14", "gr96"])
+def test_bi_geo_matrix_and_exact_paths(engine, oracle, instances, nm):
+    xy, wt = instances[nm]
+    succ, _ = oracle.nn_tour(xy, wt, 0)
+    assert _check_bi(engine, oracle, xy, wt, succ).path == 2            # matrix lookup
+    assert _check_bi(engine, oracle, xy, wt, succ, force_path=1).path == 1  # FP64 on the fly
+
+
+def test_bi_golden_costs_all_instances(engine, instances, goldens, oracle):
+    for nm, (xy, wt) in sorted(instances.items()):
+        g = goldens["instances"][nm]
+        if "bi_cost" not in g:
+            continue
+        succ, _ = oracle.nn_tour(xy, wt, 0)
+        engine.set_instance(xy, wt)
+        if wt == 4:
+            engine.dist_matrix_build()
+        s, obj, st, _ = engine.two_opt(BI, succ, 0.0)
+        assert obj == g["bi_cost"] and sha(s) == g["bi_sha256"] and st.moves == g["bi_moves"], nm
+
+
+@pytest.mark.parametrize("nm", ["berlin52", "pr299", "att532", "gr666", "dsj1000", "ulysses16"])
+def test_fi_grid_kernel_move_log_parity(engine, oracle, instances, nm):
+    xy, wt = instances[nm]
+    succ, cost = oracle.nn_tour(xy, wt, 0)
+    _check_fi(engine, oracle, xy, wt, succ, cost)
+
+
+def test_fi_reference_csv_goldens(engine, instances, goldens, oracle):
+    """the reference's published 2OPT_GREEDY column (results/constructive_heuristics_2opt_new.csv), 18 instances."""
+    for nm, row in sorted(goldens["reference_csv"].items()):
+        xy, wt = instances[nm]
+        g = goldens["instances"][nm]
+        succ, cost = oracle.nn_tour(xy, wt, 0)
+        assert cost == row["GREEDY"]
+        engine.set_instance(xy, wt)
+        if wt == 4:
+            engine.dist_matrix_build()
+        s, obj, st, _ = engine.two_opt(FI, succ, cost)
+        assert obj == row["2OPT_GREEDY"], nm
+        assert sha(s) == g["fi_sha256"] and st.moves == g["fi_moves"] and st.passes == g["fi_sweeps"], nm
+
+
+@pytest.mark.parametrize("R,TJ", [(2, 32), (2, 64), (4, 64), (8, 128), (8, 256), (4, 34)])
+def test_bi_tile_shapes(engine, oracle, R, TJ):
+    xy = uniform_instance(1500)
+    succ, _ = oracle.nn_tour(xy, 0, 0)
+    engine.set_option("rows_per_thread", R)
+    engine.set_option("tile_cols", TJ)
+    try:
+        _check_bi(engine, oracle, xy, 0, succ, max_passes=25)
+    finally:
+        engine.set_option("rows_per_thread", 0)
+        engine.set_option("tile_cols", 0)
+
+
+def test_bi_random_start_and_wraparound_reversals(engine, oracle):
+    """random permutations: most moves have pos[a] > pos[b] for some step, i.e. the reversed forward path wraps."""
+    rng = np.random.default_rng(5)
+    for n, wt in [(333, 0), (400, 3), (257, 5), (64, 0), (5, 0), (4, 0), (7, 0)]:
+        xy = rng.integers(0, 2000, size=(n, 2)).astype(np.float64)
+        succ = order_to_succ(rng.permutation(n).astype(np.int32))
+        _check_bi(engine, oracle, xy, wt, succ)
+        _check_fi(engine, oracle, xy, wt, succ, oracle.succ_cost(xy, wt, succ))
+
+
+def test_duplicate_points_and_ties(engine, oracle):
+    """many equal deltas: the (delta, i, j) tie-break must pick the reference's lowest (i, j)."""
+    rng = np.random.default_rng(9)
+    xy = rng.integers(0, 12, size=(300, 2)).astype(np.float64)  # heavy duplicates, tiny integer distances
+    succ = order_to_succ(rng.permutation(300).astype(np.int32))
+    _check_bi(engine, oracle, xy, 0, succ)
+    _check_fi(engine, oracle, xy, 0, succ, oracle.succ_cost(xy, 0, succ))
+    grid = np.array([(x, y) for x in range(20) for y in range(20)], dtype=np.float64) * 10
+    succ = order_to_succ(rng.permutation(400).astype(np.int32))
+    _check_bi(engine, oracle, grid, 0, succ)
+    _check_fi(engine, oracle, grid, 3, succ, oracle.succ_cost(grid, 3, succ))
+
+
+def test_non_fp32_coordinates_use_fp64_exact_check(engine, oracle):
+    rng = np.random.default_rng(21)
+    xy = rng.integers(0, 300000, size=(500, 2)) + rng.integers(0, 1000, size=(500, 2)) / 1000.0
+    succ, cost = oracle.nn_tour(xy, 0, 0)
+    engine.set_instance(xy, 0)
+    assert engine.info("exact32") == 0 and engine.info("fp32_ok") == 1
+    _check_bi(engine, oracle, xy, 0, succ)
+    _check_fi(engine, oracle, xy, 0, succ, cost)
+
+
+def test_uni4000_bi_first_passes_and_fi_full(engine, oracle):
+    xy = uniform_instance(4000)
+    succ, cost = oracle.nn_tour(xy, 0, 0)
+    assert cost == 565693
+    _check_bi(engine, oracle, xy, 0, succ, max_passes=40)
+    st = _check_fi(engine, oracle, xy, 0, succ, cost)
+    assert st.moves == 1156 and st.passes == 9
+
+
+def test_uni10000_bi_passes_match_oracle(engine, oracle):
+    """BASELINE config 3 at full size: the first 3 passes move-for-move, then properties to the local optimum."""
+    xy = uniform_instance(10000)
+    succ, cost = oracle.nn_tour(xy, 0, 0)
+    _check_bi(engine, oracle, xy, 0, succ, max_passes=3)
+    engine.set_instance(xy, 0)
+    s, obj, st, log = engine.two_opt(BI, succ, 0.0, log_cap=4000)
+    assert st.status == 0 and is_tour(s)
+    assert obj == oracle.succ_cost(xy, 0, s) == cost + log[:, 2].sum()
+    assert (log[:, 2] < 0).all() and (log[:, 0] < log[:, 1]).all()
+    # idempotence: a 2-opt local optimum has no improving move left -> exactly one more scan, no move
+    s2, obj2, st2, _ = engine.two_opt(BI, s, 0.0)
+    assert (s2 == s).all() and st2.moves == 0 and st2.passes == 1
+    # and the oracle agrees that nothing improves (one full CPU scan)
+    _, _, key = oracle.bi_scan_rows_mt(xy, 0, s, 0, 10000, 8)
+    assert key[0] == 0
+
+
+# ---- batched 2-opt -------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", [FI, BI])
+def test_batch_kernel_parity(engine, oracle, instances, mode):
+    for nm, batch in [("berlin52", 40), ("pr299", 12), ("att48", 20), ("ulysses22", 10)]:
+        xy, wt = instances[nm]
+        n = len(xy)
+        tours = random_tours(n, batch, seed=n)
+        tours[0], _ = oracle.nn_tour(xy, wt, 0)
+        engine.set_instance(xy, wt)
+        obj0 = np.array([oracle.succ_cost(xy, wt, t) for t in tours])
+        out, obj, st = engine.two_opt_batch(mode, tours, obj0)
+        for b in range(batch):
+            if mode == BI:
+                es, eo, est, _ = oracle.two_opt_bi(xy, wt, tours[b])
+            else:
+                es, eo, est, _ = oracle.two_opt_fi(xy, wt, tours[b], obj0[b])
+            assert (out[b] == es).all() and obj[b] == eo, (nm, b)
+
+
+def test_batch_ga_population_uni1000(engine, oracle):
+    """BASELINE config 5 shape: random population on uni1000, FI repair == reference alg_2opt per tour."""
+    xy = uniform_instance(1000)
+    tours = random_tours(1000, 64, seed=1000)
+    engine.set_instance(xy, 0)
+    obj0 = engine.tour_costs(tours, as_order=False)
+    for b in range(4):
+        assert obj0[b] == oracle.succ_cost(xy, 0, tours[b])
+    out, obj, st = engine.two_opt_batch(FI, tours, obj0)
+    for b in (0, 17, 63):
+        es, eo, _, _ = oracle.two_opt_fi(xy, 0, tours[b], obj0[b])
+        assert (out[b] == es).all() and obj[b] == eo
+    for b in range(64):
+        assert is_tour(out[b]) and obj[b] == oracle.succ_cost(xy, 0, out[b])
+
+
+# ---- NN + costs ----------------------------------------------------------------------------------------------
+def test_nn_tour_parity(engine, oracle, instances, goldens):
+    for nm in ["berlin52", "att532", "gr666", "dsj1000", "pr1002"]:
+        xy, wt = instances[nm]
+        engine.set_instance(xy, wt)
+        s, c = engine.nn_tour(0)
+        g = goldens["instances"][nm]
+        assert c == g["nn_cost"] and sha(s) == g["nn_sha256"], nm
+    xy = uniform_instance(5000)
+    engine.set_instance(xy, 0)
+    for start in (0, 4999, 1234):
+        s, c = engine.nn_tour(start)
+        es, ec = oracle.nn_tour(xy, 0, start)
+        assert (s == es).all() and c == ec
+
+
+def test_tour_costs_order_and_succ(engine, oracle, instances):
+    xy, wt = instances["att532"]
+    n = len(xy)
+    rng = np.random.default_rng(2)
+    orders = np.stack([rng.permutation(n).astype(np.int32) for _ in range(9)])
+    engine.set_instance(xy, wt)
+    got = engine.tour_costs(orders, as_order=True)
+    for b in range(9):
+        assert got[b] == oracle.order_cost(xy, wt, orders[b])
+    succs = np.stack([order_to_succ(o) for o in orders])
+    assert (engine.tour_costs(succs, as_order=False) == got).all()
+
+
+# ---- the reference-named drop-in symbols ------------------------------------------------------------------------
+def test_dropin_symbols_on_reference_instance(oracle, instances):
+    L = C.CDLL(eng.DROPIN_PATH)
+    L.calc_dist.restype = C.c_double
+    L.calc_dist.argtypes = [C.c_int, C.c_int, C.c_void_p]
+    L.alg_2opt.argtypes = [C.c_void_p]
+    L.alg_2opt_tabu.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    for nm in ["pr299", "att532", "gr666"]:
+        xy, wt = instances[nm]
+        n = len(xy)
+        succ, cost = oracle.nn_tour(xy, wt, 0)
+        inst = RefInstance(xy, wt, succ, cost)
+        for (i, j) in [(0, 0), (0, 1), (5, 17), (n - 1, 3)]:
+            assert L.calc_dist(i, j, C.byref(inst.c)) == oracle.dist(xy, wt, i, j)
+        assert L.alg_2opt(C.byref(inst.c)) == 0
+        es, eo, _, _ = oracle.two_opt_fi(xy, wt, succ, cost)
+        assert (inst.succ() == es).all() and inst.c.solution.obj_best == eo
+        inst2 = RefInstance(xy, wt, succ, 123.0)
+        prev = np.full(n, -1, dtype=np.int32)
+        assert L.alg_2opt_tabu(C.byref(inst2.c), None, prev.ctypes.data, 1, 1) == 0
+        bs, bo, _, _, bprev = oracle.two_opt_bi(xy, wt, succ, want_prev=True)
+        assert (inst2.succ() == bs).all() and inst2.c.solution.obj_best == bo and (prev == bprev).all()
+    L.tspb200_dropin_reset()
+
+
+def test_errors_are_loud(engine):
+    engine.set_instance(uniform_instance(50), 0)
+    bad = np.arange(50, dtype=np.int32)  # self loops: not a cycle
+    with pytest.raises(eng.TspB200Error):
+        engine.tour_upload(bad)
+    with pytest.raises(eng.TspB200Error):
+        engine.set_option("rows_per_thread", 3)

@@ -1,0 +1,89 @@
+"""CPU tests of the host-side logic: tile plan coverage, key packing, instance helpers."""
+import numpy as np
+import pytest
+
+from tsp_optimization_b200.engine import key_pack, key_unpack, tile_plan
+from tsp_optimization_b200.instances import (is_tour, order_to_succ, random_tours, succ_to_order,
+                                             uniform_instance)
+
+
+def covered_pairs(n, R, TJ, rs, rj, tiles=None):
+    """Set of (p,q) the BI kernel evaluates for the given tile ids (all by default): a pair is evaluated
+    by tile (I,J) iff p in its row block, q in its column block and q >= p+2, q <= n-1, not (0, n-1)."""
+    TI = 256 * R
+    ntr = len(rj)
+    cover = np.zeros((n, n), dtype=np.int32)
+    ids = range(int(rs[-1])) if tiles is None else tiles
+    for t in ids:
+        I = int(np.searchsorted(rs, t, side="right") - 1)
+        J = int(rj[I] + (t - rs[I]))
+        p_lo, p_hi = I * TI, min((I + 1) * TI, n)
+        q_lo, q_hi = J * TJ, min((J + 1) * TJ, n)
+        for p in range(p_lo, p_hi):
+            lo = max(q_lo, p + 2)
+            if lo < q_hi:
+                cover[p, lo:q_hi] += 1
+    if n > 1:
+        cover[0, n - 1] = 0 if n < 3 else cover[0, n - 1] - 1
+    return cover
+
+
+@pytest.mark.parametrize("n,R,TJ", [(52, 2, 32), (299, 2, 64), (700, 2, 64), (1500, 4, 64), (2100, 8, 128), (513, 2, 64)])
+def test_tile_plan_covers_every_pair_exactly_once(n, R, TJ):
+    r, tj, rs, rj = tile_plan(n, R, TJ)
+    assert (r, tj) == (R, TJ)
+    cover = covered_pairs(n, R, TJ, rs, rj)
+    want = np.zeros((n, n), dtype=np.int32)
+    for p in range(n):
+        want[p, p + 2:] = 1
+    want[0, n - 1] = 0
+    assert (cover == want).all()
+    assert int(want.sum()) == n * (n - 3) // 2
+
+
+def test_tile_plan_round_robin_sharding_partitions_the_tiles():
+    n, R, TJ = 1500, 2, 64
+    _, _, rs, rj = tile_plan(n, R, TJ)
+    nt = int(rs[-1])
+    total = np.zeros((n, n), dtype=np.int32)
+    for world in (2, 4, 8):
+        total[:] = 0
+        for rank in range(world):
+            total += covered_pairs(n, R, TJ, rs, rj, tiles=range(rank, nt, world)) + 0
+        # (0, n-1) is subtracted once per rank by the helper: fix up
+        total[0, n - 1] = 0
+        assert total.max() == 1 and int(total.sum()) == n * (n - 3) // 2
+
+
+def test_auto_tile_shape_gives_enough_tiles():
+    for n in (10000, 100000):
+        R, TJ, rs, rj = tile_plan(n, 0, 0, slots=296, world=1)
+        assert int(rs[-1]) >= 4 * 296
+    R, TJ, rs, rj = tile_plan(100000, 0, 0, slots=296, world=8)
+    assert int(rs[-1]) >= 4 * 296 * 8
+
+
+def test_key_pack_orders_like_the_reference_scan():
+    """uint64 min == (lowest delta, then lowest i, then lowest j): reference tabusearch.c:126-156."""
+    rng = np.random.default_rng(0)
+    keys = [(int(rng.integers(-50, 0)), int(rng.integers(0, 131072)), int(rng.integers(0, 131072))) for _ in range(2000)]
+    keys += [(-7, 5, 9), (-7, 5, 8), (-7, 4, 100000), (-(1 << 29) + 1, 131071, 131071)]
+    packed = [key_pack(*k) for k in keys]
+    assert min(packed) == key_pack(*min(keys))
+    assert sorted(keys) == [key_unpack(p) for p in sorted(packed)]
+    assert all(p < (1 << 64) for p in packed)
+    # "no move" sentinel loses against every negative delta
+    assert key_pack(0, 0x1FFFF, 0x1FFFF) > max(p for p, k in zip(packed, keys) if k[0] < 0)
+
+
+def test_instance_helpers():
+    xy = uniform_instance(1000)
+    assert xy.shape == (1000, 2) and xy.min() >= 0 and xy.max() <= 10000
+    assert (xy == uniform_instance(1000)).all()
+    assert (xy == np.floor(xy)).all()
+    t = random_tours(50, 8, seed=3)
+    for b in range(8):
+        assert is_tour(t[b])
+        o = succ_to_order(t[b])
+        assert (order_to_succ(o) == t[b]).all()
+    assert not is_tour(np.array([1, 0, 3, 2], dtype=np.int32))

@@ -1,0 +1,177 @@
+// dropin.cpp — libtspb200_dropin.so: the reference-named symbols on the reference's `instance` struct,
+// forwarding to the CUDA engine (libtspb200.so).  Error behaviour follows the reference: fatal problems
+// print "[ERROR] ..." to stderr and exit(1) like its LOG_E macro (reference include/utility.h:33);
+// alg_2opt* return 0 or TIME_LIMIT_EXCEEDED (2) (reference include/heuristics.h:6-7).
+//
+// Thread safety: the reference's only concurrent caller works on private instance copies (reference
+// src/callback.c:64-69); here one mutex serialises the shared device context.
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "../../include/tspb200.h"
+#include "../../include/tspb200_dropin.h"
+
+namespace {
+
+struct Cache {
+    tspb200_ctx *ctx = nullptr;
+    const void *nodes = nullptr;
+    int n = 0, wt = 0;
+    uint64_t hash = 0;
+    std::vector<int32_t> matrix;  // host mirror for scalar calc_dist
+    bool have_matrix = false;
+};
+Cache g_cache;
+std::mutex g_mu;
+
+[[noreturn]] void die(const char *msg, const char *detail = "") {
+    fprintf(stderr, "[ERROR] tspb200: %s%s\n", msg, detail);
+    fflush(nullptr);
+    exit(1);
+}
+
+uint64_t hash_points(const tspb200_ref_point *p, int n) {
+    uint64_t h = 1469598103934665603ull;
+    const unsigned char *b = reinterpret_cast<const unsigned char *>(p);
+    for (size_t k = 0; k < (size_t)n * sizeof(tspb200_ref_point); ++k) { h ^= b[k]; h *= 1099511628211ull; }
+    return h;
+}
+
+// device context holding this instance's coordinates; full_check re-hashes the coordinates
+tspb200_ctx *context_for(tspb200_ref_instance *inst, bool full_check) {
+    if (!inst || !inst->nodes || inst->num_nodes < 1) die("instance has no nodes");
+    if (inst->params.integer_cost != 1)
+        die("--fcost (integer_cost=0) is outside the bit-exact contract of the GPU path; run with integer costs");
+    const bool same_ptr = g_cache.ctx && g_cache.nodes == inst->nodes && g_cache.n == inst->num_nodes && g_cache.wt == inst->weight_type;
+    if (same_ptr && !full_check) return g_cache.ctx;
+    uint64_t h = hash_points(inst->nodes, inst->num_nodes);
+    if (same_ptr && h == g_cache.hash) return g_cache.ctx;
+    if (g_cache.ctx && g_cache.n == inst->num_nodes && g_cache.wt == inst->weight_type && h == g_cache.hash) {
+        g_cache.nodes = inst->nodes;  // a copy_instance() clone of the same problem (reference utility.c:724-743)
+        return g_cache.ctx;
+    }
+    if (!g_cache.ctx) {
+        const char *dev = getenv("TSPB200_DEVICE");
+        int rc = tspb200_create(dev ? atoi(dev) : 0, &g_cache.ctx);
+        if (rc) die("cannot create the CUDA context: ", g_cache.ctx ? tspb200_last_error(g_cache.ctx) : "out of memory");
+    }
+    int rc = tspb200_set_instance(g_cache.ctx, reinterpret_cast<const double *>(inst->nodes), inst->num_nodes, inst->weight_type);
+    if (rc) die("set_instance failed: ", tspb200_last_error(g_cache.ctx));
+    g_cache.nodes = inst->nodes;
+    g_cache.n = inst->num_nodes;
+    g_cache.wt = inst->weight_type;
+    g_cache.hash = h;
+    g_cache.have_matrix = false;
+    g_cache.matrix.clear();
+    if (inst->weight_type == TSPB200_GEO || inst->weight_type == TSPB200_MAN_2D || inst->weight_type == TSPB200_MAX_2D) {
+        // metrics without an FP32 filter path evaluate 2-opt on a resident matrix when it fits
+        if ((size_t)inst->num_nodes * inst->num_nodes * 4 < (8ull << 30)) {
+            rc = tspb200_dist_matrix_build(g_cache.ctx, nullptr);
+            if (rc) die("distance matrix build failed: ", tspb200_last_error(g_cache.ctx));
+        }
+    }
+    return g_cache.ctx;
+}
+
+int run_two_opt(tspb200_ref_instance *inst, int mode, int *stored_prev) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    tspb200_ctx *ctx = context_for(inst, true);
+    const int n = inst->num_nodes;
+    if (!inst->solution.edges) die("instance has no solution.edges");
+    std::vector<int32_t> succ((size_t)n);
+    for (int k = 0; k < n; ++k) succ[k] = inst->solution.edges[k].j;
+    tspb200_set_option(ctx, "time_limit_ms", inst->params.time_limit > 0 ? (int64_t)inst->params.time_limit * 1000 : 0);
+    double obj = inst->solution.obj_best;
+    tspb200_stats st;
+    int rc = tspb200_two_opt(ctx, mode, succ.data(), &obj, -1, &st, nullptr, 0, nullptr);
+    if (rc) die("2-opt failed: ", tspb200_last_error(ctx));
+    for (int k = 0; k < n; ++k) { inst->solution.edges[k].i = k; inst->solution.edges[k].j = succ[k]; }
+    inst->solution.obj_best = obj;
+    if (stored_prev)
+        for (int k = 0; k < n; ++k) stored_prev[succ[k]] = k;  // reference tabusearch.c:173-175
+    if (st.status == TSPB200_TIME_LIMIT_EXCEEDED) {
+        printf("[INFO]  2-opt heuristics time exceeded\n");  // reference heuristics.c:460
+        return TSPB200_TIME_LIMIT_EXCEEDED;
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+// Scalar distances are served from a host mirror of the device-built matrix: a GPU hop per call would be
+// meaningless.  Large instances must use the batched entry points (tspb200_tour_costs / tspb200_nn_tour).
+double calc_dist(int i, int j, tspb200_ref_instance *inst) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    tspb200_ctx *ctx = context_for(inst, false);
+    const int n = inst->num_nodes;
+    if (i < 0 || j < 0 || i >= n || j >= n) die("calc_dist index out of range");
+    if (!g_cache.have_matrix) {
+        if (n > 16384) die("scalar calc_dist needs the n*n host mirror (n <= 16384); use tspb200_tour_costs / tspb200_nn_tour / tspb200_two_opt for larger instances");
+        g_cache.matrix.resize((size_t)n * n);
+        int rc = tspb200_dist_matrix(ctx, g_cache.matrix.data());
+        if (rc) die("distance matrix failed: ", tspb200_last_error(ctx));
+        g_cache.have_matrix = true;
+    }
+    return (double)g_cache.matrix[(size_t)i * n + j];
+}
+
+int alg_2opt(tspb200_ref_instance *inst) { return run_two_opt(inst, TSPB200_FI, nullptr); }
+
+int alg_2opt_tabu(tspb200_ref_instance *inst, int *skip_edge, int *stored_prev, const int iter, const int tenure) {
+    (void)iter; (void)tenure;
+    if (skip_edge)
+        die("alg_2opt_tabu with a non-NULL tabu list is not on the GPU path yet (SURVEY.md §8 row f2, 'next'); "
+            "call it with skip_edge == NULL for plain best-improvement 2-opt");
+    return run_two_opt(inst, TSPB200_BI, stored_prev);
+}
+
+// Host-side successor flip on the caller's own arrays, same contract as reference src/utility.c:708-722
+// (walk prev[] from start_node until end_node was re-pointed, then rebuild every prev[]).  The device-side
+// reversal used inside alg_2opt* is apply_move_block() in csrc/tsp_state.cuh; this entry point exists because
+// reference callers outside the hot path (tabu kick, src/tabusearch.c:295) flip host arrays directly.
+void reverse_path(tspb200_ref_instance *inst, int start_node, int end_node, int *prev) {
+    tspb200_ref_edge *ed = inst->solution.edges;
+    for (int at = start_node;;) {
+        int before = prev[at];
+        ed[at].j = before;
+        at = before;
+        if (before == end_node) break;
+    }
+    for (int k = 0; k < inst->num_nodes; ++k) prev[ed[k].j] = k;
+}
+
+int tspb200_dropin_layout(long long *out, int cap) {
+    long long v[] = {
+        (long long)sizeof(tspb200_ref_instance),
+        (long long)offsetof(tspb200_ref_instance, params.time_limit),
+        (long long)offsetof(tspb200_ref_instance, params.integer_cost),
+        (long long)offsetof(tspb200_ref_instance, params.perf_prof),
+        (long long)offsetof(tspb200_ref_instance, nodes),
+        (long long)offsetof(tspb200_ref_instance, num_nodes),
+        (long long)offsetof(tspb200_ref_instance, weight_type),
+        (long long)offsetof(tspb200_ref_instance, num_columns),
+        (long long)offsetof(tspb200_ref_instance, solution.obj_best),
+        (long long)offsetof(tspb200_ref_instance, solution.edges),
+        (long long)sizeof(tspb200_ref_point),
+        (long long)sizeof(tspb200_ref_edge),
+        (long long)offsetof(tspb200_ref_instance, params.verbose),
+        (long long)offsetof(tspb200_ref_instance, params.seed),
+    };
+    int k = (int)(sizeof v / sizeof v[0]);
+    for (int t = 0; t < k && t < cap; ++t) out[t] = v[t];
+    return k;
+}
+
+void tspb200_dropin_reset(void) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_cache.ctx) tspb200_destroy(g_cache.ctx);
+    g_cache = Cache{};
+}
+
+}  // extern "C"

@@ -1,0 +1,850 @@
+// engine.cu — host side of libtspb200.so: context, HBM-resident instance / tour state, launch loops and
+// the C ABI declared in include/tspb200.h.  No CPU fallback anywhere: every compute entry point needs a
+// CUDA device and fails with TSPB200_E_CUDA otherwise.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/tspb200.h"
+#include "tsp_state.cuh"
+
+namespace tspb {
+
+// ---- launchers implemented in the kernel translation units ---------------------------------------------
+cudaError_t launch_bi_scan(const BiArgs &a, int rows_per_thread, int grid, cudaStream_t st);
+cudaError_t launch_bi_scan_exact(const InstDev &inst, const TourDev &tour, int rank, int world, int fuse_apply, int grid,
+                                 cudaStream_t st);
+cudaError_t launch_bi_apply_packed(const InstDev &inst, const TourDev &tour, cudaStream_t st);
+cudaError_t launch_fi_search(const InstDev &I, const TourDev &T, int grid, cudaStream_t st);
+cudaError_t launch_dist_matrix(const InstDev &I, int *out, long long ld, int row_begin, int row_end, bool fast,
+                               cudaStream_t st);
+cudaError_t launch_build_state(const InstDev &I, const TourDev &T, const int *order, cudaStream_t st);
+cudaError_t launch_export_state(const TourDev &T, int *succ, unsigned long long *cost, cudaStream_t st);
+cudaError_t launch_tour_cost(const InstDev &I, const int *tours, int as_order, long long *out, int batch, cudaStream_t st);
+cudaError_t launch_nn_tour(const NnArgs &a, int grid, cudaStream_t st);
+cudaError_t launch_prep_points(const double2 *raw, double2 *pt64, float2 *pt32, int n, int metric, cudaStream_t st);
+int nn_max_grid(int num_sms);
+cudaError_t launch_two_opt_batch(const InstDev &I, int mode, int *succ, long long *obj_delta, long long *counters,
+                                 int batch, int num_sms, cudaStream_t st, int *launched);
+
+// ---- NCCL, loaded at run time (the torch-bundled or system libnccl.so.2) -------------------------------
+typedef struct { char internal[128]; } nccl_unique_id;
+typedef void *nccl_comm_t;
+struct NcclApi {
+    void *handle = nullptr;
+    int (*GetUniqueId)(nccl_unique_id *) = nullptr;
+    int (*CommInitRank)(nccl_comm_t *, int, nccl_unique_id, int) = nullptr;
+    int (*CommDestroy)(nccl_comm_t) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    bool load(std::string &err) {
+        if (handle) return true;
+        const char *names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char *nm : names) {
+            handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+            if (handle) break;
+        }
+        if (!handle) { err = std::string("cannot dlopen libnccl.so.2: ") + dlerror(); return false; }
+        GetUniqueId = (int (*)(nccl_unique_id *))dlsym(handle, "ncclGetUniqueId");
+        CommInitRank = (int (*)(nccl_comm_t *, int, nccl_unique_id, int))dlsym(handle, "ncclCommInitRank");
+        CommDestroy = (int (*)(nccl_comm_t))dlsym(handle, "ncclCommDestroy");
+        AllReduce = (int (*)(const void *, void *, size_t, int, int, nccl_comm_t, cudaStream_t))dlsym(handle, "ncclAllReduce");
+        GetErrorString = (const char *(*)(int))dlsym(handle, "ncclGetErrorString");
+        if (!GetUniqueId || !CommInitRank || !CommDestroy || !AllReduce) { err = "libnccl.so.2 lacks required symbols"; return false; }
+        return true;
+    }
+};
+static NcclApi g_nccl;
+constexpr int NCCL_UINT64 = 5;  // ncclUint64
+constexpr int NCCL_MIN = 3;     // ncclMin
+
+}  // namespace tspb
+
+using namespace tspb;
+
+struct tspb200_ctx {
+    int device = 0;
+    int num_sms = 148;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+
+    // instance
+    int n = 0, metric = 0;
+    InstDev inst{};
+    double2 *d_raw = nullptr, *d_pt64 = nullptr;
+    float2 *d_pt32 = nullptr;
+    int *d_mat = nullptr;
+    long long mat_ld = 0;
+    double dmax = 0;
+
+    // tour
+    bool has_tour = false;
+    TourDev tour{};
+    int *d_order = nullptr, *d_succ = nullptr;
+    unsigned long long *d_cost = nullptr;
+    Ctl *d_ctl = nullptr, *h_ctl = nullptr;
+    long long log_cap = 0;
+    double obj_in = 0;
+
+    // BI tiling
+    int R = 8, TJ = 256, grid_bi = 296, ntr = 0, ntiles = 0;
+    int *d_tile_row_start = nullptr, *d_tile_row_j0 = nullptr;
+
+    // options
+    int opt_R = 0, opt_TJ = 0, opt_grid = 0, opt_force_path = -1, opt_batch = 0;
+    long long opt_time_limit_ms = 0;
+
+    // comm
+    nccl_comm_t comm = nullptr;
+    int rank = 0, world = 1;
+};
+
+static int fail(tspb200_ctx *c, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf;
+    return code;
+}
+
+#define CK(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess)                                                                            \
+            return fail(ctx, TSPB200_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+static void free_tour(tspb200_ctx *c) {
+    cudaFree(c->tour.rec); cudaFree(c->tour.pos); cudaFree(c->tour.nrec); cudaFree(c->tour.nds);
+    cudaFree(c->tour.nsucc); cudaFree(c->tour.block_best); cudaFree(c->tour.log);
+    cudaFree(c->d_order); cudaFree(c->d_succ); cudaFree(c->d_cost);
+    cudaFree(c->d_tile_row_start); cudaFree(c->d_tile_row_j0);
+    c->tour = TourDev{};
+    c->d_order = c->d_succ = nullptr; c->d_cost = nullptr;
+    c->d_tile_row_start = c->d_tile_row_j0 = nullptr;
+    c->has_tour = false;
+}
+
+static void free_instance(tspb200_ctx *c) {
+    free_tour(c);
+    cudaFree(c->d_raw); cudaFree(c->d_pt64); cudaFree(c->d_pt32); cudaFree(c->d_mat);
+    c->d_raw = c->d_pt64 = nullptr; c->d_pt32 = nullptr; c->d_mat = nullptr;
+    c->n = 0;
+}
+
+extern "C" {
+
+int tspb200_create(int device, tspb200_ctx **out) {
+    if (!out) return TSPB200_E_ARG;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    tspb200_ctx *ctx = new tspb200_ctx();
+    *out = ctx;  // returned even on failure so that the caller can read the message
+    if (e != cudaSuccess || count == 0)
+        return fail(ctx, TSPB200_E_CUDA, "no CUDA device: %s (libtspb200 has no CPU fallback)",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= count) return fail(ctx, TSPB200_E_ARG, "device %d out of range (%d devices)", device, count);
+    ctx->device = device;
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(ctx, TSPB200_E_CUDA, "device %s is sm_%d%d; this library is built for sm_100a only", prop.name, prop.major, prop.minor);
+    ctx->num_sms = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&ctx->ev0));
+    CK(cudaEventCreate(&ctx->ev1));
+    CK(cudaMalloc(&ctx->d_ctl, sizeof(Ctl)));
+    CK(cudaMallocHost(&ctx->h_ctl, sizeof(Ctl)));
+    return TSPB200_OK;
+}
+
+void tspb200_destroy(tspb200_ctx *ctx) {
+    if (!ctx) return;
+    if (ctx->stream) {
+        cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+        if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
+        free_instance(ctx);
+        cudaFree(ctx->d_ctl);
+        cudaFreeHost(ctx->h_ctl);
+        cudaEventDestroy(ctx->ev0);
+        cudaEventDestroy(ctx->ev1);
+        cudaStreamDestroy(ctx->stream);
+    }
+    delete ctx;
+}
+
+const char *tspb200_last_error(const tspb200_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int tspb200_set_option(tspb200_ctx *ctx, const char *key, int64_t value) {
+    if (!ctx || !key) return TSPB200_E_ARG;
+    std::string k(key);
+    if (k == "rows_per_thread") {
+        if (value != 0 && value != 2 && value != 4 && value != 8) return fail(ctx, TSPB200_E_ARG, "rows_per_thread must be 0 (auto), 2, 4 or 8");
+        ctx->opt_R = (int)value;
+    } else if (k == "tile_cols") {
+        if (value != 0 && (value < 32 || value > 1024 || (value & 1))) return fail(ctx, TSPB200_E_ARG, "tile_cols must be 0 (auto) or even in [32,1024]");
+        ctx->opt_TJ = (int)value;
+    } else if (k == "grid") {
+        ctx->opt_grid = (int)value;
+    } else if (k == "force_path") {
+        if (value < -1 || value > 2) return fail(ctx, TSPB200_E_ARG, "force_path must be -1..2");
+        ctx->opt_force_path = (int)value;
+    } else if (k == "batch") {
+        ctx->opt_batch = (int)value;
+    } else if (k == "time_limit_ms") {
+        ctx->opt_time_limit_ms = value;
+    } else {
+        return fail(ctx, TSPB200_E_ARG, "unknown option %s", key);
+    }
+    return TSPB200_OK;
+}
+
+int64_t tspb200_get_info(const tspb200_ctx *ctx, const char *key) {
+    if (!ctx || !key) return -1;
+    std::string k(key);
+    if (k == "num_sms") return ctx->num_sms;
+    if (k == "n") return ctx->n;
+    if (k == "rows_per_thread") return ctx->R;
+    if (k == "tile_cols") return ctx->TJ;
+    if (k == "grid_bi") return ctx->grid_bi;
+    if (k == "ntiles") return ctx->ntiles;
+    if (k == "exact32") return ctx->inst.exact32;
+    if (k == "fp32_ok") return ctx->inst.fp32_ok;
+    if (k == "window_x1000") return (int64_t)(ctx->inst.W * 1000.0f);
+    if (k == "matrix_resident") return ctx->d_mat != nullptr;
+    if (k == "matrix_ld") return ctx->mat_ld;
+    if (k == "world") return ctx->world;
+    if (k == "rank") return ctx->rank;
+    return -1;
+}
+
+// ---- instance --------------------------------------------------------------------------------------------
+
+int tspb200_set_instance(tspb200_ctx *ctx, const double *xy, int n, int weight_type) {
+    if (!ctx || !ctx->stream) return fail(ctx, TSPB200_E_CUDA, "context has no CUDA device");
+    if (!xy || n < 1) return fail(ctx, TSPB200_E_ARG, "bad instance (n=%d)", n);
+    CK(cudaSetDevice(ctx->device));
+    free_instance(ctx);
+    ctx->n = n;
+    ctx->metric = weight_type;
+    // host-side scan: FP32 representability, bounding box -> filter window
+    bool exact32 = true, finite = true;
+    double xmin = xy[0], xmax = xy[0], ymin = xy[1], ymax = xy[1], dc = 0;
+    for (int k = 0; k < n; ++k) {
+        double x = xy[2 * k], y = xy[2 * k + 1];
+        if (!std::isfinite(x) || !std::isfinite(y)) finite = false;
+        float fx = (float)x, fy = (float)y;
+        if ((double)fx != x || (double)fy != y) exact32 = false;
+        dc = std::fmax(dc, std::fmax(std::fabs((double)fx - x), std::fabs((double)fy - y)));
+        xmin = std::fmin(xmin, x); xmax = std::fmax(xmax, x);
+        ymin = std::fmin(ymin, y); ymax = std::fmax(ymax, y);
+    }
+    double dmax = std::hypot(xmax - xmin, ymax - ymin);
+    ctx->dmax = dmax;
+    const bool metric_fp32 = (weight_type != TSPB200_GEO && weight_type != TSPB200_MAN_2D && weight_type != TSPB200_MAX_2D);
+    // FP32 filter usable when distances stay well inside the FP32 integer range (exact ds as float)
+    const bool fp32_ok = finite && metric_fp32 && dmax < 4.0e6;
+    // |D_fp32 - r_true| <= eps: MUFU.SQRT + the FP32 dx/dy/s roundings are < 2^-21 relative, coordinate rounding
+    // contributes <= 2*sqrt(2)*dc; see DESIGN.md §3 for the derivation of W = 2 + 2*eps (EUC needs 1 + 2*eps).
+    double eps = dmax * std::ldexp(1.0, -20) + 4.0 * dc;
+    ctx->inst = InstDev{};
+    ctx->inst.n = n;
+    ctx->inst.metric = weight_type;
+    ctx->inst.exact32 = exact32 ? 1 : 0;
+    ctx->inst.fp32_ok = fp32_ok ? 1 : 0;
+    ctx->inst.W = (float)(2.0 + 2.0 * eps);
+    ctx->inst.band = (float)std::ldexp(1.0, -20);
+    CK(cudaMalloc(&ctx->d_raw, sizeof(double2) * (size_t)n));
+    CK(cudaMalloc(&ctx->d_pt64, sizeof(double2) * (size_t)n));
+    CK(cudaMalloc(&ctx->d_pt32, sizeof(float2) * (size_t)n));
+    CK(cudaMemcpyAsync(ctx->d_raw, xy, sizeof(double2) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(launch_prep_points(ctx->d_raw, ctx->d_pt64, ctx->d_pt32, n, weight_type, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->inst.pt64 = ctx->d_pt64;
+    ctx->inst.pt32 = ctx->d_pt32;
+    ctx->inst.dmat = nullptr;
+    ctx->inst.dmat_ld = 0;
+    return TSPB200_OK;
+}
+
+// ---- distance matrix -------------------------------------------------------------------------------------
+int tspb200_dist_matrix_build(tspb200_ctx *ctx, double *gpu_ms) {
+    if (!ctx || !ctx->stream) return fail(ctx, TSPB200_E_CUDA, "context has no CUDA device");
+    if (ctx->n < 1) return fail(ctx, TSPB200_E_STATE, "no instance");
+    CK(cudaSetDevice(ctx->device));
+    const int n = ctx->n;
+    const long long ld = ((long long)n + 3) / 4 * 4;
+    if (!ctx->d_mat) {
+        size_t bytes = (size_t)n * (size_t)ld * sizeof(int);
+        size_t free_b = 0, total_b = 0;
+        CK(cudaMemGetInfo(&free_b, &total_b));
+        if (bytes + (1ull << 30) > free_b)
+            return fail(ctx, TSPB200_E_UNSUPPORTED, "distance matrix of %d nodes needs %.1f GB, %.1f GB free: use the on-the-fly path", n, bytes / 1e9, free_b / 1e9);
+        CK(cudaMalloc(&ctx->d_mat, bytes));
+        ctx->mat_ld = ld;
+    }
+    InstDev I = ctx->inst;
+    I.dmat = nullptr;  // the kernel computes, never gathers
+    const bool fast = I.fp32_ok && I.exact32;
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    CK(launch_dist_matrix(I, ctx->d_mat, ld, 0, n, fast, ctx->stream));
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (gpu_ms) {
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        *gpu_ms = ms;
+    }
+    return TSPB200_OK;
+}
+
+int tspb200_dist_matrix_get(tspb200_ctx *ctx, int32_t *out) {
+    if (!ctx || !ctx->stream) return fail(ctx, TSPB200_E_CUDA, "context has no CUDA device");
+    if (!ctx->d_mat) return fail(ctx, TSPB200_E_STATE, "no resident matrix");
+    if (!out) return fail(ctx, TSPB200_E_ARG, "null output");
+    CK(cudaSetDevice(ctx->device));
+    const int n = ctx->n;
+    CK(cudaMemcpy2DAsync(out, sizeof(int) * (size_t)n, ctx->d_mat, sizeof(int) * (size_t)ctx->mat_ld, sizeof(int) * (size_t)n,
+                         (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return TSPB200_OK;
+}
+
+int tspb200_dist_matrix(tspb200_ctx *ctx, int32_t *out) {
+    int rc = tspb200_dist_matrix_build(ctx, nullptr);
+    if (rc) return rc;
+    return tspb200_dist_matrix_get(ctx, out);
+}
+
+int tspb200_dist_matrix_free(tspb200_ctx *ctx) {
+    if (!ctx || !ctx->stream) return TSPB200_E_CUDA;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->d_mat);
+    ctx->d_mat = nullptr;
+    ctx->mat_ld = 0;
+    return TSPB200_OK;
+}
+
+// ---- tours -----------------------------------------------------------------------------------------------
+// which evaluator a 2-opt run uses
+static int select_path(const tspb200_ctx *ctx) {
+    if (ctx->opt_force_path >= 0) return ctx->opt_force_path;
+    if (ctx->inst.fp32_ok) return 0;
+    return ctx->d_mat ? 2 : 1;
+}
+
+static InstDev inst_for_path(const tspb200_ctx *ctx, int path) {
+    InstDev I = ctx->inst;
+    if (path == 2) { I.dmat = ctx->d_mat; I.dmat_ld = ctx->mat_ld; }
+    else { I.dmat = nullptr; I.dmat_ld = 0; }
+    if (path != 0) I.fp32_ok = 0;
+    return I;
+}
+
+// Tile plan of the best-improvement scan (pure host arithmetic, also exported for the CPU-side tests).
+// Tile-row I covers positions [I*TI, (I+1)*TI), TI = 256*R; its tile columns are J0(I)..(n-1)/TJ with
+// J0(I) = (I*TI + 2) / TJ, i.e. every column block that can hold a q >= p+2 for some p of the row.
+static long long tile_plan(int n, int R, int TJ, std::vector<int> *row_start, std::vector<int> *row_j0) {
+    const int TI = 256 * R;
+    const int ntr = n >= 4 ? (n - 2 + TI - 1) / TI : 0;
+    long long total = 0;
+    if (row_start) { row_start->clear(); row_j0->clear(); }
+    for (int I = 0; I < ntr; ++I) {
+        int j0 = (int)(((long long)I * TI + 2) / TJ);
+        int jl = (n - 1) / TJ;
+        if (row_start) { row_start->push_back((int)total); row_j0->push_back(j0); }
+        total += (jl - j0 + 1);
+    }
+    if (row_start) row_start->push_back((int)total);
+    return total;
+}
+
+// picks (R, TJ): the largest tile shape that still gives every resident block >= 4 tiles per rank
+static void choose_tile_shape(int n, int slots, int world, int opt_R, int opt_TJ, int *R, int *TJ) {
+    const int cand_r[] = {8, 4, 2};
+    const int cand_tj[] = {256, 128, 64};
+    for (int a = 0; a < 3; ++a) {
+        int r = opt_R ? opt_R : cand_r[a];
+        for (int b = 0; b < 3; ++b) {
+            int tj = opt_TJ ? opt_TJ : cand_tj[b];
+            if (tile_plan(n, r, tj, nullptr, nullptr) >= 4ll * slots * world) { *R = r; *TJ = tj; return; }
+        }
+    }
+    *R = opt_R ? opt_R : 2;
+    *TJ = opt_TJ ? opt_TJ : 64;
+}
+
+static void plan_tiles(tspb200_ctx *ctx, std::vector<int> &row_start, std::vector<int> &row_j0) {
+    const int slots = 2 * ctx->num_sms;
+    choose_tile_shape(ctx->n, slots, ctx->world, ctx->opt_R, ctx->opt_TJ, &ctx->R, &ctx->TJ);
+    ctx->ntiles = (int)tile_plan(ctx->n, ctx->R, ctx->TJ, &row_start, &row_j0);
+    ctx->ntr = (int)row_j0.size();
+    long long per_rank = (ctx->ntiles + ctx->world - 1) / ctx->world;
+    int grid = ctx->opt_grid > 0 ? ctx->opt_grid : slots;
+    if (grid > per_rank) grid = (int)(per_rank > 0 ? per_rank : 1);
+    ctx->grid_bi = grid;
+}
+
+// Host-only helper (no device needed): the tile plan for (n, R, TJ); R or TJ == 0 -> automatic choice for
+// `slots` resident blocks and `world` ranks. row_start gets ntr+1 entries, row_j0 ntr entries.
+int tspb200_debug_tile_plan(int n, int R, int TJ, int slots, int world, int *out_R, int *out_TJ, int *row_start,
+                            int *row_j0, int cap, int *ntr) {
+    if (n < 1 || slots < 1 || world < 1) return TSPB200_E_ARG;
+    int r = R, tj = TJ;
+    if (r == 0 || tj == 0) choose_tile_shape(n, slots, world, R, TJ, &r, &tj);
+    std::vector<int> rs, rj;
+    tile_plan(n, r, tj, &rs, &rj);
+    if ((int)rs.size() > cap) return TSPB200_E_ARG;
+    for (size_t k = 0; k < rs.size(); ++k) row_start[k] = rs[k];
+    for (size_t k = 0; k < rj.size(); ++k) row_j0[k] = rj[k];
+    if (ntr) *ntr = (int)rj.size();
+    if (out_R) *out_R = r;
+    if (out_TJ) *out_TJ = tj;
+    return TSPB200_OK;
+}
+
+int tspb200_tour_upload(tspb200_ctx *ctx, const int32_t *succ, int64_t log_cap) {
+    if (!ctx || !ctx->stream) return fail(ctx, TSPB200_E_CUDA, "context has no CUDA device");
+    if (ctx->n < 1) return fail(ctx, TSPB200_E_STATE, "no instance");
+    if (!succ) return fail(ctx, TSPB200_E_ARG, "null succ");
+    CK(cudaSetDevice(ctx->device));
+    const int n = ctx->n;
+    // successor array -> visiting order from node 0 (also validates that succ is one Hamiltonian cycle)
+    std::vector<int> order((size_t)n);
+    {
+        std::vector<unsigned char> seen((size_t)n, 0);
+        int at = 0;
+        for (int p = 0; p < n; ++p) {
+            if (at < 0 || at >= n || seen[at]) return fail(ctx, TSPB200_E_ARG, "succ[] is not a single cycle over %d nodes", n);
+            seen[at] = 1;
+            order[p] = at;
+            at = succ[at];
+        }
+        if (at != 0) return fail(ctx, TSPB200_E_ARG, "succ[] does not close the cycle at node 0");
+    }
+    std::vector<int> row_start, row_j0;
+    plan_tiles(ctx, row_start, row_j0);
+    const int TI = 256 * ctx->R;
+    const int alloc = ((n + TI - 1) / TI) * TI + TI + 1024 + 16;
+    if (!ctx->has_tour || ctx->tour.alloc != alloc || ctx->log_cap != log_cap) {
+        free_tour(ctx);
+        CK(cudaMalloc(&ctx->tour.rec, sizeof(float4) * (size_t)alloc));
+        CK(cudaMalloc(&ctx->tour.pos, sizeof(int) * (size_t)n));
+        CK(cudaMalloc(&ctx->tour.nrec, sizeof(float4) * (size_t)n));
+        CK(cudaMalloc(&ctx->tour.nds, sizeof(float) * (size_t)n));
+        CK(cudaMalloc(&ctx->tour.nsucc, sizeof(int) * (size_t)n));
+        CK(cudaMalloc(&ctx->tour.block_best, sizeof(MoveKey) * 4096));
+        if (log_cap > 0) CK(cudaMalloc(&ctx->tour.log, sizeof(MoveRec) * (size_t)log_cap));
+        CK(cudaMalloc(&ctx->d_order, sizeof(int) * (size_t)n));
+        CK(cudaMalloc(&ctx->d_succ, sizeof(int) * (size_t)n));
+        CK(cudaMalloc(&ctx->d_cost, sizeof(unsigned long long)));
+        ctx->tour.n = n;
+        ctx->tour.alloc = alloc;
+        ctx->tour.ctl = ctx->d_ctl;
+        ctx->tour.log_cap = log_cap;
+        ctx->log_cap = log_cap;
+    }
+    cudaFree(ctx->d_tile_row_start); cudaFree(ctx->d_tile_row_j0);
+    ctx->d_tile_row_start = ctx->d_tile_row_j0 = nullptr;
+    CK(cudaMalloc(&ctx->d_tile_row_start, sizeof(int) * (row_start.size() + 1)));
+    CK(cudaMalloc(&ctx->d_tile_row_j0, sizeof(int) * (row_j0.size() + 1)));
+    CK(cudaMemcpyAsync(ctx->d_tile_row_start, row_start.data(), sizeof(int) * row_start.size(), cudaMemcpyHostToDevice, ctx->stream));
+    if (!row_j0.empty())
+        CK(cudaMemcpyAsync(ctx->d_tile_row_j0, row_j0.data(), sizeof(int) * row_j0.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_order, order.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    Ctl c0;
+    memset(&c0, 0, sizeof c0);
+    c0.cur_i = 0; c0.cur_j = 1;
+    c0.fi_found = FI_NONE;
+    c0.max_moves = -1;
+    c0.last.i = c0.last.j = 0x7fffffff;
+    *ctx->h_ctl = c0;
+    CK(cudaMemcpyAsync(ctx->d_ctl, ctx->h_ctl, sizeof(Ctl), cudaMemcpyHostToDevice, ctx->stream));
+    InstDev I = inst_for_path(ctx, select_path(ctx));
+    CK(launch_build_state(I, ctx->tour, ctx->d_order, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->has_tour = true;
+    return TSPB200_OK;
+}
+
+int tspb200_tour_download(tspb200_ctx *ctx, int32_t *succ, double *cost) {
+    if (!ctx || !ctx->stream) return fail(ctx, TSPB200_E_CUDA, "context has no CUDA device");
+    if (!ctx->has_tour) return fail(ctx, TSPB200_E_STATE, "no tour uploaded");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemsetAsync(ctx->d_cost, 0, sizeof(unsigned long long), ctx->stream));
+    CK(launch_export_state(ctx->tour, ctx->d_succ, ctx->d_cost, ctx->stream));
+    unsigned long long c = 0;
+    if (succ) CK(cudaMemcpyAsync(succ, ctx->d_succ, sizeof(int) * (size_t)ctx->n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(&c, ctx->d_cost, sizeof c, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (cost) *cost = (double)(long long)c;
+    return TSPB200_OK;
+}
+
+int tspb200_tour_log(tspb200_ctx *ctx, tspb200_move *log, int64_t cap, int64_t *count) {
+    if (!ctx || !ctx->stream) return fail(ctx, TSPB200_E_CUDA, "context has no CUDA device");
+    if (!ctx->has_tour) return fail(ctx, TSPB200_E_STATE, "no tour uploaded");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(ctx->h_ctl, ctx->d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    long long have = ctx->h_ctl->log_count;
+    if (have > ctx->log_cap) have = ctx->log_cap;
+    if (have > cap) have = cap;
+    if (count) *count = ctx->h_ctl->log_count;
+    if (log && have > 0) {
+        static_assert(sizeof(tspb200_move) == sizeof(MoveRec), "log record layout");
+        CK(cudaMemcpyAsync(log, ctx->tour.log, sizeof(MoveRec) * (size_t)have, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return TSPB200_OK;
+}
+
+static int sync_ctl(tspb200_ctx *ctx) {
+    CK(cudaMemcpyAsync(ctx->h_ctl, ctx->d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->h_ctl->error) return fail(ctx, TSPB200_E_DEVICE_CHECK, "device-side consistency check failed (code %d)", ctx->h_ctl->error);
+    return TSPB200_OK;
+}
+
+int tspb200_bi_run(tspb200_ctx *ctx, int64_t max_passes, tspb200_stats *st) {
+    if (!ctx || !ctx->stream) return fail(ctx, TSPB200_E_CUDA, "context has no CUDA device");
+    if (!ctx->has_tour) return fail(ctx, TSPB200_E_STATE, "no tour uploaded");
+    CK(cudaSetDevice(ctx->device));
+    const int n = ctx->n;
+    const int path = select_path(ctx);
+    if (path == 2 && !ctx->d_mat) return fail(ctx, TSPB200_E_STATE, "matrix path selected but no resident matrix");
+    if (path == 0 && !ctx->inst.fp32_ok) return fail(ctx, TSPB200_E_UNSUPPORTED, "FP32 filter path is not valid for this instance");
+    if (ctx->world > 1 && (n > (1 << 17))) return fail(ctx, TSPB200_E_UNSUPPORTED, "multi-GPU key packing supports n <= 131072");
+    InstDev I = inst_for_path(ctx, path);
+    BiArgs a;
+    a.inst = I;
+    a.tour = ctx->tour;
+    a.tile_row_start = ctx->d_tile_row_start;
+    a.tile_row_j0 = ctx->d_tile_row_j0;
+    a.ntr = ctx->ntr;
+    a.ntiles = ctx->ntiles;
+    a.TJ = ctx->TJ;
+    a.rank = ctx->rank;
+    a.world = ctx->world;
+    a.fuse_apply = ctx->world == 1 ? 1 : 0;
+    int rc = sync_ctl(ctx);
+    if (rc) return rc;
+    const long long passes0 = ctx->h_ctl->passes, moves0 = ctx->h_ctl->moves, launches0 = ctx->h_ctl->launches,
+                    delta0 = ctx->h_ctl->obj_delta;
+    int exact_grid = ctx->opt_grid > 0 ? ctx->opt_grid : 4 * ctx->num_sms;
+    if (exact_grid > n) exact_grid = n > 0 ? n : 1;
+    // passes per host round trip: large instances run for milliseconds per pass, small ones for microseconds
+    long long batch = ctx->opt_batch > 0 ? ctx->opt_batch : (n >= 50000 ? 8 : (n >= 5000 ? 64 : 256));
+    long long host_launches = 0;
+    int status = TSPB200_LOCAL_OPTIMUM;
+    auto t_start = std::chrono::steady_clock::now();
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    long long remaining = max_passes;
+    bool done = ctx->h_ctl->done != 0;
+    while (!done) {
+        long long k = batch;
+        if (max_passes >= 0) {
+            if (remaining <= 0) { status = TSPB200_STOPPED_BY_CAP; break; }
+            if (k > remaining) k = remaining;
+        }
+        for (long long q = 0; q < k; ++q) {
+            if (path == 0) CK(launch_bi_scan(a, ctx->R, ctx->grid_bi, ctx->stream));
+            else CK(launch_bi_scan_exact(I, ctx->tour, ctx->rank, ctx->world, a.fuse_apply, exact_grid, ctx->stream));
+            host_launches++;
+            if (ctx->world > 1) {
+                unsigned long long *p = &ctx->d_ctl->packed;
+                int nr = g_nccl.AllReduce(p, p, 1, NCCL_UINT64, NCCL_MIN, ctx->comm, ctx->stream);
+                if (nr != 0) return fail(ctx, TSPB200_E_NCCL, "ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(nr) : "?");
+                CK(launch_bi_apply_packed(I, ctx->tour, ctx->stream));
+                host_launches++;
+            }
+        }
+        if (max_passes >= 0) remaining -= k;
+        rc = sync_ctl(ctx);
+        if (rc) return rc;
+        done = ctx->h_ctl->done != 0;
+        if (!done && ctx->opt_time_limit_ms > 0) {
+            auto el = std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - t_start).count();
+            if (el > ctx->opt_time_limit_ms) { status = TSPB200_TIME_LIMIT_EXCEEDED; break; }
+        }
+    }
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (st) {
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        memset(st, 0, sizeof *st);
+        st->passes = ctx->h_ctl->passes - passes0;
+        st->moves = ctx->h_ctl->moves - moves0;
+        st->evals = st->passes * ((long long)n * (n - 3) / 2);
+        st->launches = ctx->world > 1 ? host_launches : (ctx->h_ctl->launches - launches0);
+        st->obj_delta = ctx->h_ctl->obj_delta - delta0;
+        st->gpu_ms = ms;
+        st->status = done ? TSPB200_LOCAL_OPTIMUM : status;
+        st->path = path;
+        st->cost = 0;
+    }
+    return TSPB200_OK;
+}
+
+int tspb200_fi_run(tspb200_ctx *ctx, int64_t max_moves, tspb200_stats *st) {
+    if (!ctx || !ctx->stream) return fail(ctx, TSPB200_E_CUDA, "context has no CUDA device");
+    if (!ctx->has_tour) return fail(ctx, TSPB200_E_STATE, "no tour uploaded");
+    CK(cudaSetDevice(ctx->device));
+    const int n = ctx->n;
+    const int path = select_path(ctx);
+    if (path == 2 && !ctx->d_mat) return fail(ctx, TSPB200_E_STATE, "matrix path selected but no resident matrix");
+    InstDev I = inst_for_path(ctx, path);
+    int rc = sync_ctl(ctx);
+    if (rc) return rc;
+    const long long passes0 = ctx->h_ctl->passes, moves0 = ctx->h_ctl->moves, launches0 = ctx->h_ctl->launches,
+                    delta0 = ctx->h_ctl->obj_delta, swept0 = ctx->h_ctl->pairs_swept;
+    // max_moves is an absolute cap on the device counter
+    long long cap = max_moves >= 0 ? moves0 + max_moves : -1;
+    CK(cudaMemcpyAsync(&ctx->d_ctl->max_moves, &cap, sizeof cap, cudaMemcpyHostToDevice, ctx->stream));
+    if (n < 4) {  // no non-adjacent pair exists: one empty sweep
+        if (st) { memset(st, 0, sizeof *st); st->passes = 1; st->path = path; }
+        return TSPB200_OK;
+    }
+    int grid = ctx->opt_grid > 0 ? ctx->opt_grid : 2 * ctx->num_sms;
+    if (grid > n - 1) grid = n - 1;
+    long long batch = ctx->opt_batch > 0 ? ctx->opt_batch : 128;
+    int status = TSPB200_LOCAL_OPTIMUM;
+    auto t_start = std::chrono::steady_clock::now();
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    bool done = false;
+    if (max_moves == 0) { done = false; status = TSPB200_STOPPED_BY_CAP; }
+    else {
+        // a previous capped run leaves done=1 behind: clear it when the caller asks for more
+        int zero = 0;
+        if (ctx->h_ctl->done && cap != -1 && ctx->h_ctl->moves < cap) CK(cudaMemcpyAsync(&ctx->d_ctl->done, &zero, sizeof zero, cudaMemcpyHostToDevice, ctx->stream));
+        while (!done) {
+            for (long long q = 0; q < batch; ++q) CK(launch_fi_search(I, ctx->tour, grid, ctx->stream));
+            rc = sync_ctl(ctx);
+            if (rc) return rc;
+            done = ctx->h_ctl->done != 0;
+            if (!done && ctx->opt_time_limit_ms > 0) {
+                auto el = std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - t_start).count();
+                if (el > ctx->opt_time_limit_ms) { status = TSPB200_TIME_LIMIT_EXCEEDED; break; }
+            }
+        }
+        if (done && cap >= 0 && ctx->h_ctl->moves >= cap) status = TSPB200_STOPPED_BY_CAP;
+    }
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (st) {
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        memset(st, 0, sizeof *st);
+        st->passes = ctx->h_ctl->passes - passes0;
+        st->moves = ctx->h_ctl->moves - moves0;
+        st->evals = ctx->h_ctl->pairs_swept - swept0;
+        st->launches = ctx->h_ctl->launches - launches0;
+        st->obj_delta = ctx->h_ctl->obj_delta - delta0;
+        st->gpu_ms = ms;
+        st->status = status;
+        st->path = path;
+    }
+    return TSPB200_OK;
+}
+
+int tspb200_two_opt(tspb200_ctx *ctx, int mode, int32_t *succ, double *obj, int64_t max_iters, tspb200_stats *st,
+                    tspb200_move *log, int64_t log_cap, int64_t *log_count) {
+    if (!ctx || !ctx->stream) return fail(ctx, TSPB200_E_CUDA, "context has no CUDA device");
+    if (mode != TSPB200_FI && mode != TSPB200_BI) return fail(ctx, TSPB200_E_ARG, "mode must be TSPB200_FI or TSPB200_BI");
+    int rc = tspb200_tour_upload(ctx, succ, log ? log_cap : 0);
+    if (rc) return rc;
+    tspb200_stats local;
+    memset(&local, 0, sizeof local);
+    rc = (mode == TSPB200_BI) ? tspb200_bi_run(ctx, max_iters, &local) : tspb200_fi_run(ctx, max_iters, &local);
+    if (rc) return rc;
+    double cost = 0;
+    rc = tspb200_tour_download(ctx, succ, &cost);
+    if (rc) return rc;
+    if (mode == TSPB200_BI) {
+        local.cost = cost;  // reference tabusearch.c:168-172: recomputed from scratch
+        if (obj) *obj = cost;
+    } else {
+        double o = (obj ? *obj : 0.0) + (double)local.obj_delta;  // reference heuristics.c:486
+        local.cost = o;
+        if (obj) *obj = o;
+    }
+    if (log || log_count) {
+        rc = tspb200_tour_log(ctx, log, log_cap, log_count);
+        if (rc) return rc;
+    }
+    if (st) *st = local;
+    return TSPB200_OK;
+}
+
+int tspb200_two_opt_batch(tspb200_ctx *ctx, int mode, int32_t *succ, double *obj, int batch, tspb200_stats *st) {
+    if (!ctx || !ctx->stream) return fail(ctx, TSPB200_E_CUDA, "context has no CUDA device");
+    if (ctx->n < 1) return fail(ctx, TSPB200_E_STATE, "no instance");
+    if (mode != TSPB200_FI && mode != TSPB200_BI) return fail(ctx, TSPB200_E_ARG, "mode must be TSPB200_FI or TSPB200_BI");
+    if (!succ || batch < 1) return fail(ctx, TSPB200_E_ARG, "bad batch");
+    CK(cudaSetDevice(ctx->device));
+    const int n = ctx->n;
+    const int path = select_path(ctx);
+    if (path == 2 && !ctx->d_mat) return fail(ctx, TSPB200_E_STATE, "matrix path selected but no resident matrix");
+    InstDev I = inst_for_path(ctx, path);
+    int *d_succ = nullptr;
+    long long *d_delta = nullptr, *d_cnt = nullptr;
+    CK(cudaMalloc(&d_succ, sizeof(int) * (size_t)n * batch));
+    CK(cudaMalloc(&d_delta, sizeof(long long) * (size_t)batch));
+    CK(cudaMalloc(&d_cnt, sizeof(long long) * 4 * (size_t)batch));
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    CK(cudaMemcpyAsync(d_succ, succ, sizeof(int) * (size_t)n * batch, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(d_delta, 0, sizeof(long long) * (size_t)batch, ctx->stream));
+    CK(cudaMemsetAsync(d_cnt, 0, sizeof(long long) * 4 * (size_t)batch, ctx->stream));
+    int launched = 0;
+    cudaError_t le = launch_two_opt_batch(I, mode, d_succ, d_delta, d_cnt, batch, ctx->num_sms, ctx->stream, &launched);
+    if (le != cudaSuccess) {
+        cudaFree(d_succ); cudaFree(d_delta); cudaFree(d_cnt);
+        if (le == cudaErrorInvalidValue) return fail(ctx, TSPB200_E_UNSUPPORTED, "batched 2-opt keeps a tour in shared memory: n=%d is too large", n);
+        return fail(ctx, TSPB200_E_CUDA, "batched 2-opt launch failed: %s", cudaGetErrorString(le));
+    }
+    std::vector<long long> h_delta((size_t)batch), h_cnt((size_t)batch * 4);
+    CK(cudaMemcpyAsync(succ, d_succ, sizeof(int) * (size_t)n * batch, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(h_delta.data(), d_delta, sizeof(long long) * (size_t)batch, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(h_cnt.data(), d_cnt, sizeof(long long) * 4 * (size_t)batch, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_succ); cudaFree(d_delta); cudaFree(d_cnt);
+    tspb200_stats local;
+    memset(&local, 0, sizeof local);
+    for (int b = 0; b < batch; ++b) {
+        local.moves += h_cnt[4 * b + 0];
+        local.passes += h_cnt[4 * b + 1];
+        local.evals += h_cnt[4 * b + 2];
+        if (h_cnt[4 * b + 3]) return fail(ctx, TSPB200_E_DEVICE_CHECK, "batched 2-opt: tour %d failed its device-side check", b);
+        local.obj_delta += h_delta[b];
+        if (obj) {
+            if (mode == TSPB200_BI) obj[b] = (double)h_delta[b];  // kernel stores the recomputed cost for BI
+            else obj[b] += (double)h_delta[b];
+        }
+    }
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    local.gpu_ms = ms;
+    local.launches = launched;
+    local.path = path;
+    if (st) *st = local;
+    return TSPB200_OK;
+}
+
+int tspb200_nn_tour(tspb200_ctx *ctx, int start, int32_t *succ, double *cost) {
+    if (!ctx || !ctx->stream) return fail(ctx, TSPB200_E_CUDA, "context has no CUDA device");
+    if (ctx->n < 1) return fail(ctx, TSPB200_E_STATE, "no instance");
+    const int n = ctx->n;
+    if (start < 0 || start >= n) return fail(ctx, TSPB200_E_ARG, "start node %d out of range", start);  // WRONG_STARTING_NODE
+    CK(cudaSetDevice(ctx->device));
+    int path = select_path(ctx);
+    if (path == 2 && !ctx->d_mat) path = 1;
+    InstDev I = inst_for_path(ctx, path == 2 ? 2 : 1);
+    int *d_succ = nullptr;
+    unsigned char *d_vis = nullptr;
+    unsigned long long *d_slots = nullptr;
+    unsigned *d_bar = nullptr;
+    long long *d_cost = nullptr;
+    CK(cudaMalloc(&d_succ, sizeof(int) * (size_t)n));
+    CK(cudaMalloc(&d_vis, (size_t)n));
+    CK(cudaMalloc(&d_slots, sizeof(unsigned long long) * 2));
+    CK(cudaMalloc(&d_bar, sizeof(unsigned)));
+    CK(cudaMalloc(&d_cost, sizeof(long long)));
+    CK(cudaMemsetAsync(d_vis, 0, (size_t)n, ctx->stream));
+    CK(cudaMemsetAsync(d_slots, 0xff, sizeof(unsigned long long) * 2, ctx->stream));
+    CK(cudaMemsetAsync(d_bar, 0, sizeof(unsigned), ctx->stream));
+    NnArgs a;
+    a.inst = I; a.start = start; a.succ = d_succ; a.visited = d_vis; a.slots = d_slots; a.barrier = d_bar; a.cost = d_cost;
+    int grid = nn_max_grid(ctx->num_sms);
+    int want = (n + 255) / 256;
+    if (grid > want) grid = want;
+    if (grid < 1) grid = 1;
+    cudaError_t le = launch_nn_tour(a, grid, ctx->stream);
+    long long c = 0;
+    if (le == cudaSuccess) le = cudaMemcpyAsync(succ, d_succ, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream);
+    if (le == cudaSuccess) le = cudaMemcpyAsync(&c, d_cost, sizeof c, cudaMemcpyDeviceToHost, ctx->stream);
+    if (le == cudaSuccess) le = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_succ); cudaFree(d_vis); cudaFree(d_slots); cudaFree(d_bar); cudaFree(d_cost);
+    if (le != cudaSuccess) return fail(ctx, TSPB200_E_CUDA, "nearest-neighbour kernel failed: %s", cudaGetErrorString(le));
+    if (cost) *cost = (double)c;
+    return TSPB200_OK;
+}
+
+int tspb200_tour_costs(tspb200_ctx *ctx, const int32_t *tours, int batch, int as_order, double *out) {
+    if (!ctx || !ctx->stream) return fail(ctx, TSPB200_E_CUDA, "context has no CUDA device");
+    if (ctx->n < 1) return fail(ctx, TSPB200_E_STATE, "no instance");
+    if (!tours || !out || batch < 1) return fail(ctx, TSPB200_E_ARG, "bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    const int n = ctx->n;
+    int path = select_path(ctx);
+    if (path == 2 && !ctx->d_mat) path = 1;
+    InstDev I = inst_for_path(ctx, path == 2 ? 2 : 1);
+    int *d_t = nullptr;
+    long long *d_o = nullptr;
+    CK(cudaMalloc(&d_t, sizeof(int) * (size_t)n * batch));
+    CK(cudaMalloc(&d_o, sizeof(long long) * (size_t)batch));
+    CK(cudaMemcpyAsync(d_t, tours, sizeof(int) * (size_t)n * batch, cudaMemcpyHostToDevice, ctx->stream));
+    cudaError_t le = launch_tour_cost(I, d_t, as_order, d_o, batch, ctx->stream);
+    std::vector<long long> h((size_t)batch);
+    if (le == cudaSuccess) le = cudaMemcpyAsync(h.data(), d_o, sizeof(long long) * (size_t)batch, cudaMemcpyDeviceToHost, ctx->stream);
+    if (le == cudaSuccess) le = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_t); cudaFree(d_o);
+    if (le != cudaSuccess) return fail(ctx, TSPB200_E_CUDA, "tour cost kernel failed: %s", cudaGetErrorString(le));
+    for (int b = 0; b < batch; ++b) out[b] = (double)h[b];
+    return TSPB200_OK;
+}
+
+// ---- multi-GPU -------------------------------------------------------------------------------------------
+int tspb200_comm_unique_id(void *id128) {
+    std::string err;
+    if (!id128) return TSPB200_E_ARG;
+    if (!g_nccl.load(err)) { fprintf(stderr, "tspb200: %s\n", err.c_str()); return TSPB200_E_NCCL; }
+    nccl_unique_id id;
+    if (g_nccl.GetUniqueId(&id) != 0) return TSPB200_E_NCCL;
+    memcpy(id128, &id, sizeof id);
+    return TSPB200_OK;
+}
+
+int tspb200_comm_init(tspb200_ctx *ctx, const void *id128, int rank, int world) {
+    if (!ctx || !ctx->stream) return fail(ctx, TSPB200_E_CUDA, "context has no CUDA device");
+    if (!id128 || world < 1 || rank < 0 || rank >= world) return fail(ctx, TSPB200_E_ARG, "bad communicator arguments");
+    std::string err;
+    if (!g_nccl.load(err)) return fail(ctx, TSPB200_E_NCCL, "%s", err.c_str());
+    CK(cudaSetDevice(ctx->device));
+    nccl_unique_id id;
+    memcpy(&id, id128, sizeof id);
+    if (ctx->comm) { g_nccl.CommDestroy(ctx->comm); ctx->comm = nullptr; }
+    int nr = g_nccl.CommInitRank(&ctx->comm, world, id, rank);
+    if (nr != 0) return fail(ctx, TSPB200_E_NCCL, "ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(nr) : "?");
+    ctx->rank = rank;
+    ctx->world = world;
+    ctx->has_tour = false;  // tile plan depends on the world size
+    return TSPB200_OK;
+}
+
+int tspb200_comm_destroy(tspb200_ctx *ctx) {
+    if (!ctx) return TSPB200_E_ARG;
+    if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
+    ctx->comm = nullptr;
+    ctx->rank = 0;
+    ctx->world = 1;
+    ctx->has_tour = false;
+    return TSPB200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,264 @@
+// kernels_misc.cu — instance set-up, distance matrix, tour state build/export, tour costs, and the
+// nearest-neighbour construction.
+#include "tsp_state.cuh"
+
+namespace tspb {
+
+// ---- instance tables -----------------------------------------------------------------------------------
+// pt64[k] = raw point, or for GEO the (lat, lon) radians of reference src/distutil.c:51-58; pt32 = FP32 copy.
+__global__ void prep_points_kernel(const double2 *raw, double2 *pt64, float2 *pt32, int n, int metric) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    double2 p = raw[k];
+    pt32[k] = make_float2((float)p.x, (float)p.y);
+    if (metric == M_GEO) p = make_double2(geo_radians(p.x), geo_radians(p.y));
+    pt64[k] = p;
+}
+
+cudaError_t launch_prep_points(const double2 *raw, double2 *pt64, float2 *pt32, int n, int metric, cudaStream_t st) {
+    prep_points_kernel<<<(n + 255) / 256, 256, 0, st>>>(raw, pt64, pt32, n, metric);
+    return cudaGetLastError();
+}
+
+// ---- distance matrix --------------------------------------------------------------------------------------
+// out[i*ld + j] = (int32) calc_dist(i, j)  (reference src/distutil.c:73-92), ld % 4 == 0 so that every row
+// starts 16-byte aligned.  One thread = 4 consecutive j of ROWS_PER_BLOCK rows -> one st.global.v4.s32 per row;
+// a warp writes 512 contiguous bytes.  HBM-store-bound: 4*n*ld bytes written, O(n) read.
+// FAST: FP32 distance with a guard band around the rounding boundary; inside the band (or when the
+// instance is not FP32-safe) the entry is recomputed in FP64 with the reference's exact operation order.
+constexpr int MAT_THREADS = 256;
+constexpr int MAT_ROWS = 16;
+
+template <bool FAST>
+__global__ void __launch_bounds__(MAT_THREADS) dist_matrix_kernel(const InstDev I, int *__restrict__ out, long long ld,
+                                                                  int row_begin, int row_end) {
+    const int n = I.n;
+    const int j4 = (blockIdx.x * MAT_THREADS + threadIdx.x) * 4;
+    if (j4 >= n) return;
+    const int r0 = row_begin + blockIdx.y * MAT_ROWS;
+    const int r1 = min(r0 + MAT_ROWS, row_end);
+    const int metric = I.metric;
+    float cx[4], cy[4];
+    int jj[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        jj[c] = min(j4 + c, n - 1);
+        if (FAST) {
+            float2 p = I.pt32[jj[c]];
+            cx[c] = p.x;
+            cy[c] = p.y;
+        }
+    }
+    for (int i = r0; i < r1; ++i) {
+        int v[4];
+        if (FAST) {
+            const float2 pi = I.pt32[i];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                float dx = pi.x - cx[c], dy = pi.y - cy[c];
+                float s = fmaf(dy, dy, dx * dx);
+                if (metric == M_ATT) s *= 0.1f;
+                float r = sqrt_approx(s);
+                float k = (r + 12582912.0f) - 12582912.0f;  // nearest integer (ties irrelevant: they are in the band)
+                float frac = r - k;                          // in [-0.5, 0.5]
+                float band = fmaf(r, I.band, 1e-6f);
+                bool unsafe;
+                int val;
+                if (metric == M_EUC_2D || (metric != M_CEIL_2D && metric != M_ATT)) {
+                    // nint: boundary at k +- 0.5
+                    unsafe = (0.5f - fabsf(frac)) <= band;
+                    val = (int)k;
+                } else {
+                    // ceil (CEIL_2D, and ATT == ceil of r for non-integers, r itself for integers): boundary at integers
+                    unsafe = fabsf(frac) <= band;
+                    val = (int)k + (frac > 0.f ? 1 : 0);
+                }
+                if (unsafe) val = (int)exact_dist(metric, I.pt64[i], I.pt64[jj[c]]);
+                v[c] = val;
+            }
+        } else {
+            const double2 pi = I.pt64[i];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) v[c] = (int)exact_dist(metric, pi, I.pt64[jj[c]]);
+        }
+        *reinterpret_cast<int4 *>(out + (long long)(i - row_begin) * ld + j4) = make_int4(v[0], v[1], v[2], v[3]);
+    }
+}
+
+cudaError_t launch_dist_matrix(const InstDev &I, int *out, long long ld, int row_begin, int row_end, bool fast,
+                               cudaStream_t st) {
+    int rows = row_end - row_begin;
+    if (rows <= 0) return cudaSuccess;
+    dim3 grid((unsigned)((I.n + MAT_THREADS * 4 - 1) / (MAT_THREADS * 4)), (unsigned)((rows + MAT_ROWS - 1) / MAT_ROWS));
+    if (fast) dist_matrix_kernel<true><<<grid, MAT_THREADS, 0, st>>>(I, out, ld, row_begin, row_end);
+    else dist_matrix_kernel<false><<<grid, MAT_THREADS, 0, st>>>(I, out, ld, row_begin, row_end);
+    return cudaGetLastError();
+}
+
+// ---- tour state ------------------------------------------------------------------------------------------
+// order[p] = node at position p (host walks succ[] from node 0).  Builds both views + padding.
+__global__ void build_state_kernel(const InstDev I, const TourDev T, const int *order) {
+    const int n = T.n;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < T.alloc; p += gridDim.x * blockDim.x) {
+        if (p < n) {
+            int u = order[p];
+            int v = order[p + 1 == n ? 0 : p + 1];
+            float2 c = I.pt32[u];
+            float ds = (float)dist_nodes(I, u, v);
+            T.rec[p] = make_float4(c.x, c.y, ds, __int_as_float(u));
+            T.pos[u] = p;
+            if (T.nrec) {
+                float2 cn = I.pt32[v];
+                T.nrec[u] = make_float4(c.x, c.y, cn.x, cn.y);
+                T.nds[u] = ds;
+                T.nsucc[u] = v;
+            }
+        } else if (p == n) {
+            int u = order[0];
+            float2 c = I.pt32[u];
+            T.rec[p] = make_float4(c.x, c.y, -TSPB_BIG, __int_as_float(u));
+        } else {
+            T.rec[p] = make_float4(0.f, 0.f, -TSPB_BIG, __int_as_float(0));
+        }
+    }
+}
+
+// succ[node(p)] = node(p+1); cost = sum of ds (exact integers) accumulated in a 64-bit counter.
+__global__ void export_state_kernel(const TourDev T, int *succ, unsigned long long *cost) {
+    const int n = T.n;
+    unsigned long long local = 0;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+        float4 r = T.rec[p];
+        int pn = p + 1 == n ? 0 : p + 1;
+        succ[node_of(r)] = node_of(T.rec[pn]);
+        local += (unsigned long long)(long long)r.z;
+    }
+    for (int m = 16; m > 0; m >>= 1) local += __shfl_xor_sync(0xffffffffu, local, m);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(cost, local);
+}
+
+cudaError_t launch_build_state(const InstDev &I, const TourDev &T, const int *order, cudaStream_t st) {
+    int grid = (T.alloc + 255) / 256;
+    if (grid > 1184) grid = 1184;
+    build_state_kernel<<<grid, 256, 0, st>>>(I, T, order);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_export_state(const TourDev &T, int *succ, unsigned long long *cost, cudaStream_t st) {
+    int grid = (T.n + 255) / 256;
+    if (grid > 1184) grid = 1184;
+    export_state_kernel<<<grid, 256, 0, st>>>(T, succ, cost);
+    return cudaGetLastError();
+}
+
+// ---- batched tour cost (reference src/genetic.c:51-60 fitness; src/tabusearch.c:168-172) -----------------
+// tours[b*n + k]: as_order != 0 -> visiting order (chromosome), else successor array. One block per tour.
+__global__ void __launch_bounds__(256) tour_cost_kernel(const InstDev I, const int *tours, int as_order, long long *out) {
+    __shared__ long long s_part[8];
+    const int n = I.n;
+    const int *t = tours + (long long)blockIdx.x * n;
+    long long local = 0;
+    for (int k = threadIdx.x; k < n; k += 256) {
+        int u, v;
+        if (as_order) { u = t[k]; v = t[k + 1 == n ? 0 : k + 1]; }
+        else { u = k; v = t[k]; }
+        local += dist_nodes(I, u, v);
+    }
+    for (int m = 16; m > 0; m >>= 1) local += __shfl_xor_sync(0xffffffffu, local, m);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = local;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long s = 0;
+        for (int w = 0; w < 8; ++w) s += s_part[w];
+        out[blockIdx.x] = s;
+    }
+}
+
+cudaError_t launch_tour_cost(const InstDev &I, const int *tours, int as_order, long long *out, int batch, cudaStream_t st) {
+    tour_cost_kernel<<<batch, 256, 0, st>>>(I, tours, as_order, out);
+    return cudaGetLastError();
+}
+
+// ---- nearest-neighbour construction (reference src/heuristics.c:18-78 greedy) --------------------------
+// n-1 dependent steps, each an argmin over the unvisited nodes with strict '<' (lowest index wins ties).
+// One cooperative launch of a persistent grid would need grid-wide syncs; instead a single CLUSTER-free
+// design: one block of 1024 threads per step-chain is latency-bound, so we run the whole chain inside ONE
+// kernel with a grid barrier built from a monotonically increasing counter (all blocks are co-resident:
+// the launcher sizes the grid to at most one block per SM).
+// Distances are exact FP64 (or matrix lookups): n^2 evaluations in total are negligible next to 2-opt.
+
+__device__ __forceinline__ void grid_barrier(unsigned *counter, unsigned target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1u);
+        while (*((volatile unsigned *)counter) < target) { }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) nn_tour_kernel(const NnArgs A) {
+    __shared__ unsigned long long s_best[8];
+    const InstDev &I = A.inst;
+    const int n = I.n;
+    const int gsz = gridDim.x * blockDim.x;
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    int cur = A.start;
+    long long total = 0;
+    unsigned epoch = 0;
+    if (gtid == 0) A.visited[cur] = 1;
+    grid_barrier(A.barrier, (++epoch) * gridDim.x);
+    for (int step = 0; step < n - 1; ++step) {
+        unsigned long long *slot = &A.slots[step & 1];
+        unsigned long long best = ~0ull;
+        const double2 pc = I.dmat ? make_double2(0, 0) : I.pt64[cur];
+        for (int k = gtid; k < n; k += gsz) {
+            if (k == cur || ((volatile unsigned char *)A.visited)[k]) continue;
+            long long d = I.dmat ? (long long)I.dmat[(long long)cur * I.dmat_ld + k] : exact_dist(I.metric, pc, I.pt64[k]);
+            unsigned long long key = ((unsigned long long)d << 32) | (unsigned)k;
+            best = key < best ? key : best;
+        }
+        for (int m = 16; m > 0; m >>= 1) {
+            unsigned long long o = __shfl_xor_sync(0xffffffffu, best, m);
+            best = o < best ? o : best;
+        }
+        if ((threadIdx.x & 31) == 0) s_best[threadIdx.x >> 5] = best;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < 8; ++w) best = s_best[w] < best ? s_best[w] : best;
+            if (best != ~0ull) atomicMin(slot, best);
+        }
+        grid_barrier(A.barrier, (++epoch) * gridDim.x);
+        const unsigned long long win = *((volatile unsigned long long *)slot);
+        const int nxt = (int)(win & 0xffffffffu);
+        total += (long long)(win >> 32);
+        if (gtid == 0) {
+            A.succ[cur] = nxt;
+            A.visited[nxt] = 1;
+            A.slots[(step + 1) & 1] = ~0ull;  // reset the other slot for the next step
+        }
+        cur = nxt;
+        grid_barrier(A.barrier, (++epoch) * gridDim.x);
+    }
+    if (gtid == 0) {
+        A.succ[cur] = A.start;  // closing edge, reference heuristics.c:59-62,74
+        total += dist_nodes(I, cur, A.start);
+        *A.cost = total;
+    }
+}
+
+// The grid barrier needs every block resident at once: cooperative launch, grid <= SMs * occupancy.
+int nn_max_grid(int num_sms) {
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, nn_tour_kernel, 256, 0) != cudaSuccess || occ < 1) return num_sms;
+    return num_sms;  // one block per SM keeps the barrier cheap
+}
+
+cudaError_t launch_nn_tour(const NnArgs &a, int grid, cudaStream_t st) {
+    NnArgs args = a;
+    void *params[] = {&args};
+    return cudaLaunchCooperativeKernel((const void *)nn_tour_kernel, dim3(grid), dim3(256), params, 0, st);
+}
+
+}  // namespace tspb

@@ -1,0 +1,285 @@
+"""ctypes binding of libtspb200.so (include/tspb200.h) — the host-side mirror of the reference's hot-path
+interface for Python callers (tests, bench, the torch.distributed bootstrap).
+
+The reference is a C program whose 2-opt / distance entry points take an ``instance*``
+(reference include/heuristics.h:82 ``alg_2opt``, src/tabusearch.c:107 ``alg_2opt_tabu``,
+include/distutil.h:137 ``calc_dist``); ``Engine`` exposes the same operations on numpy arrays:
+``xy`` = the instance's ``point[]`` (n x 2 float64), ``succ`` = ``solution.edges[k].j``.
+
+There is no CPU fallback: if the CUDA library is missing, cannot be loaded, or no GPU is present,
+construction raises ``TspB200Error``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libtspb200.so")
+DROPIN_PATH = os.path.join(_HERE, "lib", "libtspb200_dropin.so")
+
+EUC_2D, MAX_2D, MAN_2D, CEIL_2D, GEO, ATT = 0, 1, 2, 3, 4, 5
+FI, BI = 0, 1
+LOCAL_OPTIMUM, TIME_LIMIT_EXCEEDED, STOPPED_BY_CAP = 0, 2, 3
+
+#: every symbol include/tspb200.h declares (checked by tests/test_abi.py)
+ABI_SYMBOLS = [
+    "tspb200_create", "tspb200_destroy", "tspb200_last_error", "tspb200_set_option", "tspb200_get_info",
+    "tspb200_set_instance", "tspb200_dist_matrix_build", "tspb200_dist_matrix_get", "tspb200_dist_matrix",
+    "tspb200_dist_matrix_free", "tspb200_tour_upload", "tspb200_tour_download", "tspb200_tour_log",
+    "tspb200_bi_run", "tspb200_fi_run", "tspb200_two_opt", "tspb200_two_opt_batch", "tspb200_nn_tour",
+    "tspb200_tour_costs", "tspb200_comm_unique_id", "tspb200_comm_init", "tspb200_comm_destroy",
+    "tspb200_debug_tile_plan",
+]
+
+
+class TspB200Error(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"tspb200 error {code}: {msg}")
+        self.code = code
+
+
+class _Stats(C.Structure):
+    _fields_ = [("passes", C.c_int64), ("moves", C.c_int64), ("evals", C.c_int64), ("launches", C.c_int64),
+                ("obj_delta", C.c_int64), ("gpu_ms", C.c_double), ("cost", C.c_double), ("status", C.c_int32),
+                ("path", C.c_int32)]
+
+
+class _Move(C.Structure):
+    _fields_ = [("i", C.c_int32), ("j", C.c_int32), ("delta", C.c_int64)]
+
+
+@dataclass
+class Stats:
+    passes: int
+    moves: int
+    evals: int
+    launches: int
+    obj_delta: int
+    gpu_ms: float
+    cost: float
+    status: int
+    path: int
+
+    @staticmethod
+    def of(s: _Stats) -> "Stats":
+        return Stats(s.passes, s.moves, s.evals, s.launches, s.obj_delta, s.gpu_ms, s.cost, s.status, s.path)
+
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """Load libtspb200.so (built in-tree by ``__graft_entry__.build()`` / ``make -C tsp_optimization_b200/csrc``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise TspB200Error(-1, f"{LIB_PATH} is missing: build it with `make -C tsp_optimization_b200/csrc` "
+                               "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, i64, i32p = C.c_void_p, C.c_int64, C.POINTER(C.c_int32)
+    L.tspb200_create.argtypes = [C.c_int, C.POINTER(vp)]
+    L.tspb200_destroy.argtypes = [vp]
+    L.tspb200_destroy.restype = None
+    L.tspb200_last_error.argtypes = [vp]
+    L.tspb200_last_error.restype = C.c_char_p
+    L.tspb200_set_option.argtypes = [vp, C.c_char_p, i64]
+    L.tspb200_get_info.argtypes = [vp, C.c_char_p]
+    L.tspb200_get_info.restype = i64
+    L.tspb200_set_instance.argtypes = [vp, C.c_void_p, C.c_int, C.c_int]
+    L.tspb200_dist_matrix_build.argtypes = [vp, C.POINTER(C.c_double)]
+    L.tspb200_dist_matrix_get.argtypes = [vp, C.c_void_p]
+    L.tspb200_dist_matrix.argtypes = [vp, C.c_void_p]
+    L.tspb200_dist_matrix_free.argtypes = [vp]
+    L.tspb200_tour_upload.argtypes = [vp, C.c_void_p, i64]
+    L.tspb200_tour_download.argtypes = [vp, C.c_void_p, C.POINTER(C.c_double)]
+    L.tspb200_tour_log.argtypes = [vp, C.c_void_p, i64, C.POINTER(i64)]
+    L.tspb200_bi_run.argtypes = [vp, i64, C.POINTER(_Stats)]
+    L.tspb200_fi_run.argtypes = [vp, i64, C.POINTER(_Stats)]
+    L.tspb200_two_opt.argtypes = [vp, C.c_int, C.c_void_p, C.POINTER(C.c_double), i64, C.POINTER(_Stats),
+                                  C.c_void_p, i64, C.POINTER(i64)]
+    L.tspb200_two_opt_batch.argtypes = [vp, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(_Stats)]
+    L.tspb200_nn_tour.argtypes = [vp, C.c_int, C.c_void_p, C.POINTER(C.c_double)]
+    L.tspb200_tour_costs.argtypes = [vp, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    L.tspb200_comm_unique_id.argtypes = [C.c_void_p]
+    L.tspb200_comm_init.argtypes = [vp, C.c_void_p, C.c_int, C.c_int]
+    L.tspb200_comm_destroy.argtypes = [vp]
+    L.tspb200_debug_tile_plan.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, i32p, i32p, C.c_void_p,
+                                          C.c_void_p, C.c_int, i32p]
+    _lib = L
+    return L
+
+
+def tile_plan(n: int, rows_per_thread: int = 0, tile_cols: int = 0, slots: int = 296, world: int = 1):
+    """Host-only: the BI tile plan -> (R, TJ, row_start[ntr+1], row_j0[ntr]). Needs no GPU."""
+    L = load_library()
+    cap = n // 256 + 8
+    rs = np.zeros(cap, dtype=np.int32)
+    rj = np.zeros(cap, dtype=np.int32)
+    r, tj, ntr = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+    rc = L.tspb200_debug_tile_plan(n, rows_per_thread, tile_cols, slots, world, C.byref(r), C.byref(tj),
+                                   rs.ctypes.data, rj.ctypes.data, cap, C.byref(ntr))
+    if rc:
+        raise TspB200Error(rc, "tile plan failed")
+    return r.value, tj.value, rs[:ntr.value + 1].copy(), rj[:ntr.value].copy()
+
+
+def key_pack(delta: int, i: int, j: int) -> int:
+    """Python mirror of key_pack() in csrc/tsp_device.cuh (the 8-byte payload of the NCCL min-allreduce)."""
+    return ((delta + (1 << 29)) << 34) | (i << 17) | j
+
+
+def key_unpack(p: int):
+    return (p >> 34) - (1 << 29), (p >> 17) & 0x1FFFF, p & 0x1FFFF
+
+
+def _moves_to_array(buf, k: int) -> np.ndarray:
+    out = np.zeros((k, 3), dtype=np.int64)
+    for t in range(k):
+        out[t] = (buf[t].i, buf[t].j, buf[t].delta)
+    return out
+
+
+class Engine:
+    """One engine = one CUDA device + stream; holds one instance and one resident tour."""
+
+    def __init__(self, device: int = 0):
+        self.L = load_library()
+        self.h = C.c_void_p()
+        rc = self.L.tspb200_create(device, C.byref(self.h))
+        if rc:
+            msg = self.L.tspb200_last_error(self.h).decode() if self.h else "create failed"
+            if self.h:
+                self.L.tspb200_destroy(self.h)
+                self.h = C.c_void_p()
+            raise TspB200Error(rc, msg)
+        self.n = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.tspb200_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc: int):
+        if rc:
+            raise TspB200Error(rc, self.L.tspb200_last_error(self.h).decode())
+
+    # -- options / info
+    def set_option(self, key: str, value: int):
+        self._ck(self.L.tspb200_set_option(self.h, key.encode(), int(value)))
+
+    def info(self, key: str) -> int:
+        return int(self.L.tspb200_get_info(self.h, key.encode()))
+
+    # -- instance
+    def set_instance(self, xy, weight_type: int):
+        xy = np.ascontiguousarray(xy, dtype=np.float64).reshape(-1, 2)
+        self._ck(self.L.tspb200_set_instance(self.h, xy.ctypes.data, len(xy), int(weight_type)))
+        self.n = len(xy)
+
+    # -- distance matrix (reference calc_dist for all pairs)
+    def dist_matrix(self) -> np.ndarray:
+        out = np.empty((self.n, self.n), dtype=np.int32)
+        self._ck(self.L.tspb200_dist_matrix(self.h, out.ctypes.data))
+        return out
+
+    def dist_matrix_build(self) -> float:
+        ms = C.c_double(0)
+        self._ck(self.L.tspb200_dist_matrix_build(self.h, C.byref(ms)))
+        return ms.value
+
+    def dist_matrix_get(self) -> np.ndarray:
+        out = np.empty((self.n, self.n), dtype=np.int32)
+        self._ck(self.L.tspb200_dist_matrix_get(self.h, out.ctypes.data))
+        return out
+
+    def dist_matrix_free(self):
+        self._ck(self.L.tspb200_dist_matrix_free(self.h))
+
+    # -- resident tour
+    def tour_upload(self, succ, log_cap: int = 0):
+        succ = np.ascontiguousarray(succ, dtype=np.int32)
+        assert succ.shape == (self.n,)
+        self._ck(self.L.tspb200_tour_upload(self.h, succ.ctypes.data, int(log_cap)))
+
+    def tour_download(self):
+        succ = np.empty(self.n, dtype=np.int32)
+        cost = C.c_double(0)
+        self._ck(self.L.tspb200_tour_download(self.h, succ.ctypes.data, C.byref(cost)))
+        return succ, cost.value
+
+    def tour_log(self, cap: int) -> np.ndarray:
+        buf = (_Move * max(1, cap))()
+        cnt = C.c_int64(0)
+        self._ck(self.L.tspb200_tour_log(self.h, C.cast(buf, C.c_void_p), cap, C.byref(cnt)))
+        return _moves_to_array(buf, min(cap, cnt.value))
+
+    def bi_run(self, max_passes: int = -1) -> Stats:
+        st = _Stats()
+        self._ck(self.L.tspb200_bi_run(self.h, int(max_passes), C.byref(st)))
+        return Stats.of(st)
+
+    def fi_run(self, max_moves: int = -1) -> Stats:
+        st = _Stats()
+        self._ck(self.L.tspb200_fi_run(self.h, int(max_moves), C.byref(st)))
+        return Stats.of(st)
+
+    # -- host-buffer entry points (mirror alg_2opt / alg_2opt_tabu on an instance)
+    def two_opt(self, mode: int, succ, obj: float = 0.0, max_iters: int = -1, log_cap: int = 0):
+        """Returns (succ, obj, Stats, log[k,3]) — FI == reference alg_2opt, BI == alg_2opt_tabu(NULL list)."""
+        succ = np.array(succ, dtype=np.int32, copy=True)
+        o = C.c_double(obj)
+        st = _Stats()
+        buf = (_Move * max(1, log_cap))()
+        cnt = C.c_int64(0)
+        self._ck(self.L.tspb200_two_opt(self.h, mode, succ.ctypes.data, C.byref(o), int(max_iters), C.byref(st),
+                                        C.cast(buf, C.c_void_p) if log_cap else None, log_cap, C.byref(cnt)))
+        return succ, o.value, Stats.of(st), _moves_to_array(buf, min(log_cap, cnt.value))
+
+    def two_opt_batch(self, mode: int, succ_batch, obj=None):
+        succ_batch = np.array(succ_batch, dtype=np.int32, copy=True)
+        b = succ_batch.shape[0]
+        assert succ_batch.shape == (b, self.n)
+        o = np.zeros(b, dtype=np.float64) if obj is None else np.array(obj, dtype=np.float64, copy=True)
+        st = _Stats()
+        self._ck(self.L.tspb200_two_opt_batch(self.h, mode, succ_batch.ctypes.data, o.ctypes.data, b, C.byref(st)))
+        return succ_batch, o, Stats.of(st)
+
+    def nn_tour(self, start: int = 0):
+        succ = np.empty(self.n, dtype=np.int32)
+        cost = C.c_double(0)
+        self._ck(self.L.tspb200_nn_tour(self.h, start, succ.ctypes.data, C.byref(cost)))
+        return succ, cost.value
+
+    def tour_costs(self, tours, as_order: bool) -> np.ndarray:
+        tours = np.ascontiguousarray(tours, dtype=np.int32).reshape(-1, self.n)
+        out = np.empty(len(tours), dtype=np.float64)
+        self._ck(self.L.tspb200_tour_costs(self.h, tours.ctypes.data, len(tours), 1 if as_order else 0, out.ctypes.data))
+        return out
+
+    # -- multi-GPU
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        L = load_library()
+        buf = C.create_string_buffer(128)
+        rc = L.tspb200_comm_unique_id(buf)
+        if rc:
+            raise TspB200Error(rc, "ncclGetUniqueId failed (is libnccl.so.2 loadable?)")
+        return buf.raw
+
+    def comm_init(self, uid: bytes, rank: int, world: int):
+        assert len(uid) == 128
+        self._ck(self.L.tspb200_comm_init(self.h, uid, rank, world))
+
+    def comm_destroy(self):
+        self._ck(self.L.tspb200_comm_destroy(self.h))

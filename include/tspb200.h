@@ -83,7 +83,7 @@ typedef struct {
 int tspb200_create(int device, tspb200_ctx **out);
 void tspb200_destroy(tspb200_ctx *ctx);
 const char *tspb200_last_error(const tspb200_ctx *ctx);
-/* Tuning / mode knobs. keys: "rows_per_thread" (2|4|8), "tile_cols" (even, 32..1024), "grid" (blocks),
+/* Tuning / mode knobs. keys: "rows_per_thread" (2|4|8|16), "tile_cols" (multiple of 4, 32..1024), "grid" (blocks),
  * "force_path" (-1 auto, 0 fp32 filter, 1 exact on the fly, 2 matrix), "batch" (passes per host sync),
  * "time_limit_ms" (<=0 unlimited; checked between launch batches). */
 int tspb200_set_option(tspb200_ctx *ctx, const char *key, int64_t value);

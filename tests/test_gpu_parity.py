@@ -228,7 +228,7 @@ def test_fi_reference_csv_goldens(engine, instances, goldens, oracle):
         assert sha(s) == g["fi_sha256"] and st.moves == g["fi_moves"] and st.passes == g["fi_sweeps"], nm
 
 
-@pytest.mark.parametrize("R,TJ", [(2, 32), (2, 64), (4, 64), (8, 128), (8, 256), (4, 34)])
+@pytest.mark.parametrize("R,TJ", [(2, 32), (2, 64), (4, 64), (8, 128), (8, 256), (4, 36), (16, 64)])
 def test_bi_tile_shapes(engine, oracle, R, TJ):
     xy = uniform_instance(1500)
     succ, _ = oracle.nn_tour(xy, 0, 0)

@@ -1,0 +1,25 @@
+"""GPU tuning sweep (dev tool): BI pass throughput vs tile shape / grid."""
+import sys, time, json
+import numpy as np
+from tsp_optimization_b200 import Engine, BI
+from tsp_optimization_b200.instances import uniform_instance
+
+def main():
+    ns = [int(x) for x in sys.argv[1].split(",")] if len(sys.argv) > 1 else [100000]
+    eng = Engine(0)
+    for n in ns:
+        xy = uniform_instance(n)
+        eng.set_instance(xy, 0)
+        succ, _ = eng.nn_tour(0)
+        pairs = n * (n - 3) // 2
+        for R in (8, 4):
+            for TJ in (64, 128, 256):
+                for grid in (296,):
+                    eng.set_option("rows_per_thread", R); eng.set_option("tile_cols", TJ); eng.set_option("grid", grid)
+                    eng.tour_upload(succ)
+                    eng.bi_run(3)
+                    k = 20 if n >= 50000 else 100
+                    st = eng.bi_run(k)
+                    print(json.dumps({"n": n, "R": R, "TJ": TJ, "grid": grid, "tiles": eng.info("ntiles"),
+                                      "ms_per_pass": st.gpu_ms / st.passes, "Gevals_s": st.passes * pairs / st.gpu_ms / 1e6}), flush=True)
+main()

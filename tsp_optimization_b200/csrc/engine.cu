@@ -22,7 +22,9 @@ namespace tspb {
 cudaError_t launch_bi_scan(const BiArgs &a, int rows_per_thread, int grid, cudaStream_t st);
 cudaError_t launch_bi_scan_exact(const InstDev &inst, const TourDev &tour, int rank, int world, int fuse_apply, int grid,
                                  cudaStream_t st);
-cudaError_t launch_bi_apply_packed(const InstDev &inst, const TourDev &tour, cudaStream_t st);
+cudaError_t launch_bi_decode_packed(const TourDev &tour, cudaStream_t st);
+cudaError_t launch_apply_move(const InstDev &inst, const TourDev &tour, int num_sms, cudaStream_t st);
+cudaError_t launch_refresh_node_space(const TourDev &tour, int num_sms, cudaStream_t st);
 cudaError_t launch_fi_search(const InstDev &I, const TourDev &T, int grid, cudaStream_t st);
 cudaError_t launch_dist_matrix(const InstDev &I, int *out, long long ld, int row_begin, int row_end, bool fast,
                                cudaStream_t st);
@@ -192,10 +194,10 @@ int tspb200_set_option(tspb200_ctx *ctx, const char *key, int64_t value) {
     if (!ctx || !key) return TSPB200_E_ARG;
     std::string k(key);
     if (k == "rows_per_thread") {
-        if (value != 0 && value != 2 && value != 4 && value != 8) return fail(ctx, TSPB200_E_ARG, "rows_per_thread must be 0 (auto), 2, 4 or 8");
+        if (value != 0 && value != 2 && value != 4 && value != 8 && value != 16) return fail(ctx, TSPB200_E_ARG, "rows_per_thread must be 0 (auto), 2, 4, 8 or 16");
         ctx->opt_R = (int)value;
     } else if (k == "tile_cols") {
-        if (value != 0 && (value < 32 || value > 1024 || (value & 1))) return fail(ctx, TSPB200_E_ARG, "tile_cols must be 0 (auto) or even in [32,1024]");
+        if (value != 0 && (value < 32 || value > 1024 || (value & 3))) return fail(ctx, TSPB200_E_ARG, "tile_cols must be 0 (auto) or a multiple of 4 in [32,1024]");
         ctx->opt_TJ = (int)value;
     } else if (k == "grid") {
         ctx->opt_grid = (int)value;
@@ -569,9 +571,11 @@ int tspb200_bi_run(tspb200_ctx *ctx, int64_t max_passes, tspb200_stats *st) {
                 unsigned long long *p = &ctx->d_ctl->packed;
                 int nr = g_nccl.AllReduce(p, p, 1, NCCL_UINT64, NCCL_MIN, ctx->comm, ctx->stream);
                 if (nr != 0) return fail(ctx, TSPB200_E_NCCL, "ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(nr) : "?");
-                CK(launch_bi_apply_packed(I, ctx->tour, ctx->stream));
+                CK(launch_bi_decode_packed(ctx->tour, ctx->stream));
                 host_launches++;
             }
+            CK(launch_apply_move(I, ctx->tour, ctx->num_sms, ctx->stream));
+            host_launches++;
         }
         if (max_passes >= 0) remaining -= k;
         rc = sync_ctl(ctx);
@@ -591,7 +595,7 @@ int tspb200_bi_run(tspb200_ctx *ctx, int64_t max_passes, tspb200_stats *st) {
         st->passes = ctx->h_ctl->passes - passes0;
         st->moves = ctx->h_ctl->moves - moves0;
         st->evals = st->passes * ((long long)n * (n - 3) / 2);
-        st->launches = ctx->world > 1 ? host_launches : (ctx->h_ctl->launches - launches0);
+        st->launches = host_launches;
         st->obj_delta = ctx->h_ctl->obj_delta - delta0;
         st->gpu_ms = ms;
         st->status = done ? TSPB200_LOCAL_OPTIMUM : status;
@@ -623,6 +627,7 @@ int tspb200_fi_run(tspb200_ctx *ctx, int64_t max_moves, tspb200_stats *st) {
     int grid = ctx->opt_grid > 0 ? ctx->opt_grid : 2 * ctx->num_sms;
     if (grid > n - 1) grid = n - 1;
     long long batch = ctx->opt_batch > 0 ? ctx->opt_batch : 128;
+    long long host_launches = 0;
     int status = TSPB200_LOCAL_OPTIMUM;
     auto t_start = std::chrono::steady_clock::now();
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
@@ -633,7 +638,12 @@ int tspb200_fi_run(tspb200_ctx *ctx, int64_t max_moves, tspb200_stats *st) {
         int zero = 0;
         if (ctx->h_ctl->done && cap != -1 && ctx->h_ctl->moves < cap) CK(cudaMemcpyAsync(&ctx->d_ctl->done, &zero, sizeof zero, cudaMemcpyHostToDevice, ctx->stream));
         while (!done) {
-            for (long long q = 0; q < batch; ++q) CK(launch_fi_search(I, ctx->tour, grid, ctx->stream));
+            for (long long q = 0; q < batch; ++q) {
+                CK(launch_fi_search(I, ctx->tour, grid, ctx->stream));
+                CK(launch_apply_move(I, ctx->tour, ctx->num_sms, ctx->stream));
+                CK(launch_refresh_node_space(ctx->tour, ctx->num_sms, ctx->stream));
+                host_launches += 3;
+            }
             rc = sync_ctl(ctx);
             if (rc) return rc;
             done = ctx->h_ctl->done != 0;
@@ -653,7 +663,7 @@ int tspb200_fi_run(tspb200_ctx *ctx, int64_t max_moves, tspb200_stats *st) {
         st->passes = ctx->h_ctl->passes - passes0;
         st->moves = ctx->h_ctl->moves - moves0;
         st->evals = ctx->h_ctl->pairs_swept - swept0;
-        st->launches = ctx->h_ctl->launches - launches0;
+        st->launches = host_launches;
         st->obj_delta = ctx->h_ctl->obj_delta - delta0;
         st->gpu_ms = ms;
         st->status = status;

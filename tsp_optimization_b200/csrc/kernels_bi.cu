@@ -30,50 +30,111 @@ __device__ __forceinline__ float dist32(float ax, float ay, float bx, float by) 
     return sqrt_approx(s);
 }
 
-// Exact re-evaluation of one filtered pair (p,q): returns the reference's integer delta, or LLONG_MAX for
-// pairs the reference skips.  Not inlined: it is the cold path and everything goes in/out by value so that
-// the caller's running best stays in registers.
-#define BI_INVALID 0x7fffffffffffffffll
-template <bool EXACT32>
-__device__ __noinline__ long long bi_exact_delta(const InstDev I, const float4 *rec, int n, int p, int q, float xp,
-                                                 float yp, float xp1, float yp1, float c0x, float c0y, float c0z,
-                                                 float c0w, float c1x, float c1y, float c1w, float ds_p) {
-    if (q < p + 2 || q > n - 1 || (p == 0 && q == n - 1)) return BI_INVALID;  // reference tabusearch.c:134
-    long long d1, d2;
-    if (EXACT32) {
-        d1 = exact_dist(I.metric, make_double2((double)xp, (double)yp), make_double2((double)c0x, (double)c0y));
-        d2 = exact_dist(I.metric, make_double2((double)xp1, (double)yp1), make_double2((double)c1x, (double)c1y));
-    } else {
-        int u = node_of(rec[p]);
-        int u1 = node_of(rec[p + 1]);
-        int v = __float_as_int(c0w);
-        int v1 = __float_as_int(c1w);
-        d1 = exact_dist(I.metric, I.pt64[u], I.pt64[v]);
-        d2 = exact_dist(I.metric, I.pt64[u1], I.pt64[v1]);
-    }
-    return d1 + d2 - (long long)ds_p - (long long)c0z;
+
+// ---- packed FP32x2 arithmetic (sm_100: FADD2 / FMUL2 / FFMA2, one issue slot for two values) --------------
+// Packed values live in 64-bit registers for their whole life so that ptxas keeps them in aligned pairs.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 f2pack(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ float f2lo(f32x2 v) {
+    float lo, hi;
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+    return lo;
+}
+__device__ __forceinline__ float f2hi(f32x2 v) {
+    float lo, hi;
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+    return hi;
+}
+__device__ __forceinline__ f32x2 f2sub(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("sub.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 f2add(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("add.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 f2mul(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("mul.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 f2fma(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
 }
 
-// Inline tail of the cold path: fold an exact delta into the thread's running (delta, i, j) minimum.
-#define BI_CONSIDER(r_, q_)                                                                                       \
-    do {                                                                                                          \
-        long long dl_ = bi_exact_delta<EXACT32>(A.inst, rec, n, p0 + (r_), (q_), xr[r_], yr[r_], xr[(r_) + 1],     \
-                                                yr[(r_) + 1], c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.w, -cp[r_]); \
-        if (dl_ < 0 && dl_ <= (long long)best.delta) {                                                            \
-            int u_ = node_of(rec[p0 + (r_)]);                                                                     \
-            int v_ = __float_as_int(c0.w);                                                                        \
-            MoveKey k_;                                                                                           \
-            k_.delta = (int)dl_; k_.i = min(u_, v_); k_.j = max(u_, v_); k_.pad = 0;                              \
-            if (key_less(k_, best)) {                                                                             \
-                best = k_;                                                                                        \
-                thr = fminf(thr, (float)k_.delta + W);                                                            \
-                atomicMin(&s_hint, k_.delta);                                                                     \
-            }                                                                                                     \
-        }                                                                                                         \
-    } while (0)
+// distances from R+1 consecutive rows to one column point: rows 0..R-1 in R/2 packed pairs, row R scalar
+template <int R, bool ATT>
+__device__ __forceinline__ void column_dists(const f32x2 (&xr2)[R / 2], const f32x2 (&yr2)[R / 2], float xrl, float yrl,
+                                             float cx, float cy, float (&D)[R + 1]) {
+    const f32x2 cxx = f2pack(cx, cx), cyy = f2pack(cy, cy);
+#pragma unroll
+    for (int k = 0; k < R / 2; ++k) {
+        f32x2 dx = f2sub(xr2[k], cxx);
+        f32x2 dy = f2sub(yr2[k], cyy);
+        f32x2 s = f2fma(dy, dy, f2mul(dx, dx));
+        if (ATT) s = f2mul(s, f2pack(0.1f, 0.1f));
+        D[2 * k] = sqrt_approx(f2lo(s));
+        D[2 * k + 1] = sqrt_approx(f2hi(s));
+    }
+    D[R] = dist32<ATT>(xrl, yrl, cx, cy);
+}
+
+// ---- cold path ------------------------------------------------------------------------------------------
+// Exact re-evaluation of the pairs (rows p0..p0+R-1) x (columns Q0+jj0 .. Q0+jj0+ncols-1) of one thread after its
+// FP32 filter fired somewhere in that column block.  Everything is re-read from memory (row records from L2,
+// column records from shared memory), so the hot loop keeps no per-pair state alive for it.  For each pair the
+// FP32 filter is applied again; pairs that pass get the reference's exact integer delta (FP64, reference
+// src/tabusearch.c:150 / src/distutil.c) and are folded into the running (delta, i, j) minimum.
+// Not inlined; the running best goes in and out by value so that it stays in registers in the caller.
+template <bool ATT, bool EXACT32>
+__device__ __noinline__ MoveKey bi_cold_block(const InstDev I, const float4 *rec, const float4 *sc, int n, int p0, int R,
+                                              int Q0, int jj0, int ncols, float thr, MoveKey best) {
+    const float W = I.W;
+    for (int r = 0; r < R; ++r) {
+        const int p = p0 + r;
+        const float4 rp = rec[p], rp1 = rec[p + 1];
+        const float cp = -rp.z;
+        for (int c = 0; c < ncols; ++c) {
+            const int q = Q0 + jj0 + c;
+            if (q < p + 2 || q > n - 1 || (p == 0 && q == n - 1)) continue;  // reference tabusearch.c:134
+            const float4 c0 = sc[jj0 + c], c1 = sc[jj0 + c + 1];
+            const float qv = (dist32<ATT>(rp.x, rp.y, c0.x, c0.y) + cp) + dist32<ATT>(rp1.x, rp1.y, c1.x, c1.y);
+            if (!(qv <= thr + c0.z)) continue;
+            const int u = node_of(rp), v = node_of(c0);
+            long long d1, d2;
+            if (EXACT32) {
+                d1 = exact_dist(I.metric, make_double2((double)rp.x, (double)rp.y), make_double2((double)c0.x, (double)c0.y));
+                d2 = exact_dist(I.metric, make_double2((double)rp1.x, (double)rp1.y), make_double2((double)c1.x, (double)c1.y));
+            } else {
+                d1 = exact_dist(I.metric, I.pt64[u], I.pt64[v]);
+                d2 = exact_dist(I.metric, I.pt64[node_of(rp1)], I.pt64[node_of(c1)]);
+            }
+            const long long delta = d1 + d2 - (long long)rp.z - (long long)c0.z;
+            if (delta < 0 && delta <= (long long)best.delta) {
+                MoveKey k;
+                k.delta = (int)delta; k.i = min(u, v); k.j = max(u, v); k.pad = 0;
+                if (key_less(k, best)) {
+                    best = k;
+                    thr = fminf(thr, (float)k.delta + W);
+                }
+            }
+        }
+    }
+    return best;
+}
+
+constexpr int BI_CB = 4;  // columns per filter check
 
 template <int R, bool ATT, bool EXACT32>
-__global__ void __launch_bounds__(BI_THREADS, 2) bi_scan_kernel(const BiArgs A) {
+__global__ void __launch_bounds__(BI_THREADS, (R >= 16 ? 1 : 2)) bi_scan_kernel(const BiArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long bars[2];
     __shared__ int s_hint;
@@ -81,7 +142,10 @@ __global__ void __launch_bounds__(BI_THREADS, 2) bi_scan_kernel(const BiArgs A) 
     __shared__ MoveKey s_keys[BI_THREADS / 32];
 
     Ctl *ctl = A.tour.ctl;
-    if (ctl->done) return;
+    if (ctl->done) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) ctl->ap_valid = 0;
+        return;
+    }
 
     const int tid = threadIdx.x;
     const int n = A.inst.n;
@@ -143,15 +207,24 @@ __global__ void __launch_bounds__(BI_THREADS, 2) bi_scan_kernel(const BiArgs A) 
             }
         }
 
-        // rows of this thread: p0 .. p0+R-1 (+ successor row p0+R)
+        // rows of this thread: p0 .. p0+R-1 in packed pairs (+ successor row p0+R, scalar)
         const int p0 = P0 + tid * R;
-        float xr[R + 1], yr[R + 1], cp[R];
+        f32x2 xr2[R / 2], yr2[R / 2], cp2[R / 2];
+        float xrl, yrl;
 #pragma unroll
-        for (int r = 0; r <= R; ++r) {
-            float4 v = rec[p0 + r];
-            xr[r] = v.x;
-            yr[r] = v.y;
-            if (r < R) cp[r] = -v.z;  // padding rows carry ds = -BIG -> cp = +BIG -> never a candidate
+        for (int k = 0; k < R / 2; ++k) {
+            float4 v0 = rec[p0 + 2 * k], v1 = rec[p0 + 2 * k + 1];
+            // "+ 0" is a real FADD2 (not an identity for -0.0, so it is never folded): its 64-bit result is an aligned
+            // register pair that stays live across the column loop, instead of being re-packed with MOVs per step
+            const f32x2 zero2 = f2pack(0.f, 0.f);
+            xr2[k] = f2add(f2pack(v0.x, v1.x), zero2);
+            yr2[k] = f2add(f2pack(v0.y, v1.y), zero2);
+            cp2[k] = f2sub(zero2, f2pack(v0.z, v1.z));  // padding rows carry ds = -BIG -> cp = +BIG -> never a candidate
+        }
+        {
+            float4 v = rec[p0 + R];
+            xrl = v.x;
+            yrl = v.y;
         }
         thr = fminf(thr, (float)(*((volatile int *)&s_hint)) + W);
 
@@ -160,66 +233,61 @@ __global__ void __launch_bounds__(BI_THREADS, 2) bi_scan_kernel(const BiArgs A) 
         // pairs with q < p+2 exist in this tile?  (mask them; they are mirrored / adjacent pairs)
         const bool diag = (Q0 < P0 + TI + 1);
         float4 c0 = sc[0];
-        float U[R];
+        f32x2 U2[R / 2];
+        {
+            float D0[R + 1];
+            column_dists<R, ATT>(xr2, yr2, xrl, yrl, c0.x, c0.y, D0);
 #pragma unroll
-        for (int r = 0; r < R; ++r) U[r] = dist32<ATT>(xr[r], yr[r], c0.x, c0.y) + cp[r];
-
-        if (!diag) {
-#pragma unroll 2
-            for (int jj = 0; jj < TJ; ++jj) {
-                const float4 c1 = sc[jj + 1];
-                float Dn[R + 1];
-#pragma unroll
-                for (int r = 0; r <= R; ++r) Dn[r] = dist32<ATT>(xr[r], yr[r], c1.x, c1.y);
-                float Q[R];
-                float m = TSPB_BIG;
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    Q[r] = U[r] + Dn[r + 1];
-                    m = fminf(m, Q[r]);
-                }
-                const float Tq = thr + c0.z;
-                if (m <= Tq) {
-#pragma unroll
-                    for (int r = 0; r < R; ++r)
-                        if (Q[r] <= Tq)
-                            BI_CONSIDER(r, Q0 + jj);
-                }
-#pragma unroll
-                for (int r = 0; r < R; ++r) U[r] = Dn[r] + cp[r];
-                c0 = c1;
-                if ((jj & 63) == 63) thr = fminf(thr, (float)(*((volatile int *)&s_hint)) + W);
-            }
-        } else {
-            const int qrel0 = Q0 - p0;  // q - p0 at jj = 0
-#pragma unroll 2
-            for (int jj = 0; jj < TJ; ++jj) {
-                const float4 c1 = sc[jj + 1];
-                float Dn[R + 1];
-#pragma unroll
-                for (int r = 0; r <= R; ++r) Dn[r] = dist32<ATT>(xr[r], yr[r], c1.x, c1.y);
-                float Q[R];
-                float m = TSPB_BIG;
-                const int qrel = qrel0 + jj;
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    float qv = U[r] + Dn[r + 1];
-                    Q[r] = (qrel >= r + 2) ? qv : TSPB_BIG;
-                    m = fminf(m, Q[r]);
-                }
-                const float Tq = thr + c0.z;
-                if (m <= Tq) {
-#pragma unroll
-                    for (int r = 0; r < R; ++r)
-                        if (Q[r] <= Tq)
-                            BI_CONSIDER(r, Q0 + jj);
-                }
-#pragma unroll
-                for (int r = 0; r < R; ++r) U[r] = Dn[r] + cp[r];
-                c0 = c1;
-                if ((jj & 63) == 63) thr = fminf(thr, (float)(*((volatile int *)&s_hint)) + W);
-            }
+            for (int k = 0; k < R / 2; ++k) U2[k] = f2add(f2pack(D0[2 * k], D0[2 * k + 1]), cp2[k]);
         }
+#define UU(r_) (((r_) & 1) ? f2hi(U2[(r_) >> 1]) : f2lo(U2[(r_) >> 1]))
+
+// one column: R+1 fresh distances -> R move deltas Q[r] = (D[p_r][q] - ds_p) + D[p_r+1][q+1]; the filter quantity
+// min_r Q[r] - ds_q is folded into the running block minimum M (no branch, no per-pair state kept)
+#define BI_COL(DIAG, jj_)                                                                              \
+    {                                                                                                  \
+        const float4 c1 = cnext;                                                                       \
+        cnext = sc[(jj_) + 2]; /* prefetched one column ahead */                                       \
+        float Dn[R + 1];                                                                               \
+        column_dists<R, ATT>(xr2, yr2, xrl, yrl, c1.x, c1.y, Dn);                                      \
+        float m = TSPB_BIG;                                                                            \
+        _Pragma("unroll") for (int r = 0; r < R; ++r) {                                                \
+            float qv = UU(r) + Dn[r + 1];                                                              \
+            if (DIAG) qv = (qrel0 + (jj_) >= r + 2) ? qv : TSPB_BIG;                                   \
+            m = fminf(m, qv);                                                                          \
+        }                                                                                              \
+        M = fminf(M, m - c0.z);                                                                        \
+        _Pragma("unroll") for (int k = 0; k < R / 2; ++k)                                              \
+            U2[k] = f2add(f2pack(Dn[2 * k], Dn[2 * k + 1]), cp2[k]);                                   \
+        c0 = c1;                                                                                       \
+    }
+
+// BI_CB columns, then ONE filter check; on a hit the cold path re-evaluates exactly that column block
+#define BI_BLOCK(DIAG)                                                                                 \
+    for (int jj = 0; jj < TJ; jj += BI_CB) {                                                           \
+        float M = TSPB_BIG;                                                                            \
+        _Pragma("unroll") for (int c = 0; c < BI_CB; ++c) BI_COL(DIAG, jj + c)                         \
+        if (M <= thr) {                                                                                \
+            const MoveKey nb = bi_cold_block<ATT, EXACT32>(A.inst, rec, sc, n, p0, R, Q0, jj, BI_CB, thr, best); \
+            if (key_less(nb, best)) {                                                                  \
+                best = nb;                                                                             \
+                thr = fminf(thr, (float)nb.delta + W);                                                 \
+                atomicMin(&s_hint, nb.delta);                                                          \
+            }                                                                                          \
+        }                                                                                              \
+        if ((jj & 63) == 64 - BI_CB) thr = fminf(thr, (float)(*((volatile int *)&s_hint)) + W);        \
+    }
+
+        const int qrel0 = Q0 - p0;  // q - p0 at jj = 0
+        float4 cnext = sc[1];
+        if (!diag) {
+            BI_BLOCK(false)
+        } else {
+            BI_BLOCK(true)
+        }
+#undef BI_BLOCK
+#undef BI_COL
+#undef UU
 
         __syncthreads();  // every thread is done with sc[] before the next prefetch overwrites it
         if (tid == 0) {
@@ -264,64 +332,45 @@ __global__ void __launch_bounds__(BI_THREADS, 2) bi_scan_kernel(const BiArgs A) 
     for (int w = 1; w < BI_THREADS / 32; ++w)
         if (key_less(s_keys[w], k)) k = s_keys[w];
 
-    if (!A.fuse_apply) {
-        if (tid == 0) {
-            ctl->packed = (k.delta < 0) ? key_pack(k.delta, k.i, k.j) : key_pack(0, 0x1ffff, 0x1ffff);
-            ctl->last = k;
-            ctl->ticket = 0;
-            ctl->hint = 0;
-            ctl->launches += 1;
-        }
-        return;
-    }
-
-    if (k.delta < 0) apply_move_block(A.inst, A.tour, k.i, k.j);
     if (tid == 0) {
-        ctl->passes += 1;
-        ctl->launches += 1;
         ctl->last = k;
-        if (k.delta < 0) {
-            ctl->moves += 1;
-            ctl->obj_delta += k.delta;
-            long long lc = ctl->log_count;
-            if (A.tour.log && lc < A.tour.log_cap) {
-                MoveRec mr;
-                mr.i = k.i; mr.j = k.j; mr.delta = k.delta;
-                A.tour.log[lc] = mr;
-            }
-            ctl->log_count = lc + 1;
-        } else {
-            ctl->done = 1;  // reference src/tabusearch.c:158: mindelta >= 0 -> stop
-        }
         ctl->ticket = 0;
         ctl->hint = 0;
+        ctl->launches += 1;
+        if (!A.fuse_apply) {
+            // multi-GPU: publish this rank's key for the NCCL min-allreduce; bi_decode_packed_kernel continues
+            ctl->packed = (k.delta < 0) ? key_pack(k.delta, k.i, k.j) : key_pack(0, 0x1ffff, 0x1ffff);
+        } else {
+            ctl->passes += 1;
+            publish_move(A.tour, k.i, k.j, k.delta);
+            if (k.delta >= 0) ctl->done = 1;  // reference src/tabusearch.c:158: mindelta >= 0 -> stop
+        }
     }
 }
 
-// Applies the globally reduced key after the NCCL min-allreduce (multi-GPU): every rank applies the
-// same move to its replica of the tour, so no tour data ever crosses NVLink.
-__global__ void __launch_bounds__(1024) bi_apply_packed_kernel(const InstDev inst, const TourDev tour) {
+// After the NCCL min-allreduce (multi-GPU): every rank decodes the same winning key and publishes the move for
+// its own replica of the tour, so no tour data ever crosses NVLink.
+__global__ void bi_decode_packed_kernel(const TourDev tour) {
     Ctl *ctl = tour.ctl;
-    if (ctl->done) return;
+    if (ctl->done) { ctl->ap_valid = 0; return; }
     int delta, i, j;
     key_unpack(ctl->packed, &delta, &i, &j);
-    if (delta < 0) apply_move_block(inst, tour, i, j);
-    if (threadIdx.x == 0) {
-        ctl->passes += 1;
-        if (delta < 0) {
-            ctl->moves += 1;
-            ctl->obj_delta += delta;
-            long long lc = ctl->log_count;
-            if (tour.log && lc < tour.log_cap) {
-                MoveRec mr;
-                mr.i = i; mr.j = j; mr.delta = delta;
-                tour.log[lc] = mr;
-            }
-            ctl->log_count = lc + 1;
-        } else {
-            ctl->done = 1;
-        }
-    }
+    ctl->passes += 1;
+    publish_move(tour, i, j, delta);
+    if (delta >= 0) ctl->done = 1;
+}
+
+// Grid-wide application of the published move (see apply_swap_range).
+__global__ void __launch_bounds__(256) apply_move_kernel(const InstDev inst, const TourDev tour) {
+    const Ctl *ctl = tour.ctl;
+    if (!ctl->ap_valid) return;
+    apply_swap_range(inst, tour, ctl->ap_pa, ctl->ap_pb, blockIdx.x * 256 + threadIdx.x, gridDim.x * 256);
+}
+
+__global__ void __launch_bounds__(256) refresh_node_space_kernel(const TourDev tour) {
+    const Ctl *ctl = tour.ctl;
+    if (!ctl->ap_valid) return;
+    refresh_node_space(tour, ctl->ap_pa, ctl->ap_pb, blockIdx.x * 256 + threadIdx.x, gridDim.x * 256);
 }
 
 // ---- generic exact pass (any metric, incl. GEO / matrix lookup / oversized coordinates) ------------
@@ -332,7 +381,10 @@ __global__ void __launch_bounds__(256) bi_scan_exact_kernel(const InstDev inst, 
     __shared__ MoveKey s_keys[8];
     __shared__ int s_last;
     Ctl *ctl = tour.ctl;
-    if (ctl->done) return;
+    if (ctl->done) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) ctl->ap_valid = 0;
+        return;
+    }
     const int n = tour.n;
     const int tid = threadIdx.x;
     const float4 *rec = tour.rec;
@@ -380,34 +432,17 @@ __global__ void __launch_bounds__(256) bi_scan_exact_kernel(const InstDev inst, 
     k = s_keys[0];
     for (int w = 1; w < 8; ++w)
         if (key_less(s_keys[w], k)) k = s_keys[w];
-    if (!fuse_apply) {
-        if (tid == 0) {
-            ctl->packed = (k.delta < 0) ? key_pack(k.delta, k.i, k.j) : key_pack(0, 0x1ffff, 0x1ffff);
-            ctl->last = k;
-            ctl->ticket = 0;
-            ctl->launches += 1;
-        }
-        return;
-    }
-    if (k.delta < 0) apply_move_block(inst, tour, k.i, k.j);
     if (tid == 0) {
-        ctl->passes += 1;
-        ctl->launches += 1;
         ctl->last = k;
-        if (k.delta < 0) {
-            ctl->moves += 1;
-            ctl->obj_delta += k.delta;
-            long long lc = ctl->log_count;
-            if (tour.log && lc < tour.log_cap) {
-                MoveRec mr;
-                mr.i = k.i; mr.j = k.j; mr.delta = k.delta;
-                tour.log[lc] = mr;
-            }
-            ctl->log_count = lc + 1;
-        } else {
-            ctl->done = 1;
-        }
         ctl->ticket = 0;
+        ctl->launches += 1;
+        if (!fuse_apply) {
+            ctl->packed = (k.delta < 0) ? key_pack(k.delta, k.i, k.j) : key_pack(0, 0x1ffff, 0x1ffff);
+        } else {
+            ctl->passes += 1;
+            publish_move(tour, k.i, k.j, k.delta);
+            if (k.delta >= 0) ctl->done = 1;
+        }
     }
 }
 
@@ -425,6 +460,7 @@ static cudaError_t launch_bi_r(const BiArgs &a, int grid, cudaStream_t st) {
 }
 
 cudaError_t launch_bi_scan(const BiArgs &a, int rows_per_thread, int grid, cudaStream_t st) {
+    if (rows_per_thread == 16) return launch_bi_r<16>(a, grid, st);
     if (rows_per_thread == 8) return launch_bi_r<8>(a, grid, st);
     if (rows_per_thread == 4) return launch_bi_r<4>(a, grid, st);
     return launch_bi_r<2>(a, grid, st);
@@ -436,8 +472,25 @@ cudaError_t launch_bi_scan_exact(const InstDev &inst, const TourDev &tour, int r
     return cudaGetLastError();
 }
 
-cudaError_t launch_bi_apply_packed(const InstDev &inst, const TourDev &tour, cudaStream_t st) {
-    bi_apply_packed_kernel<<<1, 1024, 0, st>>>(inst, tour);
+cudaError_t launch_bi_decode_packed(const TourDev &tour, cudaStream_t st) {
+    bi_decode_packed_kernel<<<1, 1, 0, st>>>(tour);
+    return cudaGetLastError();
+}
+
+// grid sized for n/2 swaps at ~4 per thread, capped at 2 blocks per SM
+cudaError_t launch_apply_move(const InstDev &inst, const TourDev &tour, int num_sms, cudaStream_t st) {
+    int grid = (tour.n / 2 + 1023) / 1024;
+    if (grid < 1) grid = 1;
+    if (grid > 2 * num_sms) grid = 2 * num_sms;
+    apply_move_kernel<<<grid, 256, 0, st>>>(inst, tour);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_refresh_node_space(const TourDev &tour, int num_sms, cudaStream_t st) {
+    int grid = (tour.n + 1023) / 1024;
+    if (grid < 1) grid = 1;
+    if (grid > 2 * num_sms) grid = 2 * num_sms;
+    refresh_node_space_kernel<<<grid, 256, 0, st>>>(tour);
     return cudaGetLastError();
 }
 

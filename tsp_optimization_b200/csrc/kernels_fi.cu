@@ -29,7 +29,11 @@ __global__ void __launch_bounds__(FI_THREADS) fi_search_kernel(const InstDev I, 
     __shared__ int s_last;
     __shared__ unsigned long long s_found;
     Ctl *ctl = T.ctl;
-    if (ctl->done) return;
+    if (ctl->done) {
+        // a capped run stops right after publishing a move: make sure later apply launches are no-ops
+        if (blockIdx.x == 0 && threadIdx.x == 0) ctl->ap_valid = 0;
+        return;
+    }
     const int n = T.n;
     const int tid = threadIdx.x;
     const int i0 = ctl->cur_i, j0 = ctl->cur_j;
@@ -108,21 +112,11 @@ __global__ void __launch_bounds__(FI_THREADS) fi_search_kernel(const InstDev I, 
     bool sweep_end = false;
     if (f != FI_NONE) {
         const int i = (int)(f / (unsigned long long)n), j = (int)(f % (unsigned long long)n);
-        const long long delta = move_delta_nodes(I, T, i, j);
-        __syncthreads();
-        apply_move_block(I, T, i, j);
         if (tid == 0) {
+            const long long delta = move_delta_nodes(I, T, i, j);
             if (delta >= 0) ctl->error = 1;  // cannot happen: the searching thread saw delta < 0
-            ctl->moves += 1;
+            publish_move(T, i, j, delta);    // reference heuristics.c:476-486; applied by the next two launches
             ctl->sweep_moves += 1;
-            ctl->obj_delta += delta;  // reference heuristics.c:486: obj_best += delta
-            long long lc = ctl->log_count;
-            if (T.log && lc < T.log_cap) {
-                MoveRec mr;
-                mr.i = i; mr.j = j; mr.delta = delta;
-                T.log[lc] = mr;
-            }
-            ctl->log_count = lc + 1;
             ctl->pairs_swept += (long long)(f - ((unsigned long long)i0 * n + j0)) + 1;
         }
         ci = i;
@@ -131,6 +125,7 @@ __global__ void __launch_bounds__(FI_THREADS) fi_search_kernel(const InstDev I, 
         if (ci >= n - 1) sweep_end = true;
     } else {
         sweep_end = true;
+        if (tid == 0) ctl->ap_valid = 0;
         if (tid == 0) ctl->pairs_swept += (long long)((unsigned long long)(n - 1) * n - ((unsigned long long)i0 * n + j0));
     }
     if (tid == 0) {

@@ -50,6 +50,8 @@ struct Ctl {
     long long max_moves;            // FI only: stop after this many moves (<0 = unlimited)
     long long pairs_swept;          // FI: linear pairs covered (statistics only)
     MoveKey last;                   // last selected key
+    int ap_pa, ap_pb, ap_valid;     // move to apply: positions of a and b (published by the selecting kernel)
+    int pad0;
 };
 
 struct TourDev {
@@ -76,83 +78,112 @@ __device__ __forceinline__ long long dist_nodes(const InstDev &I, int u, int v) 
     return exact_dist(I.metric, I.pt64[u], I.pt64[v]);
 }
 
-// Block-wide application of the 2-opt move (i,j), i<j node ids, exactly as the reference does it:
+// Application of the 2-opt move (i,j), i<j node ids, exactly as the reference does it:
 //   a=i, b=j, a1=succ[a], b1=succ[b]; succ[a]=b; succ[a1]=b1; reverse_path(b, a1)
 // (reference src/heuristics.c:476-483, src/tabusearch.c:161-165, src/utility.c:708-722): the FORWARD path
 // a1 -> ... -> b is reversed, wrap-around included, never "the shorter side", so the orientation of the
 // tour — and with it the (i,j) -> (a1,b1) mapping of every later move — stays the reference's.
-// In position space that is an in-place reversal of the cyclic range [pos[a]+1, pos[b]].
-// Must be called by every thread of the block; ends with a __syncthreads().
-__device__ __forceinline__ void apply_move_block(const InstDev &I, const TourDev &T, int i, int j) {
+// In position space that is an in-place reversal of the cyclic range [pa+1, pb], pa = pos[a], pb = pos[b].
+//
+// The selecting kernel publishes (pa, pb) in Ctl; this routine is then run by a whole GRID (gtid of gthreads
+// threads) with no synchronisation at all: every swap t touches only positions s+t and e-t, the edge-length
+// reversal touches only the .z words of s..e-1, and the thread that owns swap 0 knows all four end nodes
+// (a, a1, b, b1) from its own loads, so it also writes the two new edge lengths.
+__device__ __forceinline__ void apply_swap_range(const InstDev &I, const TourDev &T, int pa, int pb, int gtid, int gthreads) {
     const int n = T.n;
-    const int tid = threadIdx.x, nt = blockDim.x;
     float4 *rec = T.rec;
-    const int pa = T.pos[i];
-    const int pb = T.pos[j];
-    __syncthreads();  // everyone has read pos[] before anyone rewrites it
     int s = pa + 1;
     if (s >= n) s -= n;
     int len = pb - pa;
     if (len < 0) len += n;  // number of nodes on the path a1..b
     const int e = pb;
-    // (x, y, node) of positions s+t <-> e-t
     const int half = len >> 1;
-    for (int t = tid; t < half; t += nt) {
+    for (int t = gtid; t < half; t += gthreads) {
         int A = s + t;
         if (A >= n) A -= n;
         int B = e - t;
         if (B < 0) B += n;
-        float2 xa = *reinterpret_cast<float2 *>(&rec[A].x);
-        float wa = rec[A].w;
-        float2 xb = *reinterpret_cast<float2 *>(&rec[B].x);
-        float wb = rec[B].w;
+        const float2 xa = *reinterpret_cast<const float2 *>(&rec[A].x);
+        const float wa = rec[A].w;
+        const float2 xb = *reinterpret_cast<const float2 *>(&rec[B].x);
+        const float wb = rec[B].w;
         *reinterpret_cast<float2 *>(&rec[A].x) = xb;
         rec[A].w = wb;
         *reinterpret_cast<float2 *>(&rec[B].x) = xa;
         rec[B].w = wa;
         T.pos[__float_as_int(wb)] = A;
         T.pos[__float_as_int(wa)] = B;
+        if (A == 0) {  // rec[n] mirrors rec[0] (wrap-around successor of position n-1)
+            *reinterpret_cast<float2 *>(&rec[n].x) = xb;
+            rec[n].w = wb;
+        }
+        if (B == 0) {
+            *reinterpret_cast<float2 *>(&rec[n].x) = xa;
+            rec[n].w = wa;
+        }
+        if (t == 0) {
+            // new edges: (a, b) at position pa and (a1, b1) at position pb; a and b1 are outside the range
+            int pb1 = pb + 1;
+            if (pb1 >= n) pb1 -= n;
+            const int na = node_of(rec[pa]);
+            const int nb1 = (pb1 == pa) ? na : node_of(rec[pb1]);
+            rec[pa].z = (float)dist_nodes(I, na, __float_as_int(wb));
+            rec[pb].z = (float)dist_nodes(I, __float_as_int(wa), nb1);
+        }
     }
     // inner edge lengths: positions s .. s+len-2 are reversed among themselves
     const int m = len - 1;
     const int mhalf = m >> 1;
-    for (int t = tid; t < mhalf; t += nt) {
+    for (int t = gtid; t < mhalf; t += gthreads) {
         int A = s + t;
         if (A >= n) A -= n;
         int Cc = s + m - 1 - t;
         if (Cc >= n) Cc -= n;
-        float za = rec[A].z, zc = rec[Cc].z;
+        const float za = rec[A].z, zc = rec[Cc].z;
         rec[A].z = zc;
         rec[Cc].z = za;
     }
-    __syncthreads();
-    if (tid == 0) {
-        // new edges (a,b) at position pa and (a1,b1) at position pb
-        int pa1 = pa + 1; if (pa1 >= n) pa1 -= n;
-        int pb1 = pb + 1; if (pb1 >= n) pb1 -= n;
-        int na = node_of(rec[pa]), nb = node_of(rec[pa1]);
-        int na1 = node_of(rec[pb]), nb1 = node_of(rec[pb1]);
-        rec[pa].z = (float)dist_nodes(I, na, nb);
-        rec[pb].z = (float)dist_nodes(I, na1, nb1);
-        float4 r0 = rec[0];
-        rec[n] = make_float4(r0.x, r0.y, -TSPB_BIG, r0.w);
+}
+
+// Node-space view refresh after a move (separate launch, first-improvement search only): every node at
+// positions pa..pb (cyclic) got a new successor.
+__device__ __forceinline__ void refresh_node_space(const TourDev &T, int pa, int pb, int gtid, int gthreads) {
+    const int n = T.n;
+    int len = pb - pa;
+    if (len < 0) len += n;
+    for (int t = gtid; t <= len; t += gthreads) {
+        int P = pa + t;
+        if (P >= n) P -= n;
+        int Pn = P + 1;
+        if (Pn >= n) Pn -= n;
+        const float4 rp = T.rec[P];
+        const float4 rn = T.rec[Pn];
+        const int k = node_of(rp);
+        T.nrec[k] = make_float4(rp.x, rp.y, rn.x, rn.y);
+        T.nds[k] = rp.z;
+        T.nsucc[k] = node_of(rn);
     }
-    __syncthreads();
-    if (T.nrec) {
-        // node-space view: every node at positions pa..pb (cyclic) got a new successor
-        for (int t = tid; t <= len; t += nt) {
-            int P = pa + t;
-            if (P >= n) P -= n;
-            int Pn = P + 1;
-            if (Pn >= n) Pn -= n;
-            float4 rp = rec[P];
-            float4 rn = rec[Pn];
-            int k = node_of(rp);
-            T.nrec[k] = make_float4(rp.x, rp.y, rn.x, rn.y);
-            T.nds[k] = rp.z;
-            T.nsucc[k] = node_of(rn);
+}
+
+// Bookkeeping done by ONE thread of the selecting kernel once the move (i,j,delta) is known: publishes the
+// positions for the apply launch, counts, logs.  delta >= 0 means "no move".
+__device__ __forceinline__ void publish_move(const TourDev &T, int i, int j, long long delta) {
+    Ctl *ctl = T.ctl;
+    if (delta < 0) {
+        ctl->ap_pa = T.pos[i];
+        ctl->ap_pb = T.pos[j];
+        ctl->ap_valid = 1;
+        ctl->moves += 1;
+        ctl->obj_delta += delta;
+        const long long lc = ctl->log_count;
+        if (T.log && lc < T.log_cap) {
+            MoveRec mr;
+            mr.i = i; mr.j = j; mr.delta = delta;
+            T.log[lc] = mr;
         }
-        __syncthreads();
+        ctl->log_count = lc + 1;
+    } else {
+        ctl->ap_valid = 0;
     }
 }
 

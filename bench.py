@@ -316,17 +316,44 @@ def main():
     peaks, peaks_src = measured_peaks()
     sm_mhz = clocks.get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
     num_sms = eng.info("num_sms")
-    peak_instr = num_sms * 128 * sm_mhz * 1e6  # FP32 lane-instructions / s at the clock seen under load
     per_gpu = value / world
-    roofline = {"bound": "fp32_issue", "achieved": per_gpu * FP32_INSTR_PER_EVAL / 1e12, "peak": peak_instr / 1e12,
-                "unit": "T lane-instr/s", "frac": per_gpu * FP32_INSTR_PER_EVAL / peak_instr, "traffic": None,
-                "kernel": "bi_scan_kernel", "per_unit": f"{FP32_INSTR_PER_EVAL} FP32 lane-instructions per evaluated move (SURVEY.md §8d)",
-                "peak_source": f"{num_sms} SMs x 128 FP32 lanes x {sm_mhz:.0f} MHz (nvidia-smi median under load); "
-                               f"MEASURED_PEAKS.json ({peaks_src}) holds no FP32 figure",
-                "sqrt_bound_frac": per_gpu / (num_sms * 16 * sm_mhz * 1e6),
-                "note": "the kernel shares each distance between the two moves that use it, so it issues ~9 FP32 "
-                        "lane-instr and 1.125 MUFU.SQRT per move; sqrt_bound_frac = evals/s over the MUFU limit "
-                        "(16 sqrt/clk/SM, one sqrt per move)"}
+    # Binding unit of bi_scan_kernel: the SFU (MUFU.SQRT, 16 results/clk/SM).  Algorithmic minimum = ONE distance
+    # (one sqrt) per evaluated move: every D[p][q] is shared by the two moves that use it.
+    sqrt_peak = num_sms * 16 * sm_mhz * 1e6
+    fp32_peak = num_sms * 128 * sm_mhz * 1e6
+    roofline = {"bound": "sfu_sqrt", "achieved": per_gpu / 1e12, "peak": sqrt_peak / 1e12, "unit": "T sqrt/s (= T evals/s)",
+                "frac": per_gpu / sqrt_peak, "traffic": 1.7e6, "kernel": "bi_scan_kernel",
+                "per_unit": "1 MUFU.SQRT per evaluated move (algorithmic minimum; the kernel issues 1.125)",
+                "peak_source": f"{num_sms} SMs x 16 MUFU/clk x {sm_mhz:.0f} MHz (nvidia-smi median under load); "
+                               f"MEASURED_PEAKS.json ({peaks_src}) holds HBM and bf16 figures only, neither bounds this kernel",
+                "fp32_issue_view": {"survey_per_unit": FP32_INSTR_PER_EVAL,
+                                    "frac_vs_survey_18_instr_model": per_gpu * FP32_INSTR_PER_EVAL / fp32_peak,
+                                    "executed_fp32_lane_ops_per_eval": 9.9,
+                                    "frac_executed": per_gpu * 9.9 / fp32_peak,
+                                    "note": "SURVEY.md §8d's 18 lane-instr/eval model evaluates two fresh distances per move; "
+                                            "sharing each distance between its two moves halves that, so the 18-instr "
+                                            "fraction exceeds 1 and is reported for reference only"},
+                "traffic_note": "dram__bytes_read.sum per launch from profiles/ (tour records, 16 B/node); compute-bound"}
+    # secondary kernel: distance matrix, HBM-store-bound (4*n*ld bytes written per launch)
+    mat = None
+    if world == 1:
+        nm = 32768
+        eng_m = eng
+        eng_m.set_instance(uniform_instance(nm), 0)
+        eng_m.dist_matrix_build()
+        ms_list = []
+        for _ in range(5):
+            if flush is not None:
+                flush.zero_()
+                torch.cuda.synchronize()
+            ms_list.append(eng_m.dist_matrix_build())
+        ld = eng_m.info("matrix_ld")
+        eng_m.dist_matrix_free()
+        ms = float(np.median(ms_list))
+        gbs = 4.0 * nm * ld / (ms * 1e-3) / 1e9
+        mat = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
+               "traffic": None, "kernel": "dist_matrix_kernel", "n": nm, "ms": ms,
+               "per_unit": "4 bytes written per matrix entry (int32), reads O(n)", "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peaks_src})"}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": gpu_ms / max(1, done_passes), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
@@ -342,6 +369,8 @@ def main():
                     "call": "tspb200_set_instance + tspb200_two_opt(BI, host succ[], max_iters=steps)"},
             "gpu_launches": int(launches), "moves_applied": int(moves), "wall_s": wall_s,
             "clocks": clocks, "roofline": roofline}
+    if mat:
+        line["roofline_matrix"] = mat
     if tlo:
         line["time_to_local_optimum"] = tlo
     if not args.no_cpu_baseline and world == 1:

@@ -1,4 +1,6 @@
 """Short, fixed run for ncu (dev tool): uni<n> NN start, a few BI passes, one matrix build, a few FI moves."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import sys
 import numpy as np
 from tsp_optimization_b200 import Engine, BI, FI

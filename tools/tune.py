@@ -1,4 +1,6 @@
 """GPU tuning sweep (dev tool): BI pass throughput vs tile shape / grid."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import sys, time, json
 import numpy as np
 from tsp_optimization_b200 import Engine, BI

@@ -122,6 +122,22 @@ def test_matrix_adversarial_half_boundaries(engine, oracle):
     engine.dist_matrix_free()
 
 
+@pytest.mark.parametrize("wt", [0, 3, 5])
+def test_matrix_full_compare_n4096(engine, oracle, wt):
+    """16.7 M entries per metric against the oracle, entry by entry: exercises the deferred exact re-evaluation of
+    rows flagged by the FP32 guard band (integer coordinates -> exact FP64 compare; quarter-integer coordinates ->
+    reference operation order in FP64) and both the full-block and the tail-row code paths (4100 % 32 != 0)."""
+    rng = np.random.default_rng(4096 + wt)
+    for n, scale in [(4096, 1.0), (4100, 0.25)]:
+        xy = rng.integers(0, 40000, size=(n, 2)).astype(np.float64) * scale
+        engine.set_instance(xy, wt)
+        assert engine.info("exact32") == 1 and engine.info("int_coords") == (1 if scale == 1.0 else 0)
+        m = engine.dist_matrix()
+        ref = oracle.dist_matrix(xy, wt)
+        assert (m == ref).all(), (wt, n, np.argwhere(m != ref)[:3].tolist())
+    engine.dist_matrix_free()
+
+
 def test_matrix_large_checksum_property(engine, oracle):
     """n = 6000 (144 MB matrix): symmetry, zero diagonal, and 64 sampled rows == oracle."""
     xy = uniform_instance(6000)

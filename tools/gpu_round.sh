@@ -1,9 +1,3 @@
 set -x
-nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.txt
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"
-timeout 600 python bench.py > gpurun_out/bench_r1c.json 2> gpurun_out/bench_r1c.err; echo "bench rc=$?"
-timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_short.json 2>&1 && \
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_bench_r1.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1
-timeout 300 python tools/prof.py 100000 6 matrix > gpurun_out/prof_plain.log 2>&1 && \
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'bi_scan_kernel|dist_matrix_kernel' -s 2 -c 5 -f -o gpurun_out/prof_r1c python tools/prof.py 100000 6 matrix > gpurun_out/ncu_full.log 2>&1
-echo done
+timeout 900 python -m pytest tests -m gpu -x -q -k "matrix" > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"
+timeout 600 python tools/matbench.py > gpurun_out/matbench.jsonl 2>&1; echo "rc=$?"

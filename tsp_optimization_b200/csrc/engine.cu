@@ -225,6 +225,7 @@ int64_t tspb200_get_info(const tspb200_ctx *ctx, const char *key) {
     if (k == "ntiles") return ctx->ntiles;
     if (k == "exact32") return ctx->inst.exact32;
     if (k == "fp32_ok") return ctx->inst.fp32_ok;
+    if (k == "int_coords") return ctx->inst.int_coords;
     if (k == "window_x1000") return (int64_t)(ctx->inst.W * 1000.0f);
     if (k == "matrix_resident") return ctx->d_mat != nullptr;
     if (k == "matrix_ld") return ctx->mat_ld;
@@ -243,13 +244,14 @@ int tspb200_set_instance(tspb200_ctx *ctx, const double *xy, int n, int weight_t
     ctx->n = n;
     ctx->metric = weight_type;
     // host-side scan: FP32 representability, bounding box -> filter window
-    bool exact32 = true, finite = true;
+    bool exact32 = true, finite = true, int_coords = true;
     double xmin = xy[0], xmax = xy[0], ymin = xy[1], ymax = xy[1], dc = 0;
     for (int k = 0; k < n; ++k) {
         double x = xy[2 * k], y = xy[2 * k + 1];
         if (!std::isfinite(x) || !std::isfinite(y)) finite = false;
         float fx = (float)x, fy = (float)y;
         if ((double)fx != x || (double)fy != y) exact32 = false;
+        if (x != std::nearbyint(x) || y != std::nearbyint(y)) int_coords = false;
         dc = std::fmax(dc, std::fmax(std::fabs((double)fx - x), std::fabs((double)fy - y)));
         xmin = std::fmin(xmin, x); xmax = std::fmax(xmax, x);
         ymin = std::fmin(ymin, y); ymax = std::fmax(ymax, y);
@@ -267,6 +269,7 @@ int tspb200_set_instance(tspb200_ctx *ctx, const double *xy, int n, int weight_t
     ctx->inst.metric = weight_type;
     ctx->inst.exact32 = exact32 ? 1 : 0;
     ctx->inst.fp32_ok = fp32_ok ? 1 : 0;
+    ctx->inst.int_coords = (int_coords && exact32 && finite) ? 1 : 0;
     ctx->inst.W = (float)(2.0 + 2.0 * eps);
     ctx->inst.band = (float)std::ldexp(1.0, -20);
     CK(cudaMalloc(&ctx->d_raw, sizeof(double2) * (size_t)n));

@@ -31,45 +31,6 @@ __device__ __forceinline__ float dist32(float ax, float ay, float bx, float by) 
 }
 
 
-// ---- packed FP32x2 arithmetic (sm_100: FADD2 / FMUL2 / FFMA2, one issue slot for two values) --------------
-// Packed values live in 64-bit registers for their whole life so that ptxas keeps them in aligned pairs.
-typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 f2pack(float lo, float hi) {
-    f32x2 r;
-    asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ float f2lo(f32x2 v) {
-    float lo, hi;
-    asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-    return lo;
-}
-__device__ __forceinline__ float f2hi(f32x2 v) {
-    float lo, hi;
-    asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-    return hi;
-}
-__device__ __forceinline__ f32x2 f2sub(f32x2 a, f32x2 b) {
-    f32x2 r;
-    asm("sub.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-__device__ __forceinline__ f32x2 f2add(f32x2 a, f32x2 b) {
-    f32x2 r;
-    asm("add.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-__device__ __forceinline__ f32x2 f2mul(f32x2 a, f32x2 b) {
-    f32x2 r;
-    asm("mul.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-__device__ __forceinline__ f32x2 f2fma(f32x2 a, f32x2 b, f32x2 c) {
-    f32x2 r;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-    return r;
-}
-
 // distances from R+1 consecutive rows to one column point: rows 0..R-1 in R/2 packed pairs, row R scalar
 template <int R, bool ATT>
 __device__ __forceinline__ void column_dists(const f32x2 (&xr2)[R / 2], const f32x2 (&yr2)[R / 2], float xrl, float yrl,

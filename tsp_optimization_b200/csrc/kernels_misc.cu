@@ -22,65 +22,154 @@ cudaError_t launch_prep_points(const double2 *raw, double2 *pt64, float2 *pt32, 
 
 // ---- distance matrix --------------------------------------------------------------------------------------
 // out[i*ld + j] = (int32) calc_dist(i, j)  (reference src/distutil.c:73-92), ld % 4 == 0 so that every row
-// starts 16-byte aligned.  One thread = 4 consecutive j of ROWS_PER_BLOCK rows -> one st.global.v4.s32 per row;
+// starts 16-byte aligned.  One thread = 4 consecutive j of MAT_ROWS rows -> one st.global.v4.s32 per row;
 // a warp writes 512 contiguous bytes.  HBM-store-bound: 4*n*ld bytes written, O(n) read.
-// FAST: FP32 distance with a guard band around the rounding boundary; inside the band (or when the
-// instance is not FP32-safe) the entry is recomputed in FP64 with the reference's exact operation order.
+//
+// Fast kernel (EUC_2D / CEIL_2D / ATT with FP32-exact coordinates): packed FP32x2 arithmetic, MUFU.SQRT, the
+// integer taken straight from the bits of (r + 1.5*2^23).  A row whose 4 entries contain a value within the
+// FP32 error band of a rounding boundary (|r_fp32 - r| <= r*2^-22: two roundings of s, MUFU.SQRT <= 2^-23) is
+// only FLAGGED in the hot loop; flagged rows are re-evaluated exactly after the loop and stored again, so the
+// hot loop has no divergent branch.  Exact re-evaluation: integer coordinates -> the rounding decision is an
+// exact FP64 compare of s = dx^2+dy^2 against the boundary's square (no sqrt: for integer s the boundary can
+// never be closer than 1/(8k+4) to sqrt(s), far outside double rounding); otherwise the
+// reference's operation order in FP64 (exact_dist).
 constexpr int MAT_THREADS = 256;
-constexpr int MAT_ROWS = 16;
+constexpr int MAT_ROWS = 32;
+constexpr int MAT_ROWS_SLOW = 16;
+enum { MK_NINT = 0, MK_CEIL = 1, MK_ATT = 2 };
 
-template <bool FAST>
+// exact entry for integer coordinates; k0 = FP32 estimate rint(r), correct to +-1
+template <int KIND>
+__device__ __forceinline__ int exact_entry_int(float xi, float yi, float xj, float yj, int k0) {
+    const double dx = (double)xi - (double)xj, dy = (double)yi - (double)yj;
+    const double S = dx * dx + dy * dy;  // integers < 2^53: exact whatever the contraction
+    const double k = (double)k0;
+    if (KIND == MK_NINT) {  // floor(sqrt(S) + 0.5)
+        if (S > k * k + k) return k0 + 1;
+        if (k0 >= 1 && S <= k * k - k) return k0 - 1;
+        return k0;
+    } else if (KIND == MK_CEIL) {  // ceil(sqrt(S))
+        if (S > k * k) return k0 + 1;
+        if (k0 >= 1 && S <= (k - 1.0) * (k - 1.0)) return k0 - 1;
+        return k0;
+    } else {  // ATT: smallest t with 10 t^2 >= S  (== t = nint(r); t < r ? t+1 : t  for r = sqrt(S/10))
+        if (S > 10.0 * k * k) return k0 + 1;
+        if (k0 >= 1 && S <= 10.0 * (k - 1.0) * (k - 1.0)) return k0 - 1;
+        return k0;
+    }
+}
+
+template <int KIND>
 __global__ void __launch_bounds__(MAT_THREADS) dist_matrix_kernel(const InstDev I, int *__restrict__ out, long long ld,
                                                                   int row_begin, int row_end) {
     const int n = I.n;
     const int j4 = (blockIdx.x * MAT_THREADS + threadIdx.x) * 4;
     if (j4 >= n) return;
     const int r0 = row_begin + blockIdx.y * MAT_ROWS;
-    const int r1 = min(r0 + MAT_ROWS, row_end);
-    const int metric = I.metric;
+    const int nrows = min(MAT_ROWS, row_end - r0);
+    const float MAGIC = 12582912.0f;  // 1.5 * 2^23: (r + MAGIC) holds rint(r) in its low mantissa bits
+    const int MAGIC_BITS = 0x4B400000;
+    const float BAND = (KIND == MK_ATT) ? 4.76837158203125e-07f : 2.384185791015625e-07f;  // 2^-21 / 2^-22
     float cx[4], cy[4];
-    int jj[4];
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-        jj[c] = min(j4 + c, n - 1);
-        if (FAST) {
-            float2 p = I.pt32[jj[c]];
-            cx[c] = p.x;
-            cy[c] = p.y;
-        }
+        const float2 p = I.pt32[min(j4 + c, n - 1)];
+        cx[c] = p.x;
+        cy[c] = p.y;
     }
-    for (int i = r0; i < r1; ++i) {
-        int v[4];
-        if (FAST) {
-            const float2 pi = I.pt32[i];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                float dx = pi.x - cx[c], dy = pi.y - cy[c];
-                float s = fmaf(dy, dy, dx * dx);
-                if (metric == M_ATT) s *= 0.1f;
-                float r = sqrt_approx(s);
-                float k = (r + 12582912.0f) - 12582912.0f;  // nearest integer (ties irrelevant: they are in the band)
-                float frac = r - k;                          // in [-0.5, 0.5]
-                float band = fmaf(r, I.band, 1e-6f);
-                bool unsafe;
-                int val;
-                if (metric == M_EUC_2D || (metric != M_CEIL_2D && metric != M_ATT)) {
-                    // nint: boundary at k +- 0.5
-                    unsafe = (0.5f - fabsf(frac)) <= band;
-                    val = (int)k;
-                } else {
-                    // ceil (CEIL_2D, and ATT == ceil of r for non-integers, r itself for integers): boundary at integers
-                    unsafe = fabsf(frac) <= band;
-                    val = (int)k + (frac > 0.f ? 1 : 0);
-                }
-                if (unsafe) val = (int)exact_dist(metric, I.pt64[i], I.pt64[jj[c]]);
-                v[c] = val;
-            }
-        } else {
-            const double2 pi = I.pt64[i];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) v[c] = (int)exact_dist(metric, pi, I.pt64[jj[c]]);
+    const f32x2 cx01 = f2pack(cx[0], cx[1]), cx23 = f2pack(cx[2], cx[3]);
+    const f32x2 cy01 = f2pack(cy[0], cy[1]), cy23 = f2pack(cy[2], cy[3]);
+    const f32x2 magic2 = f2pack(MAGIC, MAGIC);
+    const f32x2 tenth2 = f2pack(0.1f, 0.1f);
+    const float2 *__restrict__ prow = I.pt32 + r0;
+    int *__restrict__ orow = out + (long long)(r0 - row_begin) * ld + j4;
+    unsigned flags = 0;
+
+    auto row = [&](int rr) {
+        const float2 pi = __ldg(prow + rr);
+        const f32x2 px = f2pack(pi.x, pi.x), py = f2pack(pi.y, pi.y);
+        const f32x2 dx01 = f2sub(px, cx01), dx23 = f2sub(px, cx23);
+        const f32x2 dy01 = f2sub(py, cy01), dy23 = f2sub(py, cy23);
+        f32x2 s01 = f2fma(dy01, dy01, f2mul(dx01, dx01));
+        f32x2 s23 = f2fma(dy23, dy23, f2mul(dx23, dx23));
+        if (KIND == MK_ATT) {
+            s01 = f2mul(s01, tenth2);
+            s23 = f2mul(s23, tenth2);
         }
+        const float r[4] = {sqrt_approx(f2lo(s01)), sqrt_approx(f2hi(s01)), sqrt_approx(f2lo(s23)), sqrt_approx(f2hi(s23))};
+        const f32x2 r01 = f2pack(r[0], r[1]), r23 = f2pack(r[2], r[3]);
+        const f32x2 t01 = f2add(r01, magic2), t23 = f2add(r23, magic2);
+        const f32x2 f01 = f2sub(r01, f2sub(t01, magic2)), f23 = f2sub(r23, f2sub(t23, magic2));
+        const float t[4] = {f2lo(t01), f2hi(t01), f2lo(t23), f2hi(t23)};
+        const float fr[4] = {f2lo(f01), f2hi(f01), f2lo(f23), f2hi(f23)};  // r - rint(r), in [-0.5, 0.5]
+        int v[4];
+        float u[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            v[c] = __float_as_int(t[c]) - MAGIC_BITS;
+            if (KIND == MK_NINT) {
+                u[c] = fmaf(r[c], BAND, fabsf(fr[c]));  // unsafe iff >= 0.5: within the band of k +- 0.5
+            } else {
+                u[c] = fmaf(r[c], -BAND, fabsf(fr[c]));  // unsafe iff <= 0: within the band of the integer k
+                v[c] += (fr[c] > 0.f) ? 1 : 0;            // ceil
+            }
+        }
+        bool flag;
+        if (KIND == MK_NINT) flag = fmaxf(fmaxf(u[0], u[1]), fmaxf(u[2], u[3])) >= 0.5f;
+        else flag = fminf(fminf(u[0], u[1]), fminf(u[2], u[3])) <= 0.f;
+        if (flag) flags |= 1u << rr;
+        *reinterpret_cast<int4 *>(orow + (long long)rr * ld) = make_int4(v[0], v[1], v[2], v[3]);
+    };
+
+    if (nrows == MAT_ROWS) {
+#pragma unroll 4
+        for (int rr = 0; rr < MAT_ROWS; ++rr) row(rr);
+    } else {
+        for (int rr = 0; rr < nrows; ++rr) row(rr);
+    }
+
+    // exact re-evaluation of the flagged rows (rare: ~1 % of a thread's rows at 10^4-range coordinates)
+    while (flags) {
+        const int rr = __ffs(flags) - 1;
+        flags &= flags - 1;
+        const int i = r0 + rr;
+        const float2 pi = __ldg(prow + rr);
+        int v[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            if (I.int_coords) {
+                const float dx = pi.x - cx[c], dy = pi.y - cy[c];
+                float s = fmaf(dy, dy, dx * dx);
+                if (KIND == MK_ATT) s *= 0.1f;
+                const int k0 = __float_as_int(sqrt_approx(s) + MAGIC) - MAGIC_BITS;
+                v[c] = exact_entry_int<KIND>(pi.x, pi.y, cx[c], cy[c], k0);
+            } else {
+                const double2 a = I.pt64[i], b = I.pt64[min(j4 + c, n - 1)];
+                v[c] = (int)(KIND == MK_ATT ? exact_att(a.x, a.y, b.x, b.y)
+                                            : (KIND == MK_CEIL ? exact_ceil(a.x, a.y, b.x, b.y) : exact_euc(a.x, a.y, b.x, b.y)));
+            }
+        }
+        *reinterpret_cast<int4 *>(orow + (long long)rr * ld) = make_int4(v[0], v[1], v[2], v[3]);
+    }
+}
+
+// Any metric / any coordinates: every entry in FP64 with the reference's operation order.
+__global__ void __launch_bounds__(MAT_THREADS) dist_matrix_exact_kernel(const InstDev I, int *__restrict__ out, long long ld,
+                                                                        int row_begin, int row_end) {
+    const int n = I.n;
+    const int j4 = (blockIdx.x * MAT_THREADS + threadIdx.x) * 4;
+    if (j4 >= n) return;
+    const int r0 = row_begin + blockIdx.y * MAT_ROWS_SLOW;
+    const int r1 = min(r0 + MAT_ROWS_SLOW, row_end);
+    const int metric = I.metric;
+    double2 pj[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) pj[c] = I.pt64[min(j4 + c, n - 1)];
+    for (int i = r0; i < r1; ++i) {
+        const double2 pi = I.pt64[i];
+        int v[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) v[c] = (int)exact_dist(metric, pi, pj[c]);
         *reinterpret_cast<int4 *>(out + (long long)(i - row_begin) * ld + j4) = make_int4(v[0], v[1], v[2], v[3]);
     }
 }
@@ -89,9 +178,16 @@ cudaError_t launch_dist_matrix(const InstDev &I, int *out, long long ld, int row
                                cudaStream_t st) {
     int rows = row_end - row_begin;
     if (rows <= 0) return cudaSuccess;
-    dim3 grid((unsigned)((I.n + MAT_THREADS * 4 - 1) / (MAT_THREADS * 4)), (unsigned)((rows + MAT_ROWS - 1) / MAT_ROWS));
-    if (fast) dist_matrix_kernel<true><<<grid, MAT_THREADS, 0, st>>>(I, out, ld, row_begin, row_end);
-    else dist_matrix_kernel<false><<<grid, MAT_THREADS, 0, st>>>(I, out, ld, row_begin, row_end);
+    const unsigned gx = (unsigned)((I.n + MAT_THREADS * 4 - 1) / (MAT_THREADS * 4));
+    if (fast) {
+        dim3 grid(gx, (unsigned)((rows + MAT_ROWS - 1) / MAT_ROWS));
+        if (I.metric == M_ATT) dist_matrix_kernel<MK_ATT><<<grid, MAT_THREADS, 0, st>>>(I, out, ld, row_begin, row_end);
+        else if (I.metric == M_CEIL_2D) dist_matrix_kernel<MK_CEIL><<<grid, MAT_THREADS, 0, st>>>(I, out, ld, row_begin, row_end);
+        else dist_matrix_kernel<MK_NINT><<<grid, MAT_THREADS, 0, st>>>(I, out, ld, row_begin, row_end);
+    } else {
+        dim3 grid(gx, (unsigned)((rows + MAT_ROWS_SLOW - 1) / MAT_ROWS_SLOW));
+        dist_matrix_exact_kernel<<<grid, MAT_THREADS, 0, st>>>(I, out, ld, row_begin, row_end);
+    }
     return cudaGetLastError();
 }
 

@@ -20,6 +20,7 @@ struct InstDev {
     int metric;             // reference weight_type value
     int exact32;            // every coordinate is exactly representable in FP32
     int fp32_ok;            // FP32 filter path usable (metric in EUC/CEIL/ATT, |coords| small enough)
+    int int_coords;         // every coordinate is an integer (and exact32): rounding decisions reduce to exact compares
     float W;                // filter window: candidate iff Q <= best + W
     float band;             // matrix kernel guard band, relative to r
     const double2 *pt64;    // node-indexed exact points (GEO: lat/lon radians)

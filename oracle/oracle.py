@@ -20,6 +20,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_SO = os.path.join(_HERE, "_build", "libtsporacle.so")
 REF_SO = os.path.join(_HERE, "_ref", "libtspref.so")
+#: the same reference objects linked against the product's drop-in symbols (oracle/Makefile)
+REF_GPU_SO = os.path.join(_HERE, "_ref", "libtspref_gpu.so")
 
 EUC_2D, MAX_2D, MAN_2D, CEIL_2D, GEO, ATT = 0, 1, 2, 3, 4, 5
 
@@ -152,11 +154,14 @@ class RefLib:
                    "off_num_nodes", "off_weight_type", "off_num_columns", "off_obj_best", "off_edges",
                    "sizeof_point", "sizeof_edge", "off_verbose", "off_seed"]
 
-    def __init__(self):
+    def __init__(self, gpu_link: bool = False):
+        """gpu_link=True loads libtspref_gpu.so: the reference's callers run unmodified, but calc_dist / alg_2opt /
+        alg_2opt_tabu / reverse_path resolve to the product's CUDA-backed definitions (needs a GPU at call time)."""
         build()
-        if not os.path.exists(REF_SO):
-            raise FileNotFoundError(REF_SO)
-        L = C.CDLL(REF_SO)
+        so = REF_GPU_SO if gpu_link else REF_SO
+        if not os.path.exists(so):
+            raise FileNotFoundError(so)
+        L = C.CDLL(so)
         L.refshim_new.restype = C.c_void_p
         L.refshim_new.argtypes = [C.c_int, _f64p, C.c_int]
         L.refshim_parse.restype = C.c_void_p
@@ -183,6 +188,18 @@ class RefLib:
         L.alg_2opt_tabu.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.reverse_path.argtypes = [C.c_void_p, C.c_int, C.c_int, _i32p]
         self.L = L
+
+    def run_method(self, name: str, xy, wt):
+        """Runs one of the reference's own heuristic drivers (e.g. HEU_2opt_greedy, src/heuristics.c:572) on a fresh
+        instance, as solve_problem_HEUC (src/solver.c:114-151) would; returns (status, succ, obj_best)."""
+        h = self.new(xy, wt)
+        fn = getattr(self.L, name)
+        fn.argtypes = [C.c_void_p]
+        fn.restype = C.c_int
+        status = fn(h)
+        out = status, self.get_succ(h), self.L.refshim_obj(h)
+        self.free(h)
+        return out
 
     def layout(self) -> dict:
         buf = (C.c_int64 * 32)()

@@ -1,3 +1,2 @@
 set -x
-timeout 900 python -m pytest tests -m gpu -x -q -k "matrix" > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"
-timeout 600 python tools/matbench.py > gpurun_out/matbench.jsonl 2>&1; echo "rc=$?"
+timeout 900 python -m pytest tests/test_gpu_dropin_link.py -m gpu -x -q > gpurun_out/pytest_link.log 2>&1; echo "pytest rc=$?"

@@ -189,10 +189,13 @@ class RefLib:
         L.reverse_path.argtypes = [C.c_void_p, C.c_int, C.c_int, _i32p]
         self.L = L
 
-    def run_method(self, name: str, xy, wt):
+    def run_method(self, name: str, xy, wt, time_limit: int = -1):
         """Runs one of the reference's own heuristic drivers (e.g. HEU_2opt_greedy, src/heuristics.c:572) on a fresh
         instance, as solve_problem_HEUC (src/solver.c:114-151) would; returns (status, succ, obj_best)."""
         h = self.new(xy, wt)
+        # -1 = unlimited for every driver (HEU_Greedy_iter treats 0 as "0 seconds", src/heuristics.c:181)
+        self.L.refshim_set_time_limit.argtypes = [C.c_void_p, C.c_int]
+        self.L.refshim_set_time_limit(h, time_limit)
         fn = getattr(self.L, name)
         fn.argtypes = [C.c_void_p]
         fn.restype = C.c_int

@@ -9,7 +9,8 @@
  * Reference interfaces replaced (paths relative to the reference repository):
  *   calc_dist        include/distutil.h:137, src/distutil.c:73-92   -> tspb200_dist_matrix*, tspb200_tour_costs
  *   alg_2opt         include/heuristics.h:82, src/heuristics.c:438  -> tspb200_two_opt(mode = TSPB200_FI)
- *   alg_2opt_tabu    src/tabusearch.c:107 (no header)                -> tspb200_two_opt(mode = TSPB200_BI)
+ *   alg_2opt_tabu    src/tabusearch.c:107 (no header)                -> tspb200_two_opt(mode = TSPB200_BI), tspb200_two_opt_tabu
+ *   check_tenure     src/tabusearch.c:83-92                          -> inside tspb200_two_opt_tabu (device)
  *   reverse_path     include/utility.h:334, src/utility.c:708        -> applied on the device inside two_opt
  *   greedy           include/heuristics.h, src/heuristics.c:18       -> tspb200_nn_tour
  *   fitness          src/genetic.c:51-60                             -> tspb200_tour_costs
@@ -119,6 +120,14 @@ int tspb200_fi_run(tspb200_ctx *ctx, int64_t max_moves, tspb200_stats *st);
  * cost (reference tabusearch.c:168-172). log may be NULL. */
 int tspb200_two_opt(tspb200_ctx *ctx, int mode, int32_t *succ, double *obj, int64_t max_iters,
                     tspb200_stats *st, tspb200_move *log, int64_t log_cap, int64_t *log_count);
+
+/* alg_2opt_tabu WITH a tabu list (reference src/tabusearch.c:107-178, check_tenure :83-92): best improvement over the
+ * pairs whose four edges (a,b), (a,a1), (b,b1), (a,b1) pass check_tenure(skip_edge[x_udir_pos(..)], iter, tenure).
+ * skip_edge = the caller's n(n-1)/2 ints (in/out): entries whose tenure ran out and that a pair tested are zeroed,
+ * exactly like the reference's lazy expiry.  skip_edge == NULL is plain best improvement.  n <= 46340 (the
+ * reference's int edge index). */
+int tspb200_two_opt_tabu(tspb200_ctx *ctx, int32_t *succ, double *obj, int32_t *skip_edge, int iter, int tenure,
+                         int64_t max_passes, tspb200_stats *st, tspb200_move *log, int64_t log_cap, int64_t *log_count);
 
 /* Batched 2-opt of `batch` independent tours of the same instance (GA offspring repair, multi-start,
  * VNS / tabu restarts): one thread block per tour, tour state in shared memory, run to the local optimum.

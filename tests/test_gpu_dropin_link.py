@@ -56,3 +56,17 @@ def test_reference_plain_bi_through_dropin(gpulib, reflib, instances):
     s_g, o_g, p_g = gpulib.two_opt_bi(xy, wt, succ0, want_prev=True)
     s_r, o_r, p_r = reflib.two_opt_bi(xy, wt, succ0, want_prev=True)
     assert (s_g == s_r).all() and o_g == o_r and (p_g == p_r).all()
+
+
+def test_reference_masked_bi_through_dropin(gpulib, reflib, instances):
+    """alg_2opt_tabu WITH a tabu list through the reference-named symbol: same tour, cost and mutated list."""
+    xy, wt = instances["berlin52"]
+    n = len(xy)
+    rng = np.random.default_rng(3)
+    succ0, _ = reflib.nn_tour(xy, wt, 0)
+    ncols = n * (n - 1) // 2
+    mask = np.where(rng.random(ncols) < 0.15, rng.integers(1, 40, size=ncols), 0).astype(np.int32)
+    m_g, m_r = mask.copy(), mask.copy()
+    s_g, o_g = gpulib.two_opt_bi(xy, wt, succ0, skip_edge=m_g, iter_=40, tenure=9)
+    s_r, o_r = reflib.two_opt_bi(xy, wt, succ0, skip_edge=m_r, iter_=40, tenure=9)
+    assert (s_g == s_r).all() and o_g == o_r and (m_g == m_r).all()

@@ -413,3 +413,82 @@ def test_errors_are_loud(engine):
         engine.tour_upload(bad)
     with pytest.raises(eng.TspB200Error):
         engine.set_option("rows_per_thread", 3)
+
+
+# ---- tabu-masked best improvement (reference src/tabusearch.c:83-92,137-149) ---------------------------------
+@pytest.mark.parametrize("n,wt,density,iter_,tenure", [(60, 0, 0.2, 30, 12), (200, 0, 0.05, 100, 20), (299, 5, 0.3, 50, 49),
+                                                       (150, 4, 0.1, 40, 5), (120, 3, 0.5, 10, -1), (500, 0, 0.02, 1000, 50)])
+def test_tabu_masked_bi_equals_oracle(engine, oracle, n, wt, density, iter_, tenure):
+    """same move log, tour, cost AND the same lazily-expired tabu list as the oracle (itself pinned to the compiled
+    reference by tests/test_oracle.py::test_tabu_mask_restatement)."""
+    rng = np.random.default_rng(n + iter_)
+    xy = rng.integers(0, 1000, size=(n, 2)).astype(np.float64)
+    if wt == 4:
+        xy = xy / 10.0 - 50.0  # GEO: degrees.minutes
+    succ = order_to_succ(rng.permutation(n).astype(np.int32))
+    ncols = n * (n - 1) // 2
+    mask = np.where(rng.random(ncols) < density, rng.integers(1, iter_ + 1, size=ncols), 0).astype(np.int32)
+    m_ref = mask.copy()
+    es, eobj, est, elog = oracle.two_opt_bi(xy, wt, succ, skip_edge=m_ref, iter_=iter_, tenure=tenure, log_cap=100000)
+    engine.set_instance(xy, wt)
+    for use_matrix in (False, True):
+        if use_matrix:
+            engine.dist_matrix_build()
+        s, obj, st, log, m_out = engine.two_opt_tabu(succ, mask, iter_, tenure, log_cap=100000)
+        assert log.tolist() == elog.tolist()
+        assert (s == es).all() and obj == eobj and st.moves == est.moves and st.passes == est.passes
+        assert (m_out == m_ref).all(), int((m_out != m_ref).sum())
+    engine.dist_matrix_free()
+
+
+def _two_exchange(succ, a, b):
+    """The tabu kick (reference src/tabusearch.c:293-295): succ[a]=b; succ[a1]=b1; reverse_path(b, a1)."""
+    succ = succ.copy()
+    a1, b1 = int(succ[a]), int(succ[b])
+    path = [a1]
+    while path[-1] != b:
+        path.append(int(succ[path[-1]]))
+    succ[a] = b
+    for k in range(len(path) - 1, 0, -1):
+        succ[path[k]] = path[k - 1]
+    succ[a1] = b1
+    return succ
+
+
+def test_tabu_search_iterations_replayed(engine, oracle):
+    """A deterministic replay of the reference's tabu() loop (src/tabusearch.c:228-311): masked 2-opt, random
+    non-adjacent kick, the two removed edges enter the list with the iteration stamp, the tenure steps between two
+    values (so expired entries can become tabu again unless the lazy expiry zeroed them).  The device path must track
+    the oracle for 40 iterations: tours, costs and the list itself."""
+    rng = np.random.default_rng(5)
+    n = 180
+    xy = rng.integers(0, 2000, size=(n, 2)).astype(np.float64)
+    engine.set_instance(xy, 0)
+    succ_o, _ = oracle.nn_tour(xy, 0, 0)
+    succ_g = succ_o.copy()
+    ncols = n * (n - 1) // 2
+    tl_o = np.zeros(ncols, dtype=np.int32)
+    tl_g = np.zeros(ncols, dtype=np.int32)
+
+    def pos(i, j):
+        if i > j:
+            i, j = j, i
+        return i * n + j - ((i + 1) * (i + 2)) // 2
+
+    tenure = 4
+    for it in range(1, 41):
+        succ_o, obj_o, _, _ = oracle.two_opt_bi(xy, 0, succ_o, skip_edge=tl_o, iter_=it, tenure=tenure)
+        succ_g, obj_g, _, _, tl_g = engine.two_opt_tabu(succ_g, tl_g, it, tenure)
+        assert (succ_o == succ_g).all() and obj_o == obj_g and (tl_o == tl_g).all(), it
+        while True:
+            a, b = int(rng.integers(0, n)), int(rng.integers(0, n))
+            a1, b1 = int(succ_o[a]), int(succ_o[b])
+            if a != b and a1 != b and b1 != a:
+                break
+        succ_o = _two_exchange(succ_o, a, b)
+        succ_g = succ_o.copy()
+        for tl in (tl_o, tl_g):
+            tl[pos(a, a1)] = it
+            tl[pos(b, b1)] = it
+        if it % 10 == 0:
+            tenure = 18 if tenure == 4 else 4

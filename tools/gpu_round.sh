@@ -1,2 +1,2 @@
 set -x
-timeout 900 python -m pytest tests/test_gpu_dropin_link.py -m gpu -x -q > gpurun_out/pytest_link.log 2>&1; echo "pytest rc=$?"
+timeout 900 python -m pytest tests -m gpu -x -q -k "tabu or dropin or masked" > gpurun_out/pytest_tabu.log 2>&1; echo "pytest rc=$?"

@@ -77,7 +77,7 @@ tspb200_ctx *context_for(tspb200_ref_instance *inst, bool full_check) {
     return g_cache.ctx;
 }
 
-int run_two_opt(tspb200_ref_instance *inst, int mode, int *stored_prev) {
+int run_two_opt(tspb200_ref_instance *inst, int mode, int *stored_prev, int *skip_edge = nullptr, int iter = 0, int tenure = 0) {
     std::lock_guard<std::mutex> lk(g_mu);
     tspb200_ctx *ctx = context_for(inst, true);
     const int n = inst->num_nodes;
@@ -87,7 +87,10 @@ int run_two_opt(tspb200_ref_instance *inst, int mode, int *stored_prev) {
     tspb200_set_option(ctx, "time_limit_ms", inst->params.time_limit > 0 ? (int64_t)inst->params.time_limit * 1000 : 0);
     double obj = inst->solution.obj_best;
     tspb200_stats st;
-    int rc = tspb200_two_opt(ctx, mode, succ.data(), &obj, -1, &st, nullptr, 0, nullptr);
+    static_assert(sizeof(int) == sizeof(int32_t), "tabu list element");
+    int rc = skip_edge ? tspb200_two_opt_tabu(ctx, succ.data(), &obj, reinterpret_cast<int32_t *>(skip_edge), iter, tenure, -1,
+                                              &st, nullptr, 0, nullptr)
+                       : tspb200_two_opt(ctx, mode, succ.data(), &obj, -1, &st, nullptr, 0, nullptr);
     if (rc) die("2-opt failed: ", tspb200_last_error(ctx));
     for (int k = 0; k < n; ++k) { inst->solution.edges[k].i = k; inst->solution.edges[k].j = succ[k]; }
     inst->solution.obj_best = obj;
@@ -124,11 +127,7 @@ double calc_dist(int i, int j, tspb200_ref_instance *inst) {
 int alg_2opt(tspb200_ref_instance *inst) { return run_two_opt(inst, TSPB200_FI, nullptr); }
 
 int alg_2opt_tabu(tspb200_ref_instance *inst, int *skip_edge, int *stored_prev, const int iter, const int tenure) {
-    (void)iter; (void)tenure;
-    if (skip_edge)
-        die("alg_2opt_tabu with a non-NULL tabu list is not on the GPU path yet (SURVEY.md §8 row f2, 'next'); "
-            "call it with skip_edge == NULL for plain best-improvement 2-opt");
-    return run_two_opt(inst, TSPB200_BI, stored_prev);
+    return run_two_opt(inst, TSPB200_BI, stored_prev, skip_edge, iter, tenure);
 }
 
 // Host-side successor flip on the caller's own arrays, same contract as reference src/utility.c:708-722

@@ -22,6 +22,8 @@ namespace tspb {
 cudaError_t launch_bi_scan(const BiArgs &a, int rows_per_thread, int grid, cudaStream_t st);
 cudaError_t launch_bi_scan_exact(const InstDev &inst, const TourDev &tour, int rank, int world, int fuse_apply, int grid,
                                  cudaStream_t st);
+cudaError_t launch_bi_scan_tabu(const InstDev &inst, const TourDev &tour, int *skip, int iter, int tenure, long long *zl,
+                                unsigned long long *zl_count, long long zl_cap, int grid, cudaStream_t st);
 cudaError_t launch_bi_decode_packed(const TourDev &tour, cudaStream_t st);
 cudaError_t launch_apply_move(const InstDev &inst, const TourDev &tour, int num_sms, cudaStream_t st);
 cudaError_t launch_refresh_node_space(const TourDev &tour, int num_sms, cudaStream_t st);
@@ -105,6 +107,15 @@ struct tspb200_ctx {
     int opt_R = 0, opt_TJ = 0, opt_grid = 0, opt_force_path = -1, opt_batch = 0;
     long long opt_time_limit_ms = 0;
 
+    // tabu list of the running alg_2opt_tabu call (device copy + indices zeroed by lazy expiry)
+    bool tabu_on = false;
+    int tabu_iter = 0, tabu_tenure = 0;
+    int *d_skip = nullptr;
+    long long skip_cap = 0;
+    long long *d_zl = nullptr;
+    unsigned long long *d_zl_count = nullptr;
+    long long zl_cap = 0;
+
     // comm
     nccl_comm_t comm = nullptr;
     int rank = 0, world = 1;
@@ -140,6 +151,10 @@ static void free_tour(tspb200_ctx *c) {
 
 static void free_instance(tspb200_ctx *c) {
     free_tour(c);
+    cudaFree(c->d_skip); cudaFree(c->d_zl); cudaFree(c->d_zl_count);
+    c->d_skip = nullptr; c->d_zl = nullptr; c->d_zl_count = nullptr;
+    c->skip_cap = c->zl_cap = 0;
+    c->tabu_on = false;
     cudaFree(c->d_raw); cudaFree(c->d_pt64); cudaFree(c->d_pt32); cudaFree(c->d_mat);
     c->d_raw = c->d_pt64 = nullptr; c->d_pt32 = nullptr; c->d_mat = nullptr;
     c->n = 0;
@@ -530,7 +545,11 @@ int tspb200_bi_run(tspb200_ctx *ctx, int64_t max_passes, tspb200_stats *st) {
     if (!ctx->has_tour) return fail(ctx, TSPB200_E_STATE, "no tour uploaded");
     CK(cudaSetDevice(ctx->device));
     const int n = ctx->n;
-    const int path = select_path(ctx);
+    int path = select_path(ctx);
+    if (ctx->tabu_on) {  // the masked scan is the literal (exact) evaluator: matrix gather when resident, else FP64
+        if (ctx->world > 1) return fail(ctx, TSPB200_E_UNSUPPORTED, "the tabu-masked scan is single-GPU");
+        path = ctx->d_mat ? 2 : 1;
+    }
     if (path == 2 && !ctx->d_mat) return fail(ctx, TSPB200_E_STATE, "matrix path selected but no resident matrix");
     if (path == 0 && !ctx->inst.fp32_ok) return fail(ctx, TSPB200_E_UNSUPPORTED, "FP32 filter path is not valid for this instance");
     if (ctx->world > 1 && (n > (1 << 17))) return fail(ctx, TSPB200_E_UNSUPPORTED, "multi-GPU key packing supports n <= 131072");
@@ -567,7 +586,10 @@ int tspb200_bi_run(tspb200_ctx *ctx, int64_t max_passes, tspb200_stats *st) {
             if (k > remaining) k = remaining;
         }
         for (long long q = 0; q < k; ++q) {
-            if (path == 0) CK(launch_bi_scan(a, ctx->R, ctx->grid_bi, ctx->stream));
+            if (ctx->tabu_on)
+                CK(launch_bi_scan_tabu(I, ctx->tour, ctx->d_skip, ctx->tabu_iter, ctx->tabu_tenure, ctx->d_zl, ctx->d_zl_count,
+                                       ctx->zl_cap, exact_grid, ctx->stream));
+            else if (path == 0) CK(launch_bi_scan(a, ctx->R, ctx->grid_bi, ctx->stream));
             else CK(launch_bi_scan_exact(I, ctx->tour, ctx->rank, ctx->world, a.fuse_apply, exact_grid, ctx->stream));
             host_launches++;
             if (ctx->world > 1) {
@@ -701,6 +723,52 @@ int tspb200_two_opt(tspb200_ctx *ctx, int mode, int32_t *succ, double *obj, int6
         if (rc) return rc;
     }
     if (st) *st = local;
+    return TSPB200_OK;
+}
+
+// alg_2opt_tabu with a tabu list (reference src/tabusearch.c:107-178): best improvement over the pairs that pass the
+// four check_tenure() tests, with the reference's lazy-expiry side effects replayed on the caller's array.
+int tspb200_two_opt_tabu(tspb200_ctx *ctx, int32_t *succ, double *obj, int32_t *skip_edge, int iter, int tenure,
+                         int64_t max_passes, tspb200_stats *st, tspb200_move *log, int64_t log_cap, int64_t *log_count) {
+    if (!ctx || !ctx->stream) return fail(ctx, TSPB200_E_CUDA, "context has no CUDA device");
+    if (!skip_edge) return tspb200_two_opt(ctx, TSPB200_BI, succ, obj, max_passes, st, log, log_cap, log_count);
+    if (ctx->n < 1) return fail(ctx, TSPB200_E_STATE, "no instance");
+    const int n = ctx->n;
+    // the reference indexes the list with an int x_udir_pos (src/utility.c:17-30): n*(n-1)/2 must fit
+    if (n > 46340) return fail(ctx, TSPB200_E_UNSUPPORTED, "tabu list index overflows int for n=%d (reference limit)", n);
+    CK(cudaSetDevice(ctx->device));
+    const long long len = (long long)n * (n - 1) / 2;
+    if (ctx->skip_cap < len) {
+        cudaFree(ctx->d_skip); cudaFree(ctx->d_zl); cudaFree(ctx->d_zl_count);
+        ctx->d_skip = nullptr; ctx->d_zl = nullptr; ctx->d_zl_count = nullptr;
+        ctx->skip_cap = 0;
+        ctx->zl_cap = len < (1ll << 22) ? len : (1ll << 22);
+        CK(cudaMalloc(&ctx->d_skip, sizeof(int) * (size_t)(len > 0 ? len : 1)));
+        CK(cudaMalloc(&ctx->d_zl, sizeof(long long) * (size_t)(ctx->zl_cap > 0 ? ctx->zl_cap : 1)));
+        CK(cudaMalloc(&ctx->d_zl_count, sizeof(unsigned long long)));
+        ctx->skip_cap = len;
+    }
+    CK(cudaMemcpyAsync(ctx->d_skip, skip_edge, sizeof(int) * (size_t)len, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_zl_count, 0, sizeof(unsigned long long), ctx->stream));
+    ctx->tabu_on = true;
+    ctx->tabu_iter = iter;
+    ctx->tabu_tenure = tenure;
+    int rc = tspb200_two_opt(ctx, TSPB200_BI, succ, obj, max_passes, st, log, log_cap, log_count);
+    ctx->tabu_on = false;
+    if (rc) return rc;
+    // replay the lazy expiry (check_tenure zeroes the entry, src/tabusearch.c:86-88) on the caller's list
+    unsigned long long cnt = 0;
+    CK(cudaMemcpyAsync(&cnt, ctx->d_zl_count, sizeof cnt, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if ((long long)cnt > ctx->zl_cap) {
+        CK(cudaMemcpyAsync(skip_edge, ctx->d_skip, sizeof(int) * (size_t)len, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    } else if (cnt > 0) {
+        std::vector<long long> zl((size_t)cnt);
+        CK(cudaMemcpyAsync(zl.data(), ctx->d_zl, sizeof(long long) * (size_t)cnt, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        for (long long e : zl) skip_edge[e] = 0;
+    }
     return TSPB200_OK;
 }
 

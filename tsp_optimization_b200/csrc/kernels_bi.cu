@@ -337,8 +337,46 @@ __global__ void __launch_bounds__(256) refresh_node_space_kernel(const TourDev t
 // ---- generic exact pass (any metric, incl. GEO / matrix lookup / oversized coordinates) ------------
 // Same argmin, every delta evaluated exactly (FP64 on the fly or int32 matrix gather).  One block per
 // group of rows; not the throughput path.
+//
+// MASK = true adds the tabu list of reference src/tabusearch.c:137-149: for every non-adjacent pair the four
+// edges (a,b), (a,a1), (b,b1), (a,b1) are tested with check_tenure() (:83-92) under the reference's
+// short-circuit order, INCLUDING its side effect — an entry whose tenure has run out is zeroed when (and only
+// when) a pair actually tests it.  iter and tenure are constant during one alg_2opt_tabu call, so an entry's
+// verdict never depends on whether it was already zeroed: the set of zeroed entries is the union over all
+// tested pairs and does not depend on evaluation order, which is what makes the parallel scan exact.
+// Zeroed indices are appended to a list so that the host can replay them on the caller's array.
+struct TabuArgs {
+    int *skip;                 // n(n-1)/2 ints, device copy of the caller's tabu list
+    int iter, tenure;
+    long long *zl;             // indices zeroed by lazy expiry
+    unsigned long long *zl_count;
+    long long zl_cap;
+};
+
+// reference src/utility.c:17-30 x_udir_pos (evaluated in 64 bits; the reference's int overflows for n > 46341)
+__device__ __forceinline__ long long udir_pos(int i, int j, int n) {
+    if (i > j) { const int t = i; i = j; j = t; }
+    return (long long)i * n + j - ((long long)(i + 1) * (i + 2)) / 2;
+}
+
+// reference src/tabusearch.c:83-92 check_tenure
+__device__ __forceinline__ bool tabu_check(const TabuArgs &T, long long e) {
+    if (T.iter < 0 || T.tenure < 0) return false;
+    const int v = *((volatile int *)&T.skip[e]);
+    if (v == 0) return false;
+    if (T.iter - v > T.tenure) {
+        if (atomicExch(&T.skip[e], 0) != 0) {
+            const unsigned long long k = atomicAdd(T.zl_count, 1ull);
+            if ((long long)k < T.zl_cap) T.zl[k] = e;
+        }
+        return false;
+    }
+    return true;
+}
+
+template <bool MASK>
 __global__ void __launch_bounds__(256) bi_scan_exact_kernel(const InstDev inst, const TourDev tour, int rank, int world,
-                                                            int fuse_apply) {
+                                                            int fuse_apply, const TabuArgs tabu) {
     __shared__ MoveKey s_keys[8];
     __shared__ int s_last;
     Ctl *ctl = tour.ctl;
@@ -358,6 +396,14 @@ __global__ void __launch_bounds__(256) bi_scan_exact_kernel(const InstDev inst, 
             if (p == 0 && q == n - 1) continue;
             const float4 rq = rec[q];
             const int v = node_of(rq), v1 = node_of(rec[q + 1]);
+            if (MASK) {
+                // a = min(u,v) as the reference enumerates the pair; a1 / b1 are the successors of a / b
+                const int a = min(u, v), b = max(u, v);
+                const int a1 = (u < v) ? u1 : v1, b1 = (u < v) ? v1 : u1;
+                if (tabu_check(tabu, udir_pos(a, b, n)) || tabu_check(tabu, udir_pos(a, a1, n)) ||
+                    tabu_check(tabu, udir_pos(b, b1, n)) || tabu_check(tabu, udir_pos(a, b1, n)))
+                    continue;
+            }
             long long delta = dist_nodes(inst, u, v) + dist_nodes(inst, u1, v1) - dsp - (long long)rq.z;
             if (delta < 0 && delta <= best.delta) {
                 MoveKey k;
@@ -429,7 +475,15 @@ cudaError_t launch_bi_scan(const BiArgs &a, int rows_per_thread, int grid, cudaS
 
 cudaError_t launch_bi_scan_exact(const InstDev &inst, const TourDev &tour, int rank, int world, int fuse_apply,
                                  int grid, cudaStream_t st) {
-    bi_scan_exact_kernel<<<grid, 256, 0, st>>>(inst, tour, rank, world, fuse_apply);
+    bi_scan_exact_kernel<false><<<grid, 256, 0, st>>>(inst, tour, rank, world, fuse_apply, TabuArgs{});
+    return cudaGetLastError();
+}
+
+cudaError_t launch_bi_scan_tabu(const InstDev &inst, const TourDev &tour, int *skip, int iter, int tenure, long long *zl,
+                                unsigned long long *zl_count, long long zl_cap, int grid, cudaStream_t st) {
+    TabuArgs t;
+    t.skip = skip; t.iter = iter; t.tenure = tenure; t.zl = zl; t.zl_count = zl_count; t.zl_cap = zl_cap;
+    bi_scan_exact_kernel<true><<<grid, 256, 0, st>>>(inst, tour, 0, 1, 1, t);
     return cudaGetLastError();
 }
 

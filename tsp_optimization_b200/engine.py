@@ -30,7 +30,7 @@ ABI_SYMBOLS = [
     "tspb200_create", "tspb200_destroy", "tspb200_last_error", "tspb200_set_option", "tspb200_get_info",
     "tspb200_set_instance", "tspb200_dist_matrix_build", "tspb200_dist_matrix_get", "tspb200_dist_matrix",
     "tspb200_dist_matrix_free", "tspb200_tour_upload", "tspb200_tour_download", "tspb200_tour_log",
-    "tspb200_bi_run", "tspb200_fi_run", "tspb200_two_opt", "tspb200_two_opt_batch", "tspb200_nn_tour",
+    "tspb200_bi_run", "tspb200_fi_run", "tspb200_two_opt", "tspb200_two_opt_tabu", "tspb200_two_opt_batch", "tspb200_nn_tour",
     "tspb200_tour_costs", "tspb200_comm_unique_id", "tspb200_comm_init", "tspb200_comm_destroy",
     "tspb200_debug_tile_plan",
 ]
@@ -102,6 +102,8 @@ def load_library() -> C.CDLL:
     L.tspb200_fi_run.argtypes = [vp, i64, C.POINTER(_Stats)]
     L.tspb200_two_opt.argtypes = [vp, C.c_int, C.c_void_p, C.POINTER(C.c_double), i64, C.POINTER(_Stats),
                                   C.c_void_p, i64, C.POINTER(i64)]
+    L.tspb200_two_opt_tabu.argtypes = [vp, C.c_void_p, C.POINTER(C.c_double), C.c_void_p, C.c_int, C.c_int, i64,
+                                       C.POINTER(_Stats), C.c_void_p, i64, C.POINTER(i64)]
     L.tspb200_two_opt_batch.argtypes = [vp, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(_Stats)]
     L.tspb200_nn_tour.argtypes = [vp, C.c_int, C.c_void_p, C.POINTER(C.c_double)]
     L.tspb200_tour_costs.argtypes = [vp, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
@@ -245,6 +247,20 @@ class Engine:
         self._ck(self.L.tspb200_two_opt(self.h, mode, succ.ctypes.data, C.byref(o), int(max_iters), C.byref(st),
                                         C.cast(buf, C.c_void_p) if log_cap else None, log_cap, C.byref(cnt)))
         return succ, o.value, Stats.of(st), _moves_to_array(buf, min(log_cap, cnt.value))
+
+    def two_opt_tabu(self, succ, skip_edge, iter_: int, tenure: int, max_iters: int = -1, log_cap: int = 0):
+        """alg_2opt_tabu(inst, skip_edge, NULL, iter, tenure): returns (succ, obj, Stats, log, skip_edge_after)."""
+        succ = np.array(succ, dtype=np.int32, copy=True)
+        skip = np.array(skip_edge, dtype=np.int32, copy=True)
+        assert skip.shape == (self.n * (self.n - 1) // 2,)
+        o = C.c_double(0.0)
+        st = _Stats()
+        buf = (_Move * max(1, log_cap))()
+        cnt = C.c_int64(0)
+        self._ck(self.L.tspb200_two_opt_tabu(self.h, succ.ctypes.data, C.byref(o), skip.ctypes.data, int(iter_), int(tenure),
+                                             int(max_iters), C.byref(st), C.cast(buf, C.c_void_p) if log_cap else None,
+                                             log_cap, C.byref(cnt)))
+        return succ, o.value, Stats.of(st), _moves_to_array(buf, min(log_cap, cnt.value)), skip
 
     def two_opt_batch(self, mode: int, succ_batch, obj=None):
         succ_batch = np.array(succ_batch, dtype=np.int32, copy=True)

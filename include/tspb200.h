@@ -84,7 +84,9 @@ typedef struct {
 int tspb200_create(int device, tspb200_ctx **out);
 void tspb200_destroy(tspb200_ctx *ctx);
 const char *tspb200_last_error(const tspb200_ctx *ctx);
-/* Tuning / mode knobs. keys: "rows_per_thread" (2|4|8|16), "tile_cols" (multiple of 4, 32..1024), "grid" (blocks),
+/* Tuning / mode knobs. keys: "block_threads" (64|128|256), "rows_per_thread" (2|4|8|16), "tile_cols" (multiple of 4,
+ * 32..1024), "grid" (blocks), "fuse_apply" (-1 auto, 0 separate apply launch, 1 the scan's last block applies the move), "seed_hint" (1 = seed each
+ * pass's filter from the previous pass's runner-up moves, 0 = start every pass from delta 0),
  * "force_path" (-1 auto, 0 fp32 filter, 1 exact on the fly, 2 matrix), "batch" (passes per host sync),
  * "time_limit_ms" (<=0 unlimited; checked between launch batches). */
 int tspb200_set_option(tspb200_ctx *ctx, const char *key, int64_t value);
@@ -150,11 +152,12 @@ int tspb200_comm_init(tspb200_ctx *ctx, const void *id128, int rank, int world);
 int tspb200_comm_destroy(tspb200_ctx *ctx);
 
 /* ---- host-only helpers (no device needed) ----------------------------------------------------------- */
-/* Tile plan of the best-improvement scan for (n, R rows per thread, TJ columns per tile); R or TJ == 0 picks
- * the shape the engine would pick for `slots` resident blocks and `world` ranks. row_start: ntr+1 prefix sums
- * of tiles per tile-row; row_j0: first tile column per tile-row. Used by the CPU-side sharding tests. */
-int tspb200_debug_tile_plan(int n, int R, int TJ, int slots, int world, int *out_R, int *out_TJ, int *row_start,
-                            int *row_j0, int cap, int *ntr);
+/* Tile plan of the best-improvement scan for (n, T threads per block, R rows per thread, TJ columns per tile); T, R or
+ * TJ == 0 picks the shape the engine would pick for `num_sms` SMs and `world` ranks. row_start: ntr+1 prefix sums of
+ * tiles per tile-row (a tile-row = T*R tour positions); row_j0: first tile column per tile-row. Used by the CPU-side
+ * sharding tests. */
+int tspb200_debug_tile_plan(int n, int T, int R, int TJ, int num_sms, int world, int *out_T, int *out_R, int *out_TJ,
+                            int *row_start, int *row_j0, int cap, int *ntr);
 
 #ifdef __cplusplus
 }

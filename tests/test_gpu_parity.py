@@ -244,17 +244,26 @@ def test_fi_reference_csv_goldens(engine, instances, goldens, oracle):
         assert sha(s) == g["fi_sha256"] and st.moves == g["fi_moves"] and st.passes == g["fi_sweeps"], nm
 
 
-@pytest.mark.parametrize("R,TJ", [(2, 32), (2, 64), (4, 64), (8, 128), (8, 256), (4, 36), (16, 64)])
-def test_bi_tile_shapes(engine, oracle, R, TJ):
+@pytest.mark.parametrize("T,R,TJ,fuse", [(256, 2, 32, -1), (256, 2, 64, 0), (256, 4, 64, 1), (256, 8, 128, -1), (256, 8, 256, 0),
+                                         (256, 4, 36, 1), (256, 16, 64, -1), (128, 8, 128, 1), (128, 4, 64, 0), (64, 8, 64, 1),
+                                         (64, 8, 128, 0), (64, 4, 32, -1), (64, 2, 64, 1)])
+def test_bi_tile_shapes(engine, oracle, T, R, TJ, fuse):
+    """every supported (block threads, rows per thread) shape, with the move applied by a separate launch (fuse 0) and by
+    the scan kernel's last block (fuse 1)."""
     xy = uniform_instance(1500)
     succ, _ = oracle.nn_tour(xy, 0, 0)
+    engine.set_option("block_threads", T)
     engine.set_option("rows_per_thread", R)
     engine.set_option("tile_cols", TJ)
+    engine.set_option("fuse_apply", fuse)
     try:
         _check_bi(engine, oracle, xy, 0, succ, max_passes=25)
+        assert (engine.info("block_threads"), engine.info("rows_per_thread"), engine.info("tile_cols")) == (T, R, TJ)
     finally:
+        engine.set_option("block_threads", 0)
         engine.set_option("rows_per_thread", 0)
         engine.set_option("tile_cols", 0)
+        engine.set_option("fuse_apply", -1)
 
 
 def test_bi_random_start_and_wraparound_reversals(engine, oracle):

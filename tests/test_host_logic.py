@@ -7,10 +7,9 @@ from tsp_optimization_b200.instances import (is_tour, order_to_succ, random_tour
                                              uniform_instance)
 
 
-def covered_pairs(n, R, TJ, rs, rj, tiles=None):
+def covered_pairs(n, TI, TJ, rs, rj, tiles=None):
     """Set of (p,q) the BI kernel evaluates for the given tile ids (all by default): a pair is evaluated
     by tile (I,J) iff p in its row block, q in its column block and q >= p+2, q <= n-1, not (0, n-1)."""
-    TI = 256 * R
     ntr = len(rj)
     cover = np.zeros((n, n), dtype=np.int32)
     ids = range(int(rs[-1])) if tiles is None else tiles
@@ -28,11 +27,12 @@ def covered_pairs(n, R, TJ, rs, rj, tiles=None):
     return cover
 
 
-@pytest.mark.parametrize("n,R,TJ", [(52, 2, 32), (299, 2, 64), (700, 2, 64), (1500, 4, 64), (2100, 8, 128), (513, 2, 64)])
-def test_tile_plan_covers_every_pair_exactly_once(n, R, TJ):
-    r, tj, rs, rj = tile_plan(n, R, TJ)
-    assert (r, tj) == (R, TJ)
-    cover = covered_pairs(n, R, TJ, rs, rj)
+@pytest.mark.parametrize("n,T,R,TJ", [(52, 256, 2, 32), (299, 64, 2, 64), (700, 256, 2, 64), (1500, 64, 4, 64),
+                                      (2100, 128, 8, 128), (513, 64, 8, 64), (2100, 256, 8, 128), (130, 64, 2, 32)])
+def test_tile_plan_covers_every_pair_exactly_once(n, T, R, TJ):
+    t, r, tj, rs, rj = tile_plan(n, R, TJ, threads=T)
+    assert (t, r, tj) == (T, R, TJ)
+    cover = covered_pairs(n, T * R, TJ, rs, rj)
     want = np.zeros((n, n), dtype=np.int32)
     for p in range(n):
         want[p, p + 2:] = 1
@@ -42,25 +42,28 @@ def test_tile_plan_covers_every_pair_exactly_once(n, R, TJ):
 
 
 def test_tile_plan_round_robin_sharding_partitions_the_tiles():
-    n, R, TJ = 1500, 2, 64
-    _, _, rs, rj = tile_plan(n, R, TJ)
+    n, T, R, TJ = 1500, 64, 4, 64
+    _, _, _, rs, rj = tile_plan(n, R, TJ, threads=T)
     nt = int(rs[-1])
     total = np.zeros((n, n), dtype=np.int32)
     for world in (2, 4, 8):
         total[:] = 0
         for rank in range(world):
-            total += covered_pairs(n, R, TJ, rs, rj, tiles=range(rank, nt, world)) + 0
+            total += covered_pairs(n, T * R, TJ, rs, rj, tiles=range(rank, nt, world)) + 0
         # (0, n-1) is subtracted once per rank by the helper: fix up
         total[0, n - 1] = 0
         assert total.max() == 1 and int(total.sum()) == n * (n - 3) // 2
 
 
-def test_auto_tile_shape_gives_enough_tiles():
-    for n in (10000, 100000):
-        R, TJ, rs, rj = tile_plan(n, 0, 0, slots=296, world=1)
-        assert int(rs[-1]) >= 4 * 296
-    R, TJ, rs, rj = tile_plan(100000, 0, 0, slots=296, world=8)
-    assert int(rs[-1]) >= 4 * 296 * 8
+def test_auto_tile_shape():
+    """the cost model keeps R = 8 (1.125 sqrt per move) from mid-size tours upwards, fills every resident block at least
+    once, and lands on the big-instance shape at n = 100 000."""
+    for n, world in ((10000, 1), (20000, 1), (50000, 2), (100000, 1), (100000, 8)):
+        T, R, TJ, rs, rj = tile_plan(n, world=world)
+        slots = 148 * (512 // T)
+        assert R == 8 and -(-int(rs[-1]) // world) >= slots, (n, world, T, R, TJ)
+    assert tile_plan(100000)[:3] == (256, 8, 256)
+    assert tile_plan(52)[:2] == (64, 2)
 
 
 def test_key_pack_orders_like_the_reference_scan():

@@ -40,8 +40,8 @@ def _worker(rank, world, port, out_dir):
     for step in range(3):
         order = succ_to_order(succ)
         D = orc.dist_matrix(xy, 0).astype(np.int64)
-        R, TJ, rs, rj = tile_plan(n, 2, 64)
-        TI = 256 * R
+        T, R, TJ, rs, rj = tile_plan(n, 2, 64, threads=64)
+        TI = T * R
         best = key_pack(0, 0x1FFFF, 0x1FFFF)
         for t in range(rank, int(rs[-1]), world):
             I = int(np.searchsorted(rs, t, side="right") - 1)

@@ -19,13 +19,14 @@
 namespace tspb {
 
 // ---- launchers implemented in the kernel translation units ---------------------------------------------
-cudaError_t launch_bi_scan(const BiArgs &a, int rows_per_thread, int grid, cudaStream_t st);
+cudaError_t launch_bi_scan(const BiArgs &a, int threads, int rows_per_thread, int grid, bool pdl, cudaStream_t st);
+bool bi_shape_supported(int threads, int rows_per_thread);
 cudaError_t launch_bi_scan_exact(const InstDev &inst, const TourDev &tour, int rank, int world, int fuse_apply, int grid,
                                  cudaStream_t st);
 cudaError_t launch_bi_scan_tabu(const InstDev &inst, const TourDev &tour, int *skip, int iter, int tenure, long long *zl,
                                 unsigned long long *zl_count, long long zl_cap, int grid, cudaStream_t st);
 cudaError_t launch_bi_decode_packed(const TourDev &tour, cudaStream_t st);
-cudaError_t launch_apply_move(const InstDev &inst, const TourDev &tour, int num_sms, cudaStream_t st);
+cudaError_t launch_apply_move(const InstDev &inst, const TourDev &tour, int num_sms, int seed, bool pdl, cudaStream_t st);
 cudaError_t launch_refresh_node_space(const TourDev &tour, int num_sms, cudaStream_t st);
 cudaError_t launch_fi_search(const InstDev &I, const TourDev &T, int grid, cudaStream_t st);
 cudaError_t launch_dist_matrix(const InstDev &I, int *out, long long ld, int row_begin, int row_end, bool fast,
@@ -100,12 +101,14 @@ struct tspb200_ctx {
     double obj_in = 0;
 
     // BI tiling
-    int R = 8, TJ = 256, grid_bi = 296, ntr = 0, ntiles = 0;
+    int T = 256, R = 8, TJ = 256, grid_bi = 296, ntr = 0, ntiles = 0;
     int *d_tile_row_start = nullptr, *d_tile_row_j0 = nullptr;
 
     // options
-    int opt_R = 0, opt_TJ = 0, opt_grid = 0, opt_force_path = -1, opt_batch = 0;
+    int opt_T = 0, opt_R = 0, opt_TJ = 0, opt_grid = 0, opt_force_path = -1, opt_batch = 0, opt_fuse_apply = -1;
     long long opt_time_limit_ms = 0;
+    int opt_seed_hint = 1;
+    int opt_pdl = 1;
 
     // tabu list of the running alg_2opt_tabu call (device copy + indices zeroed by lazy expiry)
     bool tabu_on = false;
@@ -211,6 +214,16 @@ int tspb200_set_option(tspb200_ctx *ctx, const char *key, int64_t value) {
     if (k == "rows_per_thread") {
         if (value != 0 && value != 2 && value != 4 && value != 8 && value != 16) return fail(ctx, TSPB200_E_ARG, "rows_per_thread must be 0 (auto), 2, 4, 8 or 16");
         ctx->opt_R = (int)value;
+    } else if (k == "block_threads") {
+        if (value != 0 && value != 64 && value != 128 && value != 256) return fail(ctx, TSPB200_E_ARG, "block_threads must be 0 (auto), 64, 128 or 256");
+        ctx->opt_T = (int)value;
+    } else if (k == "fuse_apply") {
+        if (value < -1 || value > 1) return fail(ctx, TSPB200_E_ARG, "fuse_apply must be -1 (auto), 0 or 1");
+        ctx->opt_fuse_apply = (int)value;
+    } else if (k == "pdl") {
+        ctx->opt_pdl = value ? 1 : 0;
+    } else if (k == "seed_hint") {
+        ctx->opt_seed_hint = value < 0 ? 0 : (value > 2 ? 2 : (int)value);
     } else if (k == "tile_cols") {
         if (value != 0 && (value < 32 || value > 1024 || (value & 3))) return fail(ctx, TSPB200_E_ARG, "tile_cols must be 0 (auto) or a multiple of 4 in [32,1024]");
         ctx->opt_TJ = (int)value;
@@ -235,6 +248,7 @@ int64_t tspb200_get_info(const tspb200_ctx *ctx, const char *key) {
     if (k == "num_sms") return ctx->num_sms;
     if (k == "n") return ctx->n;
     if (k == "rows_per_thread") return ctx->R;
+    if (k == "block_threads") return ctx->T;
     if (k == "tile_cols") return ctx->TJ;
     if (k == "grid_bi") return ctx->grid_bi;
     if (k == "ntiles") return ctx->ntiles;
@@ -244,6 +258,7 @@ int64_t tspb200_get_info(const tspb200_ctx *ctx, const char *key) {
     if (k == "window_x1000") return (int64_t)(ctx->inst.W * 1000.0f);
     if (k == "matrix_resident") return ctx->d_mat != nullptr;
     if (k == "matrix_ld") return ctx->mat_ld;
+    if (k == "cold_calls") return ctx->h_ctl ? (int64_t)ctx->h_ctl->cold_calls : -1;  // as of the last host sync
     if (k == "world") return ctx->world;
     if (k == "rank") return ctx->rank;
     return -1;
@@ -376,10 +391,9 @@ static InstDev inst_for_path(const tspb200_ctx *ctx, int path) {
 }
 
 // Tile plan of the best-improvement scan (pure host arithmetic, also exported for the CPU-side tests).
-// Tile-row I covers positions [I*TI, (I+1)*TI), TI = 256*R; its tile columns are J0(I)..(n-1)/TJ with
-// J0(I) = (I*TI + 2) / TJ, i.e. every column block that can hold a q >= p+2 for some p of the row.
-static long long tile_plan(int n, int R, int TJ, std::vector<int> *row_start, std::vector<int> *row_j0) {
-    const int TI = 256 * R;
+// Tile-row I covers positions [I*TI, (I+1)*TI), TI = T*R (threads per block x rows per thread); its tile columns are
+// J0(I)..(n-1)/TJ with J0(I) = (I*TI + 2) / TJ, i.e. every column block that can hold a q >= p+2 for some p of the row.
+static long long tile_plan(int n, int TI, int TJ, std::vector<int> *row_start, std::vector<int> *row_j0) {
     const int ntr = n >= 4 ? (n - 2 + TI - 1) / TI : 0;
     long long total = 0;
     if (row_start) { row_start->clear(); row_j0->clear(); }
@@ -393,45 +407,61 @@ static long long tile_plan(int n, int R, int TJ, std::vector<int> *row_start, st
     return total;
 }
 
-// picks (R, TJ): the largest tile shape that still gives every resident block >= 4 tiles per rank
-static void choose_tile_shape(int n, int slots, int world, int opt_R, int opt_TJ, int *R, int *TJ) {
-    const int cand_r[] = {8, 4, 2};
-    const int cand_tj[] = {256, 128, 64};
-    for (int a = 0; a < 3; ++a) {
-        int r = opt_R ? opt_R : cand_r[a];
-        for (int b = 0; b < 3; ++b) {
-            int tj = opt_TJ ? opt_TJ : cand_tj[b];
-            if (tile_plan(n, r, tj, nullptr, nullptr) >= 4ll * slots * world) { *R = r; *TJ = tj; return; }
+// Picks (T, R, TJ) by a small cost model.  Every shape keeps 16 warps per SM (slots = SMs * 512/T blocks); a pass takes
+// `waves` = ceil(tiles per rank / slots) rounds of tiles, and one tile costs a thread (TJ + OV) column steps of R+1
+// square roots each (OV ~ the row loads, first column and end-of-tile barrier).  Big instances end up at 256 x 8 x 256
+// (fewest sqrt per move, fewest tiles); mid-size ones (n ~ 10^4: ~700 evaluations per thread and pass) at 64-thread
+// blocks with R = 8 and a tile width that fills the 148 SMs in one wave.
+static void choose_tile_shape(int n, int num_sms, int world, int opt_T, int opt_R, int opt_TJ, int *T, int *R, int *TJ) {
+    struct Shape { int t, r; };
+    const Shape cand[] = {{256, 8}, {128, 8}, {64, 8}, {64, 4}, {64, 2}};
+    const double OV = 16.0;
+    double best = 1e300;
+    int bt = 64, br = 2, btj = 32;
+    for (const Shape &c : cand) {
+        const int t = opt_T ? opt_T : c.t, r = opt_R ? opt_R : c.r;
+        if (!bi_shape_supported(t, r)) continue;
+        const long long slots = (long long)num_sms * (r >= 16 ? 1 : 512 / t);
+        for (int tj = 32; tj <= 256; tj += 8) {
+            const int tjj = opt_TJ ? opt_TJ : tj;
+            const long long nt = tile_plan(n, t * r, tjj, nullptr, nullptr);
+            const long long per_rank = (nt + world - 1) / world;
+            const long long waves = (per_rank + slots - 1) / slots;
+            const double cost = (double)waves * (tjj + OV) * (r + 1) * (r >= 16 ? 2.0 : 1.0) * (1.0 + 0.02 * (256 / t - 1));
+            if (cost < best) { best = cost; bt = t; br = r; btj = tjj; }
+            if (opt_TJ) break;
         }
     }
-    *R = opt_R ? opt_R : 2;
-    *TJ = opt_TJ ? opt_TJ : 64;
+    *T = bt; *R = br; *TJ = btj;
 }
 
 static void plan_tiles(tspb200_ctx *ctx, std::vector<int> &row_start, std::vector<int> &row_j0) {
-    const int slots = 2 * ctx->num_sms;
-    choose_tile_shape(ctx->n, slots, ctx->world, ctx->opt_R, ctx->opt_TJ, &ctx->R, &ctx->TJ);
-    ctx->ntiles = (int)tile_plan(ctx->n, ctx->R, ctx->TJ, &row_start, &row_j0);
+    choose_tile_shape(ctx->n, ctx->num_sms, ctx->world, ctx->opt_T, ctx->opt_R, ctx->opt_TJ, &ctx->T, &ctx->R, &ctx->TJ);
+    const int slots = ctx->num_sms * (ctx->R >= 16 ? 1 : 512 / ctx->T);
+    ctx->ntiles = (int)tile_plan(ctx->n, ctx->T * ctx->R, ctx->TJ, &row_start, &row_j0);
     ctx->ntr = (int)row_j0.size();
     long long per_rank = (ctx->ntiles + ctx->world - 1) / ctx->world;
     int grid = ctx->opt_grid > 0 ? ctx->opt_grid : slots;
     if (grid > per_rank) grid = (int)(per_rank > 0 ? per_rank : 1);
+    if (grid > 4096) grid = 4096;  // block_best[] capacity
     ctx->grid_bi = grid;
 }
 
-// Host-only helper (no device needed): the tile plan for (n, R, TJ); R or TJ == 0 -> automatic choice for
-// `slots` resident blocks and `world` ranks. row_start gets ntr+1 entries, row_j0 ntr entries.
-int tspb200_debug_tile_plan(int n, int R, int TJ, int slots, int world, int *out_R, int *out_TJ, int *row_start,
-                            int *row_j0, int cap, int *ntr) {
-    if (n < 1 || slots < 1 || world < 1) return TSPB200_E_ARG;
-    int r = R, tj = TJ;
-    if (r == 0 || tj == 0) choose_tile_shape(n, slots, world, R, TJ, &r, &tj);
+// Host-only helper (no device needed): the tile plan for (n, T, R, TJ); T, R or TJ == 0 -> automatic choice for
+// `num_sms` SMs and `world` ranks. row_start gets ntr+1 entries, row_j0 ntr entries.
+int tspb200_debug_tile_plan(int n, int T, int R, int TJ, int num_sms, int world, int *out_T, int *out_R, int *out_TJ,
+                            int *row_start, int *row_j0, int cap, int *ntr) {
+    if (n < 1 || num_sms < 1 || world < 1) return TSPB200_E_ARG;
+    int t = T, r = R, tj = TJ;
+    if (t == 0 || r == 0 || tj == 0) choose_tile_shape(n, num_sms, world, T, R, TJ, &t, &r, &tj);
+    if (!bi_shape_supported(t, r)) return TSPB200_E_ARG;
     std::vector<int> rs, rj;
-    tile_plan(n, r, tj, &rs, &rj);
+    tile_plan(n, t * r, tj, &rs, &rj);
     if ((int)rs.size() > cap) return TSPB200_E_ARG;
     for (size_t k = 0; k < rs.size(); ++k) row_start[k] = rs[k];
     for (size_t k = 0; k < rj.size(); ++k) row_j0[k] = rj[k];
     if (ntr) *ntr = (int)rj.size();
+    if (out_T) *out_T = t;
     if (out_R) *out_R = r;
     if (out_TJ) *out_TJ = tj;
     return TSPB200_OK;
@@ -458,7 +488,7 @@ int tspb200_tour_upload(tspb200_ctx *ctx, const int32_t *succ, int64_t log_cap) 
     }
     std::vector<int> row_start, row_j0;
     plan_tiles(ctx, row_start, row_j0);
-    const int TI = 256 * ctx->R;
+    const int TI = ctx->T * ctx->R;
     const int alloc = ((n + TI - 1) / TI) * TI + TI + 1024 + 16;
     if (!ctx->has_tour || ctx->tour.alloc != alloc || ctx->log_cap != log_cap) {
         free_tour(ctx);
@@ -494,6 +524,7 @@ int tspb200_tour_upload(tspb200_ctx *ctx, const int32_t *succ, int64_t log_cap) 
     c0.last.i = c0.last.j = 0x7fffffff;
     *ctx->h_ctl = c0;
     CK(cudaMemcpyAsync(ctx->d_ctl, ctx->h_ctl, sizeof(Ctl), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(ctx->tour.block_best, 0, sizeof(MoveKey) * 4096, ctx->stream));  // delta 0 = "no previous winner"
     InstDev I = inst_for_path(ctx, select_path(ctx));
     CK(launch_build_state(I, ctx->tour, ctx->d_order, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -564,7 +595,13 @@ int tspb200_bi_run(tspb200_ctx *ctx, int64_t max_passes, tspb200_stats *st) {
     a.TJ = ctx->TJ;
     a.rank = ctx->rank;
     a.world = ctx->world;
-    a.fuse_apply = ctx->world == 1 ? 1 : 0;
+    // 2 = the scan kernel's last block also applies the move (mid-size tours: a launch costs more than the swap)
+    const bool fuse_in_kernel = ctx->world == 1 && path == 0 && !ctx->tabu_on &&
+                                (ctx->opt_fuse_apply >= 0 ? ctx->opt_fuse_apply == 1 : false);
+    a.fuse_apply = ctx->world == 1 ? (fuse_in_kernel ? 2 : 1) : 0;
+    a.seed_hint = ctx->opt_seed_hint;
+    // programmatic dependent launch between the scan and apply kernels of one GPU's pass loop (no NCCL op in between)
+    const bool pdl = ctx->world == 1 && path == 0 && !ctx->tabu_on && ctx->opt_pdl;
     int rc = sync_ctl(ctx);
     if (rc) return rc;
     const long long passes0 = ctx->h_ctl->passes, moves0 = ctx->h_ctl->moves, launches0 = ctx->h_ctl->launches,
@@ -572,7 +609,8 @@ int tspb200_bi_run(tspb200_ctx *ctx, int64_t max_passes, tspb200_stats *st) {
     int exact_grid = ctx->opt_grid > 0 ? ctx->opt_grid : 4 * ctx->num_sms;
     if (exact_grid > n) exact_grid = n > 0 ? n : 1;
     // passes per host round trip: large instances run for milliseconds per pass, small ones for microseconds
-    long long batch = ctx->opt_batch > 0 ? ctx->opt_batch : (n >= 50000 ? 8 : (n >= 5000 ? 64 : 256));
+    const long long batch_cap = ctx->opt_batch > 0 ? ctx->opt_batch : (n >= 50000 ? 8 : (n >= 5000 ? 64 : 256));
+    long long batch = ctx->opt_batch > 0 ? ctx->opt_batch : 8;  // grows: short runs (TSPLIB-size tours) stop after a few passes
     long long host_launches = 0;
     int status = TSPB200_LOCAL_OPTIMUM;
     auto t_start = std::chrono::steady_clock::now();
@@ -589,7 +627,7 @@ int tspb200_bi_run(tspb200_ctx *ctx, int64_t max_passes, tspb200_stats *st) {
             if (ctx->tabu_on)
                 CK(launch_bi_scan_tabu(I, ctx->tour, ctx->d_skip, ctx->tabu_iter, ctx->tabu_tenure, ctx->d_zl, ctx->d_zl_count,
                                        ctx->zl_cap, exact_grid, ctx->stream));
-            else if (path == 0) CK(launch_bi_scan(a, ctx->R, ctx->grid_bi, ctx->stream));
+            else if (path == 0) CK(launch_bi_scan(a, ctx->T, ctx->R, ctx->grid_bi, pdl, ctx->stream));
             else CK(launch_bi_scan_exact(I, ctx->tour, ctx->rank, ctx->world, a.fuse_apply, exact_grid, ctx->stream));
             host_launches++;
             if (ctx->world > 1) {
@@ -599,10 +637,13 @@ int tspb200_bi_run(tspb200_ctx *ctx, int64_t max_passes, tspb200_stats *st) {
                 CK(launch_bi_decode_packed(ctx->tour, ctx->stream));
                 host_launches++;
             }
-            CK(launch_apply_move(I, ctx->tour, ctx->num_sms, ctx->stream));
-            host_launches++;
+            if (!fuse_in_kernel) {
+                CK(launch_apply_move(I, ctx->tour, ctx->num_sms, (path == 0 && ctx->opt_seed_hint >= 2) ? 1 : 0, pdl, ctx->stream));
+                host_launches++;
+            }
         }
         if (max_passes >= 0) remaining -= k;
+        if (batch < batch_cap) batch = batch * 2 < batch_cap ? batch * 2 : batch_cap;
         rc = sync_ctl(ctx);
         if (rc) return rc;
         done = ctx->h_ctl->done != 0;
@@ -665,7 +706,7 @@ int tspb200_fi_run(tspb200_ctx *ctx, int64_t max_moves, tspb200_stats *st) {
         while (!done) {
             for (long long q = 0; q < batch; ++q) {
                 CK(launch_fi_search(I, ctx->tour, grid, ctx->stream));
-                CK(launch_apply_move(I, ctx->tour, ctx->num_sms, ctx->stream));
+                CK(launch_apply_move(I, ctx->tour, ctx->num_sms, 0, false, ctx->stream));
                 CK(launch_refresh_node_space(ctx->tour, ctx->num_sms, ctx->stream));
                 host_launches += 3;
             }

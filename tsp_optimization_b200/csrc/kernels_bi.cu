@@ -19,7 +19,6 @@
 namespace tspb {
 
 
-constexpr int BI_THREADS = 256;
 
 template <bool ATT>
 __device__ __forceinline__ float dist32(float ax, float ay, float bx, float by) {
@@ -49,85 +48,119 @@ __device__ __forceinline__ void column_dists(const f32x2 (&xr2)[R / 2], const f3
 }
 
 // ---- cold path ------------------------------------------------------------------------------------------
-// Exact re-evaluation of the pairs (rows p0..p0+R-1) x (columns Q0+jj0 .. Q0+jj0+ncols-1) of one thread after its
-// FP32 filter fired somewhere in that column block.  Everything is re-read from memory (row records from L2,
-// column records from shared memory), so the hot loop keeps no per-pair state alive for it.  For each pair the
-// FP32 filter is applied again; pairs that pass get the reference's exact integer delta (FP64, reference
-// src/tabusearch.c:150 / src/distutil.c) and are folded into the running (delta, i, j) minimum.
-// Not inlined; the running best goes in and out by value so that it stays in registers in the caller.
-template <bool ATT, bool EXACT32>
-__device__ __noinline__ MoveKey bi_cold_block(const InstDev I, const float4 *rec, const float4 *sc, int n, int p0, int R,
-                                              int Q0, int jj0, int ncols, float thr, MoveKey best) {
-    const float W = I.W;
-    for (int r = 0; r < R; ++r) {
-        const int p = p0 + r;
-        const float4 rp = rec[p], rp1 = rec[p + 1];
-        const float cp = -rp.z;
-        for (int c = 0; c < ncols; ++c) {
-            const int q = Q0 + jj0 + c;
-            if (q < p + 2 || q > n - 1 || (p == 0 && q == n - 1)) continue;  // reference tabusearch.c:134
+// Exact re-evaluation of one filter hit: the R x BI_CB pairs (rows p0..p0+R-1) x (columns Q0+jj0 .. +BI_CB-1) of ONE
+// thread whose FP32 block minimum passed the threshold.  WARP-COOPERATIVE: the whole warp is converged at the call (the
+// hot loop has no divergent branch, the hit test is a ballot), so the 32 lanes take one pair each — row and column
+// records come from shared memory — re-apply the FP32 filter, evaluate the survivors exactly (FP64 with the reference's
+// operation order, reference src/tabusearch.c:150 / src/distutil.c) and reduce the best exact (delta, i, j) key with
+// shuffles.  A hit costs a few hundred cycles instead of a serial walk over 32 pairs by a single lane.
+constexpr int BI_CB = 4;  // columns per filter check
+
+template <int R, bool ATT, bool EXACT32>
+__device__ __noinline__ MoveKey bi_cold_warp(const InstDev I, const float4 *srow, const float4 *sc, int n, int P0, int p0,
+                                             int Q0, int jj0, float thr) {
+    const int lane = threadIdx.x & 31;
+    MoveKey best = key_none();
+#pragma unroll 1
+    for (int base = 0; base < R * BI_CB; base += 32) {
+        const int idx = base + lane;
+        const int r = idx / BI_CB, c = idx % BI_CB;
+        const int p = p0 + r, q = Q0 + jj0 + c;
+        if (idx < R * BI_CB && q >= p + 2 && q <= n - 1 && !(p == 0 && q == n - 1)) {  // reference tabusearch.c:134
+            const float4 rp = srow[p - P0], rp1 = srow[p - P0 + 1];
             const float4 c0 = sc[jj0 + c], c1 = sc[jj0 + c + 1];
-            const float qv = (dist32<ATT>(rp.x, rp.y, c0.x, c0.y) + cp) + dist32<ATT>(rp1.x, rp1.y, c1.x, c1.y);
-            if (!(qv <= thr + c0.z)) continue;
-            const int u = node_of(rp), v = node_of(c0);
-            long long d1, d2;
-            if (EXACT32) {
-                d1 = exact_dist(I.metric, make_double2((double)rp.x, (double)rp.y), make_double2((double)c0.x, (double)c0.y));
-                d2 = exact_dist(I.metric, make_double2((double)rp1.x, (double)rp1.y), make_double2((double)c1.x, (double)c1.y));
-            } else {
-                d1 = exact_dist(I.metric, I.pt64[u], I.pt64[v]);
-                d2 = exact_dist(I.metric, I.pt64[node_of(rp1)], I.pt64[node_of(c1)]);
-            }
-            const long long delta = d1 + d2 - (long long)rp.z - (long long)c0.z;
-            if (delta < 0 && delta <= (long long)best.delta) {
-                MoveKey k;
-                k.delta = (int)delta; k.i = min(u, v); k.j = max(u, v); k.pad = 0;
-                if (key_less(k, best)) {
-                    best = k;
-                    thr = fminf(thr, (float)k.delta + W);
+            const float qv = (dist32<ATT>(rp.x, rp.y, c0.x, c0.y) - rp.z) + dist32<ATT>(rp1.x, rp1.y, c1.x, c1.y);
+            if (qv <= thr + c0.z) {
+                const int u = node_of(rp), v = node_of(c0);
+                long long d1, d2;
+                if (EXACT32) {
+                    d1 = exact_dist(I.metric, make_double2((double)rp.x, (double)rp.y), make_double2((double)c0.x, (double)c0.y));
+                    d2 = exact_dist(I.metric, make_double2((double)rp1.x, (double)rp1.y), make_double2((double)c1.x, (double)c1.y));
+                } else {
+                    d1 = exact_dist(I.metric, I.pt64[u], I.pt64[v]);
+                    d2 = exact_dist(I.metric, I.pt64[node_of(rp1)], I.pt64[node_of(c1)]);
+                }
+                const long long delta = d1 + d2 - (long long)rp.z - (long long)c0.z;
+                if (delta < 0) {
+                    MoveKey k;
+                    k.delta = (int)delta; k.i = min(u, v); k.j = max(u, v); k.pad = 0;
+                    if (key_less(k, best)) best = k;
                 }
             }
         }
     }
-    return best;
+    __syncwarp();
+    return key_warp_min(best);
 }
 
-constexpr int BI_CB = 4;  // columns per filter check
-
-template <int R, bool ATT, bool EXACT32>
-__global__ void __launch_bounds__(BI_THREADS, (R >= 16 ? 1 : 2)) bi_scan_kernel(const BiArgs A) {
+// BI_THREADS x R rows per tile: 256 x 8 for big instances; smaller blocks (64 / 128 threads, up to 8 per SM) give
+// mid-size instances (n ~ 10^4: only ~20 k evaluations per warp and pass) enough tiles to fill 148 SMs while keeping
+// R = 8 rows per thread, i.e. 1.125 sqrt per evaluated move.
+//
+// Shared memory per block (dynamic): two column buffers (TJ+2 records) and two row buffers (BI_THREADS*R+1 records),
+// each pair filled by TMA bulk copies on one mbarrier per stage, plus the tile tables.
+template <int BI_THREADS, int R, bool ATT, bool EXACT32>
+__global__ void __launch_bounds__(BI_THREADS, (R >= 16 ? 1 : 512 / BI_THREADS)) bi_scan_kernel(const BiArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long bars[2];
     __shared__ int s_hint;
     __shared__ int s_last;
     __shared__ MoveKey s_keys[BI_THREADS / 32];
+    __shared__ int s_ap[2];
 
     Ctl *ctl = A.tour.ctl;
-    if (ctl->done) {
-        if (blockIdx.x == 0 && threadIdx.x == 0) ctl->ap_valid = 0;
-        return;
-    }
-
     const int tid = threadIdx.x;
+    // Programmatic dependent launch: let the apply kernel queue up behind us right away, and do everything that does not
+    // depend on the previous kernel (barrier init, the static tile tables) before waiting for it.
+    pdl_launch_dependents();
     const int n = A.inst.n;
     const int TJ = A.TJ;
-    const int TI = BI_THREADS * R;
+    constexpr int TI = BI_THREADS * R;
     const float W = A.inst.W;
     const float4 *rec = A.tour.rec;
     float4 *scols0 = reinterpret_cast<float4 *>(smem_raw);
     float4 *scols1 = scols0 + (TJ + 2);
+    float4 *srows0 = scols1 + (TJ + 2);
+    float4 *srows1 = srows0 + (TI + 2);
     const unsigned col_bytes = (unsigned)(TJ + 1) * 16u;
+    constexpr unsigned row_bytes = (unsigned)(TI + 1) * 16u;
 
+    // tile tables -> shared memory (one coalesced L2 round trip instead of a dependent chain per binary-search step)
+    int *s_rs = reinterpret_cast<int *>(srows1 + (TI + 2));  // [ntr+1] prefix sums of tiles per tile-row
+    int *s_rj = s_rs + (A.ntr + 1);                          // [ntr]   first tile column of each tile-row
+    for (int k = tid; k <= A.ntr; k += BI_THREADS) {
+        s_rs[k] = A.tile_row_start[k];
+        if (k < A.ntr) s_rj[k] = A.tile_row_j0[k];
+    }
     if (tid == 0) {
         mbar_init(&bars[0], 1);
         mbar_init(&bars[1], 1);
         mbar_fence_init();
-        s_hint = *((volatile int *)&ctl->hint);
+    }
+    pdl_wait();  // the previous kernel of the stream (apply / upload) is complete and its writes are visible
+    const int done = *((volatile int *)&ctl->done);
+    if (tid == 0) s_hint = *((volatile int *)&ctl->hint);
+    if (done) {  // local optimum already reached: later launches of the same batch return at once
+        if (blockIdx.x == 0 && tid == 0) ctl->ap_valid = 0;
+        return;
     }
     __syncthreads();
 
+    // This block's own winner of the previous pass is most likely still a legal move: its exact delta now is a valid
+    // bound for this pass (see seed_hint_from_candidates).  One thread re-evaluates it while the first tile is in
+    // flight; the result tightens s_hint / ctl->hint asynchronously.
+    if (A.seed_hint && tid == BI_THREADS - 32) {
+        const MoveKey c = key_load_cg(&A.tour.block_best[blockIdx.x]);
+        const long long d = legal_move_delta_cg(A.inst, A.tour, c);
+        if (d < 0) {
+            atomicMin(&s_hint, (int)d);
+            atomicMin(&ctl->hint, (int)d);
+        }
+    }
+
     MoveKey best = key_none();
     float thr = (float)s_hint + W;
+    int pend_hint = 0;  // tid 0: value of ctl->hint fetched 64 columns ago
 
     const int first = A.rank + A.world * (int)blockIdx.x;
     const int stride = A.world * (int)gridDim.x;
@@ -137,36 +170,38 @@ __global__ void __launch_bounds__(BI_THREADS, (R >= 16 ? 1 : 2)) bi_scan_kernel(
         int lo = 0, hi = A.ntr - 1;
         while (lo < hi) {
             int mid = (lo + hi + 1) >> 1;
-            if (A.tile_row_start[mid] <= t) lo = mid; else hi = mid - 1;
+            if (s_rs[mid] <= t) lo = mid; else hi = mid - 1;
         }
         P0 = lo * TI;
-        Q0 = (A.tile_row_j0[lo] + (t - A.tile_row_start[lo])) * TJ;
+        Q0 = (s_rj[lo] + (t - s_rs[lo])) * TJ;
+    };
+    auto stage = [&](int b, int P0, int Q0) {  // thread 0: both bulk copies of one stage on one mbarrier
+        mbar_expect_tx(&bars[b], col_bytes + row_bytes);
+        tma_load_1d(b ? scols1 : scols0, rec + Q0, col_bytes, &bars[b]);
+        tma_load_1d(b ? srows1 : srows0, rec + P0, row_bytes, &bars[b]);
     };
 
     int t = first;
     int P0 = 0, Q0 = 0;
     if (t < A.ntiles) {
         decode(t, P0, Q0);
-        if (tid == 0) {
-            mbar_expect_tx(&bars[0], col_bytes);
-            tma_load_1d(scols0, rec + Q0, col_bytes, &bars[0]);
-        }
+        if (tid == 0) stage(0, P0, Q0);
     }
 
     for (int it = 0; t < A.ntiles; ++it) {
         const int buf = it & 1;
         const unsigned parity = (unsigned)(it >> 1) & 1u;
-        float4 *sc = buf ? scols1 : scols0;
-        // prefetch the next tile's columns into the other buffer
+        const float4 *sc = buf ? scols1 : scols0;
+        const float4 *srow = buf ? srows1 : srows0;
+        // prefetch the next tile into the other stage
         const int tn = t + stride;
         int P0n = 0, Q0n = 0;
         if (tn < A.ntiles) {
             decode(tn, P0n, Q0n);
-            if (tid == 0) {
-                mbar_expect_tx(&bars[buf ^ 1], col_bytes);
-                tma_load_1d(buf ? scols0 : scols1, rec + Q0n, col_bytes, &bars[buf ^ 1]);
-            }
+            if (tid == 0) stage(buf ^ 1, P0n, Q0n);
         }
+
+        mbar_wait(&bars[buf], parity);
 
         // rows of this thread: p0 .. p0+R-1 in packed pairs (+ successor row p0+R, scalar)
         const int p0 = P0 + tid * R;
@@ -174,7 +209,7 @@ __global__ void __launch_bounds__(BI_THREADS, (R >= 16 ? 1 : 2)) bi_scan_kernel(
         float xrl, yrl;
 #pragma unroll
         for (int k = 0; k < R / 2; ++k) {
-            float4 v0 = rec[p0 + 2 * k], v1 = rec[p0 + 2 * k + 1];
+            const float4 v0 = srow[tid * R + 2 * k], v1 = srow[tid * R + 2 * k + 1];
             // "+ 0" is a real FADD2 (not an identity for -0.0, so it is never folded): its 64-bit result is an aligned
             // register pair that stays live across the column loop, instead of being re-packed with MOVs per step
             const f32x2 zero2 = f2pack(0.f, 0.f);
@@ -183,13 +218,11 @@ __global__ void __launch_bounds__(BI_THREADS, (R >= 16 ? 1 : 2)) bi_scan_kernel(
             cp2[k] = f2sub(zero2, f2pack(v0.z, v1.z));  // padding rows carry ds = -BIG -> cp = +BIG -> never a candidate
         }
         {
-            float4 v = rec[p0 + R];
+            const float4 v = srow[tid * R + R];
             xrl = v.x;
             yrl = v.y;
         }
         thr = fminf(thr, (float)(*((volatile int *)&s_hint)) + W);
-
-        mbar_wait(&bars[buf], parity);
 
         // pairs with q < p+2 exist in this tile?  (mask them; they are mirrored / adjacent pairs)
         const bool diag = (Q0 < P0 + TI + 1);
@@ -223,20 +256,38 @@ __global__ void __launch_bounds__(BI_THREADS, (R >= 16 ? 1 : 2)) bi_scan_kernel(
         c0 = c1;                                                                                       \
     }
 
-// BI_CB columns, then ONE filter check; on a hit the cold path re-evaluates exactly that column block
+// BI_CB columns, then ONE filter check per warp (ballot); hits are resolved one lane at a time by the whole warp
 #define BI_BLOCK(DIAG)                                                                                 \
     for (int jj = 0; jj < TJ; jj += BI_CB) {                                                           \
         float M = TSPB_BIG;                                                                            \
         _Pragma("unroll") for (int c = 0; c < BI_CB; ++c) BI_COL(DIAG, jj + c)                         \
-        if (M <= thr) {                                                                                \
-            const MoveKey nb = bi_cold_block<ATT, EXACT32>(A.inst, rec, sc, n, p0, R, Q0, jj, BI_CB, thr, best); \
-            if (key_less(nb, best)) {                                                                  \
-                best = nb;                                                                             \
-                thr = fminf(thr, (float)nb.delta + W);                                                 \
-                atomicMin(&s_hint, nb.delta);                                                          \
+        unsigned hits = __ballot_sync(0xffffffffu, M <= thr);                                          \
+        while (hits) {                                                                                 \
+            const int L = __ffs(hits) - 1;                                                             \
+            const float thrL = __shfl_sync(0xffffffffu, thr, L);                                       \
+            const MoveKey nb = bi_cold_warp<R, ATT, EXACT32>(A.inst, srow, sc, n, P0, P0 + ((tid & ~31) + L) * R, Q0, jj, thrL); \
+            if ((tid & 31) == L) {                                                                     \
+                atomicAdd(&ctl->cold_calls, 1ull);                                                     \
+                if (key_less(nb, best)) {                                                              \
+                    best = nb;                                                                         \
+                    atomicMin(&s_hint, nb.delta);                                                      \
+                    atomicMin(&ctl->hint, nb.delta);                                                   \
+                }                                                                                      \
             }                                                                                          \
+            /* an exact delta of a real move bounds the minimum for every lane: tighten all, drop stale hits */ \
+            if (nb.delta < 0) thr = fminf(thr, (float)nb.delta + W);                                   \
+            hits &= hits - 1;                                                                          \
+            hits &= __ballot_sync(0xffffffffu, M <= thr);                                              \
         }                                                                                              \
-        if ((jj & 63) == 64 - BI_CB) thr = fminf(thr, (float)(*((volatile int *)&s_hint)) + W);        \
+        /* every 64 columns: pick up what the other warps / blocks found (tid 0 swaps in the ctl->hint value it */ \
+        /* requested 64 columns ago, so nobody waits for L2)                                                    */ \
+        if ((jj & 63) == 64 - BI_CB) {                                                                 \
+            if (tid == 0) {                                                                            \
+                if (pend_hint < 0) atomicMin(&s_hint, pend_hint);                                      \
+                pend_hint = __ldcg(&ctl->hint);                                                        \
+            }                                                                                          \
+            thr = fminf(thr, (float)(*((volatile int *)&s_hint)) + W);                                 \
+        }                                                                                              \
     }
 
         const int qrel0 = Q0 - p0;  // q - p0 at jj = 0
@@ -250,7 +301,7 @@ __global__ void __launch_bounds__(BI_THREADS, (R >= 16 ? 1 : 2)) bi_scan_kernel(
 #undef BI_COL
 #undef UU
 
-        __syncthreads();  // every thread is done with sc[] before the next prefetch overwrites it
+        __syncthreads();  // every thread is done with this stage before the next prefetch overwrites it
         if (tid == 0) {
             // exchange the best exact delta with the other blocks (only ever tightens the filter)
             int h = s_hint;
@@ -280,20 +331,32 @@ __global__ void __launch_bounds__(BI_THREADS, (R >= 16 ? 1 : 2)) bi_scan_kernel(
     if (!s_last) return;
     __threadfence();
 
-    MoveKey k = key_none();
+    MoveKey mine = key_none();
     for (int b = tid; b < (int)gridDim.x; b += BI_THREADS) {
         MoveKey o = key_load_cg(&A.tour.block_best[b]);
-        if (key_less(o, k)) k = o;
+        if (key_less(o, mine)) mine = o;
     }
-    k = key_warp_min(k);
-    if ((tid & 31) == 0) s_keys[tid >> 5] = k;
-    __syncthreads();
-    k = s_keys[0];
+    // CTL_NCAND rounds of "block-wide minimum, then retire it": round 0 is the winner of the pass, the rest are
+    // runner-ups kept as seeds for the next pass's filter (seed_hint_from_candidates)
+    MoveKey k = key_none();
+#pragma unroll 1
+    const int rounds = (A.seed_hint >= 2) ? CTL_NCAND : 1;
+    for (int round = 0; round < rounds; ++round) {
+        MoveKey m = key_warp_min(mine);
+        if ((tid & 31) == 0) s_keys[tid >> 5] = m;
+        __syncthreads();
+        m = s_keys[0];
 #pragma unroll
-    for (int w = 1; w < BI_THREADS / 32; ++w)
-        if (key_less(s_keys[w], k)) k = s_keys[w];
+        for (int w = 1; w < BI_THREADS / 32; ++w)
+            if (key_less(s_keys[w], m)) m = s_keys[w];
+        __syncthreads();
+        if (round == 0) k = m;
+        if (tid == 0) ctl->cand[round] = m;
+        if (m.delta < 0 && mine.i == m.i && mine.j == m.j) mine = key_none();
+    }
 
     if (tid == 0) {
+        ctl->ncand = rounds;
         ctl->last = k;
         ctl->ticket = 0;
         ctl->hint = 0;
@@ -305,7 +368,19 @@ __global__ void __launch_bounds__(BI_THREADS, (R >= 16 ? 1 : 2)) bi_scan_kernel(
             ctl->passes += 1;
             publish_move(A.tour, k.i, k.j, k.delta);
             if (k.delta >= 0) ctl->done = 1;  // reference src/tabusearch.c:158: mindelta >= 0 -> stop
+            s_ap[0] = ctl->ap_pa;
+            s_ap[1] = ctl->ap_pb;
         }
+    }
+    // fuse_apply == 2: this (last) block also applies the move, saving the apply launch — every other block has
+    // finished reading rec[] before it took its ticket.  Used for mid-size tours where a launch costs more than the swap.
+    if (A.fuse_apply == 2 && k.delta < 0) {
+        __syncthreads();
+        apply_swap_range(A.inst, A.tour, s_ap[0], s_ap[1], tid, BI_THREADS);
+        if (tid == 0) ctl->ap_valid = 0;
+        __threadfence();
+        __syncthreads();
+        if (A.seed_hint) seed_hint_from_candidates(A.inst, A.tour, tid);
     }
 }
 
@@ -322,10 +397,26 @@ __global__ void bi_decode_packed_kernel(const TourDev tour) {
 }
 
 // Grid-wide application of the published move (see apply_swap_range).
-__global__ void __launch_bounds__(256) apply_move_kernel(const InstDev inst, const TourDev tour) {
-    const Ctl *ctl = tour.ctl;
+__global__ void __launch_bounds__(256) apply_move_kernel(const InstDev inst, const TourDev tour, int seed) {
+    __shared__ int s_last;
+    Ctl *ctl = tour.ctl;
+    pdl_launch_dependents();
+    pdl_wait();
     if (!ctl->ap_valid) return;
     apply_swap_range(inst, tour, ctl->ap_pa, ctl->ap_pb, blockIdx.x * 256 + threadIdx.x, gridDim.x * 256);
+    if (!seed) return;
+    // last block done: seed the next pass's filter from the runner-up moves (BI only)
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned tk = atomicAdd(&ctl->apply_ticket, 1u);
+        s_last = (tk == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (threadIdx.x == 0) ctl->apply_ticket = 0;
+    seed_hint_from_candidates(inst, tour, threadIdx.x);
 }
 
 __global__ void __launch_bounds__(256) refresh_node_space_kernel(const TourDev tour) {
@@ -454,23 +545,68 @@ __global__ void __launch_bounds__(256) bi_scan_exact_kernel(const InstDev inst, 
 }
 
 // ---- host-side launchers -----------------------------------------------------------------------------
-template <int R>
-static cudaError_t launch_bi_r(const BiArgs &a, int grid, cudaStream_t st) {
-    size_t smem = (size_t)2 * (a.TJ + 2) * sizeof(float4);
+template <int T, int R>
+static cudaError_t launch_bi_tr(const BiArgs &a, int grid, bool pdl, cudaStream_t st) {
+    const size_t smem = (size_t)2 * (a.TJ + 2) * sizeof(float4) + (size_t)2 * (T * R + 2) * sizeof(float4) +
+                        (size_t)(2 * a.ntr + 2) * sizeof(int);
     const bool att = (a.inst.metric == M_ATT);
     const bool ex = a.inst.exact32 != 0;
-    if (att && ex) bi_scan_kernel<R, true, true><<<grid, BI_THREADS, smem, st>>>(a);
-    else if (att) bi_scan_kernel<R, true, false><<<grid, BI_THREADS, smem, st>>>(a);
-    else if (ex) bi_scan_kernel<R, false, true><<<grid, BI_THREADS, smem, st>>>(a);
-    else bi_scan_kernel<R, false, false><<<grid, BI_THREADS, smem, st>>>(a);
-    return cudaGetLastError();
+    auto go = [&](auto kern) -> cudaError_t {
+        // opt in to > 48 KB of dynamic shared memory once per (kernel instantiation, device)
+        static bool attr_set[64] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (!attr_set[dev & 63]) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            if (e != cudaSuccess) return e;
+            attr_set[dev & 63] = true;
+        }
+        if (!pdl) {
+            kern<<<grid, T, smem, st>>>(a);
+            return cudaGetLastError();
+        }
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(T);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, kern, a);
+    };
+    if (att && ex) return go(bi_scan_kernel<T, R, true, true>);
+    if (att) return go(bi_scan_kernel<T, R, true, false>);
+    if (ex) return go(bi_scan_kernel<T, R, false, true>);
+    return go(bi_scan_kernel<T, R, false, false>);
 }
 
-cudaError_t launch_bi_scan(const BiArgs &a, int rows_per_thread, int grid, cudaStream_t st) {
-    if (rows_per_thread == 16) return launch_bi_r<16>(a, grid, st);
-    if (rows_per_thread == 8) return launch_bi_r<8>(a, grid, st);
-    if (rows_per_thread == 4) return launch_bi_r<4>(a, grid, st);
-    return launch_bi_r<2>(a, grid, st);
+// supported (threads, rows per thread) shapes; anything else is rejected by tspb200_set_option
+bool bi_shape_supported(int threads, int rows_per_thread) {
+    if (threads == 256) return rows_per_thread == 2 || rows_per_thread == 4 || rows_per_thread == 8 || rows_per_thread == 16;
+    if (threads == 128) return rows_per_thread == 4 || rows_per_thread == 8;
+    if (threads == 64) return rows_per_thread == 2 || rows_per_thread == 4 || rows_per_thread == 8;
+    return false;
+}
+
+cudaError_t launch_bi_scan(const BiArgs &a, int threads, int rows_per_thread, int grid, bool pdl, cudaStream_t st) {
+    const int R = rows_per_thread;
+    if (threads == 256) {
+        if (R == 16) return launch_bi_tr<256, 16>(a, grid, pdl, st);
+        if (R == 8) return launch_bi_tr<256, 8>(a, grid, pdl, st);
+        if (R == 4) return launch_bi_tr<256, 4>(a, grid, pdl, st);
+        if (R == 2) return launch_bi_tr<256, 2>(a, grid, pdl, st);
+    } else if (threads == 128) {
+        if (R == 8) return launch_bi_tr<128, 8>(a, grid, pdl, st);
+        if (R == 4) return launch_bi_tr<128, 4>(a, grid, pdl, st);
+    } else if (threads == 64) {
+        if (R == 8) return launch_bi_tr<64, 8>(a, grid, pdl, st);
+        if (R == 4) return launch_bi_tr<64, 4>(a, grid, pdl, st);
+        if (R == 2) return launch_bi_tr<64, 2>(a, grid, pdl, st);
+    }
+    return cudaErrorInvalidValue;
 }
 
 cudaError_t launch_bi_scan_exact(const InstDev &inst, const TourDev &tour, int rank, int world, int fuse_apply,
@@ -492,13 +628,25 @@ cudaError_t launch_bi_decode_packed(const TourDev &tour, cudaStream_t st) {
     return cudaGetLastError();
 }
 
-// grid sized for n/2 swaps at ~4 per thread, capped at 2 blocks per SM
-cudaError_t launch_apply_move(const InstDev &inst, const TourDev &tour, int num_sms, cudaStream_t st) {
-    int grid = (tour.n / 2 + 1023) / 1024;
+// grid sized for one swap per thread (at most n/2 swaps), capped at 4 blocks per SM
+cudaError_t launch_apply_move(const InstDev &inst, const TourDev &tour, int num_sms, int seed, bool pdl, cudaStream_t st) {
+    int grid = (tour.n / 2 + 255) / 256;
     if (grid < 1) grid = 1;
-    if (grid > 2 * num_sms) grid = 2 * num_sms;
-    apply_move_kernel<<<grid, 256, 0, st>>>(inst, tour);
-    return cudaGetLastError();
+    if (grid > 4 * num_sms) grid = 4 * num_sms;
+    if (!pdl) {
+        apply_move_kernel<<<grid, 256, 0, st>>>(inst, tour, seed);
+        return cudaGetLastError();
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(256);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, apply_move_kernel, inst, tour, seed);
 }
 
 cudaError_t launch_refresh_node_space(const TourDev &tour, int num_sms, cudaStream_t st) {

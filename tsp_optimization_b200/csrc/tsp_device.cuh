@@ -198,6 +198,12 @@ __host__ __device__ __forceinline__ void key_unpack(unsigned long long p, int *d
     *j = (int)(p & 0x1ffffu);
 }
 
+// ---- programmatic dependent launch (sm_90+): the next kernel of the stream may be scheduled while this one still runs;
+// everything it does before pdl_wait() must not depend on this kernel's results.  Without the launch attribute both
+// are no-ops.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- TMA (bulk async copy) + mbarrier, raw PTX --------------------------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 

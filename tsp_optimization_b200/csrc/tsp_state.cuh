@@ -52,8 +52,13 @@ struct Ctl {
     long long pairs_swept;          // FI: linear pairs covered (statistics only)
     MoveKey last;                   // last selected key
     int ap_pa, ap_pb, ap_valid;     // move to apply: positions of a and b (published by the selecting kernel)
-    int pad0;
+    unsigned apply_ticket;          // block completion counter of the apply launch
+    MoveKey cand[4];                // runner-up moves of the last BI pass: re-evaluated after the apply to seed `hint`
+    int ncand;
+    int pad1;
+    unsigned long long cold_calls;  // statistics: filter hits that went through the exact (cold) path
 };
+constexpr int CTL_NCAND = 4;
 
 struct TourDev {
     int n;
@@ -98,20 +103,35 @@ __device__ __forceinline__ void apply_swap_range(const InstDev &I, const TourDev
     int len = pb - pa;
     if (len < 0) len += n;  // number of nodes on the path a1..b
     const int e = pb;
-    const int half = len >> 1;
+    const int half = len >> 1;         // record swaps: positions s+t <-> e-t
+    const int mhalf = (len - 1) >> 1;  // inner edge lengths (positions s .. e-1) reversed among themselves: s+t <-> e-1-t
+    // One iteration = record swap t AND edge-length swap t, all loads issued before the first store: one L2 round trip.
+    // No two threads touch the same word: swap t owns {x,y,node} of s+t and e-t and the edge lengths of s+t and e-1-t.
     for (int t = gtid; t < half; t += gthreads) {
         int A = s + t;
         if (A >= n) A -= n;
         int B = e - t;
         if (B < 0) B += n;
+        int Bm = B - 1;
+        if (Bm < 0) Bm += n;
+        const bool dsw = t < mhalf;
         const float2 xa = *reinterpret_cast<const float2 *>(&rec[A].x);
         const float wa = rec[A].w;
         const float2 xb = *reinterpret_cast<const float2 *>(&rec[B].x);
         const float wb = rec[B].w;
+        float za = 0.f, zc = 0.f;
+        if (dsw) {
+            za = rec[A].z;
+            zc = rec[Bm].z;
+        }
         *reinterpret_cast<float2 *>(&rec[A].x) = xb;
         rec[A].w = wb;
         *reinterpret_cast<float2 *>(&rec[B].x) = xa;
         rec[B].w = wa;
+        if (dsw) {
+            rec[A].z = zc;
+            rec[Bm].z = za;
+        }
         T.pos[__float_as_int(wb)] = A;
         T.pos[__float_as_int(wa)] = B;
         if (A == 0) {  // rec[n] mirrors rec[0] (wrap-around successor of position n-1)
@@ -131,18 +151,6 @@ __device__ __forceinline__ void apply_swap_range(const InstDev &I, const TourDev
             rec[pa].z = (float)dist_nodes(I, na, __float_as_int(wb));
             rec[pb].z = (float)dist_nodes(I, __float_as_int(wa), nb1);
         }
-    }
-    // inner edge lengths: positions s .. s+len-2 are reversed among themselves
-    const int m = len - 1;
-    const int mhalf = m >> 1;
-    for (int t = gtid; t < mhalf; t += gthreads) {
-        int A = s + t;
-        if (A >= n) A -= n;
-        int Cc = s + m - 1 - t;
-        if (Cc >= n) Cc -= n;
-        const float za = rec[A].z, zc = rec[Cc].z;
-        rec[A].z = zc;
-        rec[Cc].z = za;
     }
 }
 
@@ -199,6 +207,36 @@ __device__ __forceinline__ long long move_delta_nodes(const InstDev &I, const To
     return dist_nodes(I, i, j) + dist_nodes(I, a1, b1) - (long long)T.rec[pa].z - (long long)T.rec[pb].z;
 }
 
+// Seeding the filter of the NEXT best-improvement pass.  The runner-up moves of the pass that just ended are mostly
+// still legal after the winner was applied; the exact delta of any legal move is a valid upper bound of the next
+// pass's minimum, so `hint` may start there instead of at 0 and the FP32 filter is tight from the first tile on
+// (without it every thread climbs through a series of "record" candidates, each a trip through the cold path).
+// Called by the last block of the apply launch; all loads bypass L1 (other blocks just rewrote rec[] / pos[]).
+// Exact delta of candidate move c in the CURRENT tour, or 0 when c is not a legal move any more (bad indices, the pair
+// became adjacent — e.g. it IS the move just applied).  All loads bypass L1 (another block may just have rewritten
+// rec[] / pos[]).
+__device__ __forceinline__ long long legal_move_delta_cg(const InstDev &I, const TourDev &T, const MoveKey c) {
+    const int n = T.n;
+    if (c.delta >= 0 || c.i < 0 || c.j >= n || c.i >= c.j) return 0;
+    const int pa = __ldcg(&T.pos[c.i]), pb = __ldcg(&T.pos[c.j]);
+    int d = pa - pb;
+    if (d < 0) d = -d;
+    if (d <= 1 || d == n - 1) return 0;
+    int pa1 = pa + 1; if (pa1 >= n) pa1 -= n;
+    int pb1 = pb + 1; if (pb1 >= n) pb1 -= n;
+    const float4 ra = __ldcg(&T.rec[pa]), rb = __ldcg(&T.rec[pb]);
+    const int a1 = node_of(__ldcg(&T.rec[pa1])), b1 = node_of(__ldcg(&T.rec[pb1]));
+    return dist_nodes(I, c.i, c.j) + dist_nodes(I, a1, b1) - (long long)ra.z - (long long)rb.z;
+}
+
+// Called by the last block of the apply launch with t = thread index.
+__device__ __forceinline__ void seed_hint_from_candidates(const InstDev &I, const TourDev &T, int t) {
+    Ctl *ctl = T.ctl;
+    if (t >= ctl->ncand) return;
+    const long long delta = legal_move_delta_cg(I, T, ctl->cand[t]);
+    if (delta < 0) atomicMin(&ctl->hint, (int)delta);
+}
+
 // ---- kernel argument blocks shared by the kernel translation units and engine.cu ----------------------
 struct BiArgs {
     InstDev inst;
@@ -209,7 +247,9 @@ struct BiArgs {
     int ntiles;
     int TJ;          // columns per tile (even)
     int rank, world; // tiles are dealt round-robin over ranks (multi-GPU neighbourhood sharding)
-    int fuse_apply;  // 1: the last block applies the move (single GPU); 0: it only publishes the key
+    int fuse_apply;  // 0: the last block only publishes this rank's key (multi-GPU); 1: it publishes the move for the
+                     // apply launch; 2: it also applies the move itself
+    int seed_hint;   // fuse_apply == 2 only: seed the next pass's filter after the in-kernel apply
 };
 
 struct NnArgs {

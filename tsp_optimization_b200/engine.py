@@ -110,24 +110,25 @@ def load_library() -> C.CDLL:
     L.tspb200_comm_unique_id.argtypes = [C.c_void_p]
     L.tspb200_comm_init.argtypes = [vp, C.c_void_p, C.c_int, C.c_int]
     L.tspb200_comm_destroy.argtypes = [vp]
-    L.tspb200_debug_tile_plan.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, i32p, i32p, C.c_void_p,
-                                          C.c_void_p, C.c_int, i32p]
+    L.tspb200_debug_tile_plan.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, i32p, i32p, i32p,
+                                          C.c_void_p, C.c_void_p, C.c_int, i32p]
     _lib = L
     return L
 
 
-def tile_plan(n: int, rows_per_thread: int = 0, tile_cols: int = 0, slots: int = 296, world: int = 1):
-    """Host-only: the BI tile plan -> (R, TJ, row_start[ntr+1], row_j0[ntr]). Needs no GPU."""
+def tile_plan(n: int, rows_per_thread: int = 0, tile_cols: int = 0, threads: int = 0, num_sms: int = 148, world: int = 1):
+    """Host-only: the BI tile plan -> (T, R, TJ, row_start[ntr+1], row_j0[ntr]); a tile-row is T*R tour positions.
+    0 = let the engine choose. Needs no GPU."""
     L = load_library()
-    cap = n // 256 + 8
+    cap = n // 64 + 8
     rs = np.zeros(cap, dtype=np.int32)
     rj = np.zeros(cap, dtype=np.int32)
-    r, tj, ntr = C.c_int32(0), C.c_int32(0), C.c_int32(0)
-    rc = L.tspb200_debug_tile_plan(n, rows_per_thread, tile_cols, slots, world, C.byref(r), C.byref(tj),
-                                   rs.ctypes.data, rj.ctypes.data, cap, C.byref(ntr))
+    t, r, tj, ntr = C.c_int32(0), C.c_int32(0), C.c_int32(0), C.c_int32(0)
+    rc = L.tspb200_debug_tile_plan(n, threads, rows_per_thread, tile_cols, num_sms, world, C.byref(t), C.byref(r),
+                                   C.byref(tj), rs.ctypes.data, rj.ctypes.data, cap, C.byref(ntr))
     if rc:
         raise TspB200Error(rc, "tile plan failed")
-    return r.value, tj.value, rs[:ntr.value + 1].copy(), rj[:ntr.value].copy()
+    return t.value, r.value, tj.value, rs[:ntr.value + 1].copy(), rj[:ntr.value].copy()
 
 
 def key_pack(delta: int, i: int, j: int) -> int:

@@ -361,7 +361,9 @@ def main():
                                    f"2-opt passes with on-the-fly distances (BASELINE configs[3])",
                        "n": n, "pairs_per_step": pairs, "rows_per_thread": eng.info("rows_per_thread"),
                        "tile_cols": eng.info("tile_cols"), "grid": eng.info("grid_bi"), "tiles": eng.info("ntiles"),
-                       "sharding": "tiles round-robin over ranks + 8-byte NCCL min-allreduce per pass" if world > 1 else "single GPU",
+                       "sharding": ("tiles round-robin over ranks; per pass each rank's 8-byte argmin key is " +
+                                    ("stored into every peer's slots over NVLink by the scan kernel (CUDA IPC peer memory)"
+                                     if eng.info("exchange_p2p") else "min-allreduced by NCCL")) if world > 1 else "single GPU",
                        "l2": "flushed between timed steps (256 MB write)" if flush is not None else "not flushed (2.4 MB working set)",
                        "nn_start_s": nn_s},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d / e2e_passes, "d2h_bytes_per_step": d2h / e2e_passes,

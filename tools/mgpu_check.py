@@ -30,8 +30,15 @@ def main():
     eng = Engine(local)
     eng.set_instance(xy, 0)
     attach_engine_comm(eng, rank, world)
-    s2, o2, st2, log2 = eng.two_opt(BI, succ0, 0.0, max_iters=passes, log_cap=passes + 8)
-    ok = (s1 == s2).all() and o1 == o2 and log1.tolist() == log2.tolist() and st1.passes == st2.passes
+    ok = True
+    times = {}
+    for exchange, name in ((0, "p2p"), (1, "nccl")):
+        eng.set_option("exchange", exchange)
+        s2, o2, st2, log2 = eng.two_opt(BI, succ0, 0.0, max_iters=passes, log_cap=passes + 8)
+        times[name] = st2.gpu_ms
+        ok = ok and (s1 == s2).all() and o1 == o2 and log1.tolist() == log2.tolist() and st1.passes == st2.passes
+    eng.set_option("exchange", 0)
+    p2p = eng.info("exchange_p2p")
     # all ranks must agree with each other as well
     h = torch.tensor([int(np.int64(np.sum(s2.astype(np.int64) * np.arange(1, n + 1))) % (1 << 62)), int(ok)], dtype=torch.int64, device="cuda")
     hs = [torch.zeros_like(h) for _ in range(world)]
@@ -39,7 +46,8 @@ def main():
     same = all(int(x[0]) == int(hs[0][0]) for x in hs) and all(int(x[1]) == 1 for x in hs)
     if rank == 0:
         print(f"MGPU_CHECK world={world} n={n} passes={st2.passes} moves={st2.moves} "
-              f"single_ms={st1.gpu_ms:.2f} sharded_ms={st2.gpu_ms:.2f} {'OK' if same else 'MISMATCH'}", flush=True)
+              f"single_ms={st1.gpu_ms:.2f} sharded_p2p_ms={times['p2p']:.2f} sharded_nccl_ms={times['nccl']:.2f} "
+              f"p2p_enabled={p2p} {'OK' if same else 'MISMATCH'}", flush=True)
     eng.close()
     dist.destroy_process_group()
     sys.exit(0 if same else 1)

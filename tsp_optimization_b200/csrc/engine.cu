@@ -49,6 +49,7 @@ struct NcclApi {
     int (*CommInitRank)(nccl_comm_t *, int, nccl_unique_id, int) = nullptr;
     int (*CommDestroy)(nccl_comm_t) = nullptr;
     int (*AllReduce)(const void *, void *, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, nccl_comm_t, cudaStream_t) = nullptr;
     const char *(*GetErrorString)(int) = nullptr;
     bool load(std::string &err) {
         if (handle) return true;
@@ -62,12 +63,15 @@ struct NcclApi {
         CommInitRank = (int (*)(nccl_comm_t *, int, nccl_unique_id, int))dlsym(handle, "ncclCommInitRank");
         CommDestroy = (int (*)(nccl_comm_t))dlsym(handle, "ncclCommDestroy");
         AllReduce = (int (*)(const void *, void *, size_t, int, int, nccl_comm_t, cudaStream_t))dlsym(handle, "ncclAllReduce");
+        AllGather = (int (*)(const void *, void *, size_t, int, nccl_comm_t, cudaStream_t))dlsym(handle, "ncclAllGather");
         GetErrorString = (const char *(*)(int))dlsym(handle, "ncclGetErrorString");
         if (!GetUniqueId || !CommInitRank || !CommDestroy || !AllReduce) { err = "libnccl.so.2 lacks required symbols"; return false; }
         return true;
     }
 };
 static NcclApi g_nccl;
+constexpr int NCCL_CHAR = 0;    // ncclInt8
+constexpr int NCCL_INT32 = 2;   // ncclInt32
 constexpr int NCCL_UINT64 = 5;  // ncclUint64
 constexpr int NCCL_MIN = 3;     // ncclMin
 
@@ -122,6 +126,13 @@ struct tspb200_ctx {
     // comm
     nccl_comm_t comm = nullptr;
     int rank = 0, world = 1;
+    // argmin exchange over NVLink peer memory (see XchgDev): own slots + IPC-mapped peer slots
+    XchgDev xchg{};
+    XchgSlot *d_slots = nullptr;
+    unsigned *d_epoch = nullptr;
+    void *peer_mapped[XCHG_MAX_WORLD] = {};
+    std::string xchg_note;
+    int opt_exchange = 0;  // 0 = peer memory when available, 1 = NCCL allreduce
 };
 
 static int fail(tspb200_ctx *c, int code, const char *fmt, ...) {
@@ -150,6 +161,18 @@ static void free_tour(tspb200_ctx *c) {
     c->d_order = c->d_succ = nullptr; c->d_cost = nullptr;
     c->d_tile_row_start = c->d_tile_row_j0 = nullptr;
     c->has_tour = false;
+}
+
+static void free_xchg(tspb200_ctx *c) {
+    for (int r = 0; r < XCHG_MAX_WORLD; ++r) {
+        if (c->peer_mapped[r]) cudaIpcCloseMemHandle(c->peer_mapped[r]);
+        c->peer_mapped[r] = nullptr;
+    }
+    cudaFree(c->d_slots);
+    cudaFree(c->d_epoch);
+    c->d_slots = nullptr;
+    c->d_epoch = nullptr;
+    c->xchg = XchgDev{};
 }
 
 static void free_instance(tspb200_ctx *c) {
@@ -195,6 +218,7 @@ void tspb200_destroy(tspb200_ctx *ctx) {
     if (ctx->stream) {
         cudaSetDevice(ctx->device);
         cudaStreamSynchronize(ctx->stream);
+        free_xchg(ctx);
         if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
         free_instance(ctx);
         cudaFree(ctx->d_ctl);
@@ -220,6 +244,9 @@ int tspb200_set_option(tspb200_ctx *ctx, const char *key, int64_t value) {
     } else if (k == "fuse_apply") {
         if (value < -1 || value > 1) return fail(ctx, TSPB200_E_ARG, "fuse_apply must be -1 (auto), 0 or 1");
         ctx->opt_fuse_apply = (int)value;
+    } else if (k == "exchange") {
+        if (value != 0 && value != 1) return fail(ctx, TSPB200_E_ARG, "exchange must be 0 (peer memory when available) or 1 (NCCL)");
+        ctx->opt_exchange = (int)value;
     } else if (k == "pdl") {
         ctx->opt_pdl = value ? 1 : 0;
     } else if (k == "seed_hint") {
@@ -259,6 +286,7 @@ int64_t tspb200_get_info(const tspb200_ctx *ctx, const char *key) {
     if (k == "matrix_resident") return ctx->d_mat != nullptr;
     if (k == "matrix_ld") return ctx->mat_ld;
     if (k == "cold_calls") return ctx->h_ctl ? (int64_t)ctx->h_ctl->cold_calls : -1;  // as of the last host sync
+    if (k == "exchange_p2p") return ctx->xchg.enabled && ctx->opt_exchange == 0;
     if (k == "world") return ctx->world;
     if (k == "rank") return ctx->rank;
     return -1;
@@ -567,6 +595,7 @@ int tspb200_tour_log(tspb200_ctx *ctx, tspb200_move *log, int64_t cap, int64_t *
 static int sync_ctl(tspb200_ctx *ctx) {
     CK(cudaMemcpyAsync(ctx->h_ctl, ctx->d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->h_ctl->error == 2) return fail(ctx, TSPB200_E_NCCL, "multi-GPU exchange timed out: a peer rank never delivered its key");
     if (ctx->h_ctl->error) return fail(ctx, TSPB200_E_DEVICE_CHECK, "device-side consistency check failed (code %d)", ctx->h_ctl->error);
     return TSPB200_OK;
 }
@@ -600,8 +629,12 @@ int tspb200_bi_run(tspb200_ctx *ctx, int64_t max_passes, tspb200_stats *st) {
                                 (ctx->opt_fuse_apply >= 0 ? ctx->opt_fuse_apply == 1 : false);
     a.fuse_apply = ctx->world == 1 ? (fuse_in_kernel ? 2 : 1) : 0;
     a.seed_hint = ctx->opt_seed_hint;
-    // programmatic dependent launch between the scan and apply kernels of one GPU's pass loop (no NCCL op in between)
-    const bool pdl = ctx->world == 1 && path == 0 && !ctx->tabu_on && ctx->opt_pdl;
+    // multi-GPU: keys travel as NVLink peer stores from the scan kernel (path 0) unless NCCL was asked for
+    const bool use_xchg = ctx->world > 1 && path == 0 && ctx->xchg.enabled && ctx->opt_exchange == 0;
+    a.xchg = ctx->xchg;
+    a.xchg.enabled = use_xchg ? 1 : 0;
+    // programmatic dependent launch along the scan -> (decode) -> apply chain; not across a NCCL collective
+    const bool pdl = path == 0 && !ctx->tabu_on && ctx->opt_pdl && (ctx->world == 1 || use_xchg);
     int rc = sync_ctl(ctx);
     if (rc) return rc;
     const long long passes0 = ctx->h_ctl->passes, moves0 = ctx->h_ctl->moves, launches0 = ctx->h_ctl->launches,
@@ -630,7 +663,7 @@ int tspb200_bi_run(tspb200_ctx *ctx, int64_t max_passes, tspb200_stats *st) {
             else if (path == 0) CK(launch_bi_scan(a, ctx->T, ctx->R, ctx->grid_bi, pdl, ctx->stream));
             else CK(launch_bi_scan_exact(I, ctx->tour, ctx->rank, ctx->world, a.fuse_apply, exact_grid, ctx->stream));
             host_launches++;
-            if (ctx->world > 1) {
+            if (ctx->world > 1 && !use_xchg) {  // NCCL variant; with peer memory the scan kernel's tail did the exchange
                 unsigned long long *p = &ctx->d_ctl->packed;
                 int nr = g_nccl.AllReduce(p, p, 1, NCCL_UINT64, NCCL_MIN, ctx->comm, ctx->stream);
                 if (nr != 0) return fail(ctx, TSPB200_E_NCCL, "ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(nr) : "?");
@@ -956,11 +989,70 @@ int tspb200_comm_init(tspb200_ctx *ctx, const void *id128, int rank, int world) 
     ctx->rank = rank;
     ctx->world = world;
     ctx->has_tour = false;  // tile plan depends on the world size
+
+    // ---- peer-memory exchange: every rank maps every other rank's slot array (CUDA IPC -> NVLink P2P) -------------
+    free_xchg(ctx);
+    ctx->xchg_note.clear();
+    int ok = (world <= XCHG_MAX_WORLD && g_nccl.AllGather) ? 1 : 0;
+    if (!ok) ctx->xchg_note = "peer exchange needs world <= 16 and ncclAllGather";
+    cudaIpcMemHandle_t mine;
+    memset(&mine, 0, sizeof mine);
+    char *d_h = nullptr;
+    std::vector<cudaIpcMemHandle_t> all((size_t)world);
+    if (ok) {
+        CK(cudaMalloc(&ctx->d_slots, sizeof(XchgSlot) * 2 * XCHG_MAX_WORLD));
+        CK(cudaMalloc(&ctx->d_epoch, sizeof(unsigned)));
+        CK(cudaMemsetAsync(ctx->d_slots, 0, sizeof(XchgSlot) * 2 * XCHG_MAX_WORLD, ctx->stream));
+        CK(cudaMemsetAsync(ctx->d_epoch, 0, sizeof(unsigned), ctx->stream));
+        if (cudaIpcGetMemHandle(&mine, ctx->d_slots) != cudaSuccess) {
+            cudaGetLastError();
+            ok = 0;
+            ctx->xchg_note = "cudaIpcGetMemHandle failed";
+        }
+    }
+    // the handles travel through the communicator we already have; the all-gather also orders every rank's memset of
+    // its slots before any peer can write to them
+    CK(cudaMalloc(&d_h, sizeof(cudaIpcMemHandle_t) * (size_t)(world + 1)));
+    CK(cudaMemcpyAsync(d_h, &mine, sizeof mine, cudaMemcpyHostToDevice, ctx->stream));
+    if (g_nccl.AllGather) {
+        nr = g_nccl.AllGather(d_h, d_h + sizeof(cudaIpcMemHandle_t), sizeof(cudaIpcMemHandle_t), NCCL_CHAR, ctx->comm, ctx->stream);
+        if (nr != 0) { cudaFree(d_h); return fail(ctx, TSPB200_E_NCCL, "ncclAllGather failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(nr) : "?"); }
+        CK(cudaMemcpyAsync(all.data(), d_h + sizeof(cudaIpcMemHandle_t), sizeof(cudaIpcMemHandle_t) * (size_t)world, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ok) {
+        for (int r = 0; r < world && ok; ++r) {
+            if (r == rank) { ctx->xchg.peer[r] = ctx->d_slots; continue; }
+            void *p = nullptr;
+            if (cudaIpcOpenMemHandle(&p, all[(size_t)r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                cudaGetLastError();
+                ok = 0;
+                ctx->xchg_note = "cudaIpcOpenMemHandle failed (no peer access between the ranks' devices?)";
+                break;
+            }
+            ctx->peer_mapped[r] = p;
+            ctx->xchg.peer[r] = reinterpret_cast<XchgSlot *>(p);
+        }
+    }
+    // all ranks must agree: one failure anywhere -> everybody uses the NCCL allreduce
+    int *d_ok = reinterpret_cast<int *>(d_h);
+    CK(cudaMemcpyAsync(d_ok, &ok, sizeof ok, cudaMemcpyHostToDevice, ctx->stream));
+    nr = g_nccl.AllReduce(d_ok, d_ok, 1, NCCL_INT32, NCCL_MIN, ctx->comm, ctx->stream);
+    if (nr != 0) { cudaFree(d_h); return fail(ctx, TSPB200_E_NCCL, "ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(nr) : "?"); }
+    int all_ok = 0;
+    CK(cudaMemcpyAsync(&all_ok, d_ok, sizeof all_ok, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_h);
+    ctx->xchg.epoch = ctx->d_epoch;
+    ctx->xchg.enabled = all_ok ? 1 : 0;
+    if (!all_ok && ctx->xchg_note.empty()) ctx->xchg_note = "a peer rank could not map the exchange slots";
     return TSPB200_OK;
 }
 
 int tspb200_comm_destroy(tspb200_ctx *ctx) {
     if (!ctx) return TSPB200_E_ARG;
+    if (ctx->stream) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+    free_xchg(ctx);
     if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
     ctx->comm = nullptr;
     ctx->rank = 0;

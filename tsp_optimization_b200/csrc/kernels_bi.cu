@@ -362,14 +362,63 @@ __global__ void __launch_bounds__(BI_THREADS, (R >= 16 ? 1 : 512 / BI_THREADS)) 
         ctl->hint = 0;
         ctl->launches += 1;
         if (!A.fuse_apply) {
-            // multi-GPU: publish this rank's key for the NCCL min-allreduce; bi_decode_packed_kernel continues
+            // multi-GPU: publish this rank's key for the exchange; the decode kernel continues
             ctl->packed = (k.delta < 0) ? key_pack(k.delta, k.i, k.j) : key_pack(0, 0x1ffff, 0x1ffff);
+            if (A.xchg.enabled) {
+                const unsigned e = *A.xchg.epoch + 1u;
+                *A.xchg.epoch = e;
+                s_ap[0] = (int)e;
+            }
         } else {
             ctl->passes += 1;
             publish_move(A.tour, k.i, k.j, k.delta);
             if (k.delta >= 0) ctl->done = 1;  // reference src/tabusearch.c:158: mindelta >= 0 -> stop
             s_ap[0] = ctl->ap_pa;
             s_ap[1] = ctl->ap_pb;
+        }
+    }
+    // Multi-GPU exchange over peer memory, fused into this kernel's tail: thread r stores this rank's key, then the epoch,
+    // into rank r's slot array (NVLink peer stores), then polls this rank's LOCAL slot r until rank r's key of the same
+    // epoch has arrived; the block takes the minimum — every rank gets the same winner — and publishes the move for its own
+    // replica of the tour.  No collective launch and no tour data on the wire.
+    if (!A.fuse_apply && A.xchg.enabled) {
+        __shared__ unsigned long long s_xkey[XCHG_MAX_WORLD];
+        __syncthreads();
+        if (tid < A.world) {
+            const unsigned e = (unsigned)s_ap[0];
+            XchgSlot *dst = A.xchg.peer[tid] + (e & 1u) * XCHG_MAX_WORLD + A.rank;
+            unsigned long long key = *((volatile unsigned long long *)&ctl->packed);
+            asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(&dst->key), "l"(key) : "memory");
+            __threadfence_system();
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(&dst->epoch), "r"(e) : "memory");
+            const XchgSlot *src = A.xchg.peer[A.rank] + (e & 1u) * XCHG_MAX_WORLD + tid;
+            const long long t0 = clock64();
+            for (;;) {
+                unsigned got;
+                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(got) : "l"(&src->epoch) : "memory");
+                if (got == e) break;
+                if (clock64() - t0 > 20000000000ll) {  // ~10 s: a peer died; fail loudly instead of hanging the GPU
+                    ctl->error = 2;
+                    break;
+                }
+            }
+            asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(key) : "l"(&src->key) : "memory");
+            s_xkey[tid] = key;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long win = s_xkey[0];
+            for (int r = 1; r < A.world; ++r) win = s_xkey[r] < win ? s_xkey[r] : win;
+            int delta, i, j;
+            key_unpack(win, &delta, &i, &j);
+            if (ctl->error) {
+                ctl->done = 1;
+                ctl->ap_valid = 0;
+            } else {
+                ctl->passes += 1;
+                publish_move(A.tour, i, j, delta);
+                if (delta >= 0) ctl->done = 1;
+            }
         }
     }
     // fuse_apply == 2: this (last) block also applies the move, saving the apply launch — every other block has
@@ -384,8 +433,8 @@ __global__ void __launch_bounds__(BI_THREADS, (R >= 16 ? 1 : 512 / BI_THREADS)) 
     }
 }
 
-// After the NCCL min-allreduce (multi-GPU): every rank decodes the same winning key and publishes the move for
-// its own replica of the tour, so no tour data ever crosses NVLink.
+// NCCL variant of the multi-GPU exchange: after ncclAllReduce(min) of ctl->packed every rank decodes the same winning key
+// and publishes the move for its own replica of the tour.
 __global__ void bi_decode_packed_kernel(const TourDev tour) {
     Ctl *ctl = tour.ctl;
     if (ctl->done) { ctl->ap_valid = 0; return; }

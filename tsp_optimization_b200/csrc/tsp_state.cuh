@@ -238,6 +238,25 @@ __device__ __forceinline__ void seed_hint_from_candidates(const InstDev &I, cons
 }
 
 // ---- kernel argument blocks shared by the kernel translation units and engine.cu ----------------------
+// ---- multi-GPU argmin exchange over NVLink peer memory ------------------------------------------------------
+// Every rank owns 2 x XCHG_MAX_WORLD slots (double-buffered by the parity of the pass epoch).  In the tail of its scan
+// kernel a rank STORES its packed (delta,i,j) key, then (after a system-scope fence) the epoch, into slot [epoch&1][rank]
+// of EVERY peer — plain st.global on pointers mapped with cudaIpcOpenMemHandle, i.e. NVLink writes through NVSwitch — and
+// then polls its LOCAL slots until all `world` epochs arrived.  No collective launch, no tour data on the wire: 12 bytes
+// per peer and pass.  A rank can be at most one pass ahead of a peer (it cannot finish pass k+1 without that peer's key of
+// pass k+1), so two buffers suffice.
+constexpr int XCHG_MAX_WORLD = 16;
+struct __align__(16) XchgSlot {
+    unsigned long long key;
+    unsigned epoch;
+    unsigned pad;
+};
+struct XchgDev {
+    XchgSlot *peer[XCHG_MAX_WORLD];  // peer[r] = base of rank r's slot array (peer[rank] = own, local pointer)
+    unsigned *epoch;                 // this rank's pass epoch (device word, monotonically increasing, never reset)
+    int enabled;
+};
+
 struct BiArgs {
     InstDev inst;
     TourDev tour;
@@ -249,7 +268,8 @@ struct BiArgs {
     int rank, world; // tiles are dealt round-robin over ranks (multi-GPU neighbourhood sharding)
     int fuse_apply;  // 0: the last block only publishes this rank's key (multi-GPU); 1: it publishes the move for the
                      // apply launch; 2: it also applies the move itself
-    int seed_hint;   // fuse_apply == 2 only: seed the next pass's filter after the in-kernel apply
+    int seed_hint;   // 0 = none, 1 = this block's previous winner re-evaluated at the start of the scan, 2 = also runner-ups
+    XchgDev xchg;    // fuse_apply == 0: how this rank's key reaches the other ranks (enabled = 0 -> NCCL allreduce of ctl->packed)
 };
 
 struct NnArgs {

@@ -42,7 +42,7 @@ def parse_args():
     ap.add_argument("--n", type=int, default=100000)
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--tlo", action="store_true", help="also run to the local optimum and report time_to_local_optimum_s")
+    ap.add_argument("--no-tlo", action="store_true", help="skip the time-to-local-optimum runs (uni100000 on N GPUs, uni10000)")
     ap.add_argument("--rows-per-thread", type=int, default=0)
     ap.add_argument("--tile-cols", type=int, default=0)
     return ap.parse_args()
@@ -240,7 +240,7 @@ def main():
         attach_engine_comm(eng, rank, world)
     eng.tour_upload(succ0)
 
-    flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # matrix kernel timing only
 
     def barrier():
         torch.cuda.synchronize()
@@ -248,29 +248,23 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    # ---- resident-tour timing: W warm-up passes, then exactly K timed passes --------------------------------
+    # ---- resident-tour timing: W warm-up passes, then exactly K timed passes in ONE engine call --------------------
+    # l2_flush_bytes: the engine writes 256 MB (> 126 MB L2) before every pass and times each pass with its own CUDA
+    # event pair on its stream; value = K * pairs / sum of the per-pass intervals (max over ranks).  No host round trip
+    # between passes, so multi-GPU ranks stay in step through the device-side exchange only.
     eng.bi_run(args.warmup)
+    if not args.no_flush:
+        eng.set_option("l2_flush_bytes", 256 << 20)
     sampler = ClockSampler(local)
     barrier()
     sampler.start()
-    gpu_ms, launches, moves = 0.0, 0, 0
     wall0 = time.perf_counter()
-    if flush is None:
-        st = eng.bi_run(args.steps)
-        gpu_ms, launches, moves, done_passes = st.gpu_ms, st.launches, st.moves, st.passes
-    else:
-        done_passes = 0
-        for _ in range(args.steps):
-            flush.zero_()  # > L2 (126 MB): every step starts with a cold L2
-            torch.cuda.synchronize()
-            st = eng.bi_run(1)
-            gpu_ms += st.gpu_ms
-            launches += st.launches
-            moves += st.moves
-            done_passes += st.passes
+    st = eng.bi_run(args.steps)
     barrier()
     wall_s = time.perf_counter() - wall0
     clocks = sampler.stop()
+    eng.set_option("l2_flush_bytes", 0)
+    gpu_ms, launches, moves, done_passes = st.gpu_ms, st.launches, st.moves, st.passes
     if world > 1:
         t = torch.tensor([gpu_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -297,16 +291,35 @@ def main():
     h2d = 16 * n + 4 * n
     d2h = 4 * n + 8
 
+    # ---- time to local optimum (BASELINE metric, second half): the same instance and start tour, run to the end ----
     tlo = None
-    if args.tlo:
+    if not args.no_tlo:
         eng.set_instance(h_xy, 0)
         barrier()
         w0 = time.perf_counter()
         s_out, obj_out, st_f, _ = eng.two_opt(BI, h_succ, 0.0)
+        torch.cuda.synchronize()
         tlo_s = time.perf_counter() - w0
-        tlo = {"time_to_local_optimum_s": tlo_s, "passes": st_f.passes, "moves": st_f.moves, "gpu_ms": st_f.gpu_ms,
-               "start_cost": nn_cost, "final_cost": obj_out, "evals_per_s": st_f.evals / (st_f.gpu_ms * 1e-3)}
-
+        if world > 1:
+            t = torch.tensor([tlo_s], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            tlo_s = float(t.item())
+        tlo = {"workload": f"uni{n} NN start -> best-improvement 2-opt local optimum on {world} GPU(s), host buffers in and out",
+               "time_to_local_optimum_s": tlo_s, "passes": st_f.passes, "moves": st_f.moves, "gpu_ms": st_f.gpu_ms,
+               "start_cost": nn_cost, "final_cost": obj_out, "evals": st_f.evals, "evals_per_s": st_f.evals / tlo_s}
+        if world == 1 and n != 10000:  # BASELINE configs[2]: uni10000, greedy start + 2-opt to the local optimum, 1 B200
+            xy2 = uniform_instance(10000)
+            eng.set_instance(xy2, 0)
+            s2, c2 = eng.nn_tour(0)
+            eng.two_opt(BI, s2, 0.0, max_iters=4)  # warm-up of this tile shape
+            for mode, nm in ((BI, "BI"), (1 - BI, "FI")):
+                w0 = time.perf_counter()
+                _, o2, st2, _ = eng.two_opt(mode, s2, c2)
+                d2 = time.perf_counter() - w0
+                tlo[f"uni10000_{nm}"] = {"time_to_local_optimum_s": d2, "passes": st2.passes, "moves": st2.moves,
+                                         "final_cost": o2, "evals": st2.evals}
+            eng.set_instance(h_xy, 0)
+            eng.tour_upload(h_succ)
     if rank != 0:
         eng.close()
         if world > 1:
@@ -364,7 +377,8 @@ def main():
                        "sharding": ("tiles round-robin over ranks; per pass each rank's 8-byte argmin key is " +
                                     ("stored into every peer's slots over NVLink by the scan kernel (CUDA IPC peer memory)"
                                      if eng.info("exchange_p2p") else "min-allreduced by NCCL")) if world > 1 else "single GPU",
-                       "l2": "flushed between timed steps (256 MB write)" if flush is not None else "not flushed (2.4 MB working set)",
+                       "l2": "flushed before every timed pass (256 MB write on the engine stream, outside the per-pass event pairs)"
+                             if not args.no_flush else "not flushed (5.7 MB working set)",
                        "nn_start_s": nn_s},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d / e2e_passes, "d2h_bytes_per_step": d2h / e2e_passes,
                     "passes": st_e.passes, "seconds": e2e_s,

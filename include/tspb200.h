@@ -87,6 +87,9 @@ const char *tspb200_last_error(const tspb200_ctx *ctx);
 /* Tuning / mode knobs. keys: "block_threads" (64|128|256), "rows_per_thread" (2|4|8|16), "tile_cols" (multiple of 4,
  * 32..1024), "grid" (blocks), "fuse_apply" (-1 auto, 0 separate apply launch, 1 the scan's last block applies the move), "seed_hint" (1 = seed each
  * pass's filter from the previous pass's runner-up moves, 0 = start every pass from delta 0),
+ * "exchange" (multi-GPU: 0 = NVLink peer-memory slots when available, 1 = NCCL allreduce), "pdl" (programmatic dependent
+ * launch on/off), "l2_flush_bytes" (benchmarks: write that many bytes before every BI pass and time each pass with its
+ * own CUDA event pair; stats.gpu_ms is then the sum of the per-pass intervals),
  * "force_path" (-1 auto, 0 fp32 filter, 1 exact on the fly, 2 matrix), "batch" (passes per host sync),
  * "time_limit_ms" (<=0 unlimited; checked between launch batches). */
 int tspb200_set_option(tspb200_ctx *ctx, const char *key, int64_t value);

@@ -245,7 +245,7 @@ def test_fi_reference_csv_goldens(engine, instances, goldens, oracle):
 
 
 @pytest.mark.parametrize("T,R,TJ,fuse", [(256, 2, 32, -1), (256, 2, 64, 0), (256, 4, 64, 1), (256, 8, 128, -1), (256, 8, 256, 0),
-                                         (256, 4, 36, 1), (256, 16, 64, -1), (128, 8, 128, 1), (128, 4, 64, 0), (64, 8, 64, 1),
+                                         (256, 4, 36, 1), (256, 16, 64, -1), (128, 16, 64, -1), (128, 16, 256, 1), (128, 8, 128, 1), (128, 4, 64, 0), (64, 8, 64, 1),
                                          (64, 8, 128, 0), (64, 4, 32, -1), (64, 2, 64, 1)])
 def test_bi_tile_shapes(engine, oracle, T, R, TJ, fuse):
     """every supported (block threads, rows per thread) shape, with the move applied by a separate launch (fuse 0) and by

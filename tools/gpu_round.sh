@@ -1,2 +1,2 @@
-set -x
-timeout 900 python bench.py > gpurun_out/bench_r1d.json 2> gpurun_out/bench_r1d.err; echo "rc=$?"
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1
+timeout 600 python tools/autoshape.py > gpurun_out/autoshape.jsonl 2>&1

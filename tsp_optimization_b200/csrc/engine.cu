@@ -448,27 +448,32 @@ static long long tile_plan(int n, int TI, int TJ, std::vector<int> *row_start, s
     return total;
 }
 
-// Picks (T, R, TJ) by a small cost model.  Every shape keeps 16 warps per SM (slots = SMs * 512/T blocks); a pass takes
-// `waves` = ceil(tiles per rank / slots) rounds of tiles, and one tile costs a thread (TJ + OV) column steps of R+1
-// square roots each (OV ~ the row loads, first column and end-of-tile barrier).  Big instances end up at 256 x 8 x 256
-// (fewest sqrt per move, fewest tiles); mid-size ones (n ~ 10^4: ~700 evaluations per thread and pass) at 64-thread
-// blocks with R = 8 and a tile width that fills the 148 SMs in one wave.
+// Picks (T, R, TJ) by a small cost model.  A pass takes `waves` = ceil(tiles per rank / resident blocks) rounds of tiles;
+// in one round an SM runs (resident blocks per SM) x T threads, each doing (TJ + OV) column steps of R+1 square roots
+// (OV ~ the row loads, first column and end-of-tile barrier), and the SFU is what those threads share.  So
+//   time ~ waves x threads per SM x (TJ + OV) x (R + 1).
+// R = 16 (1.0625 sqrt per move, 150 registers -> 3 blocks of 128 threads per SM) wins on big instances, R = 8 with
+// 64-thread blocks (8 per SM) on mid-size ones (n ~ 10^4: ~700 evaluations per thread and pass, one wave of narrow tiles).
+static int bi_blocks_per_sm(int t, int r) { return r >= 16 ? (t == 256 ? 1 : 384 / t) : 512 / t; }
+
 static void choose_tile_shape(int n, int num_sms, int world, int opt_T, int opt_R, int opt_TJ, int *T, int *R, int *TJ) {
-    struct Shape { int t, r; };
-    const Shape cand[] = {{256, 8}, {128, 8}, {64, 8}, {64, 4}, {64, 2}};
+    struct Shape { int t, r; double penalty; };
+    const Shape cand[] = {{128, 16, 1.02}, {256, 8, 1.0}, {128, 8, 1.02}, {64, 8, 1.04}, {64, 4, 1.04}, {64, 2, 1.04}};
     const double OV = 16.0;
     double best = 1e300;
     int bt = 64, br = 2, btj = 32;
     for (const Shape &c : cand) {
         const int t = opt_T ? opt_T : c.t, r = opt_R ? opt_R : c.r;
         if (!bi_shape_supported(t, r)) continue;
-        const long long slots = (long long)num_sms * (r >= 16 ? 1 : 512 / t);
+        const int bps = bi_blocks_per_sm(t, r);
+        const long long slots = (long long)num_sms * bps;
         for (int tj = 32; tj <= 256; tj += 8) {
             const int tjj = opt_TJ ? opt_TJ : tj;
             const long long nt = tile_plan(n, t * r, tjj, nullptr, nullptr);
             const long long per_rank = (nt + world - 1) / world;
             const long long waves = (per_rank + slots - 1) / slots;
-            const double cost = (double)waves * (tjj + OV) * (r + 1) * (r >= 16 ? 2.0 : 1.0) * (1.0 + 0.02 * (256 / t - 1));
+            if (r >= 16 && waves < 4 && !opt_R) continue;  // 12 warps per SM hide the per-tile prologue only over several waves
+            const double cost = (double)waves * (bps * t) * (tjj + OV) * (r + 1) * c.penalty;
             if (cost < best) { best = cost; bt = t; br = r; btj = tjj; }
             if (opt_TJ) break;
         }
@@ -478,7 +483,7 @@ static void choose_tile_shape(int n, int num_sms, int world, int opt_T, int opt_
 
 static void plan_tiles(tspb200_ctx *ctx, std::vector<int> &row_start, std::vector<int> &row_j0) {
     choose_tile_shape(ctx->n, ctx->num_sms, ctx->world, ctx->opt_T, ctx->opt_R, ctx->opt_TJ, &ctx->T, &ctx->R, &ctx->TJ);
-    const int slots = ctx->num_sms * (ctx->R >= 16 ? 1 : 512 / ctx->T);
+    const int slots = ctx->num_sms * bi_blocks_per_sm(ctx->T, ctx->R);
     ctx->ntiles = (int)tile_plan(ctx->n, ctx->T * ctx->R, ctx->TJ, &row_start, &row_j0);
     ctx->ntr = (int)row_j0.size();
     long long per_rank = (ctx->ntiles + ctx->world - 1) / ctx->world;

@@ -100,7 +100,7 @@ __device__ __noinline__ MoveKey bi_cold_warp(const InstDev I, const float4 *srow
 // Shared memory per block (dynamic): two column buffers (TJ+2 records) and two row buffers (BI_THREADS*R+1 records),
 // each pair filled by TMA bulk copies on one mbarrier per stage, plus the tile tables.
 template <int BI_THREADS, int R, bool ATT, bool EXACT32>
-__global__ void __launch_bounds__(BI_THREADS, (R >= 16 ? 1 : 512 / BI_THREADS)) bi_scan_kernel(const BiArgs A) {
+__global__ void __launch_bounds__(BI_THREADS, (R >= 16 ? (BI_THREADS == 256 ? 1 : 384 / BI_THREADS) : 512 / BI_THREADS)) bi_scan_kernel(const BiArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long bars[2];
     __shared__ int s_hint;
@@ -635,7 +635,7 @@ static cudaError_t launch_bi_tr(const BiArgs &a, int grid, bool pdl, cudaStream_
 // supported (threads, rows per thread) shapes; anything else is rejected by tspb200_set_option
 bool bi_shape_supported(int threads, int rows_per_thread) {
     if (threads == 256) return rows_per_thread == 2 || rows_per_thread == 4 || rows_per_thread == 8 || rows_per_thread == 16;
-    if (threads == 128) return rows_per_thread == 4 || rows_per_thread == 8;
+    if (threads == 128) return rows_per_thread == 4 || rows_per_thread == 8 || rows_per_thread == 16;
     if (threads == 64) return rows_per_thread == 2 || rows_per_thread == 4 || rows_per_thread == 8;
     return false;
 }
@@ -648,6 +648,7 @@ cudaError_t launch_bi_scan(const BiArgs &a, int threads, int rows_per_thread, in
         if (R == 4) return launch_bi_tr<256, 4>(a, grid, pdl, st);
         if (R == 2) return launch_bi_tr<256, 2>(a, grid, pdl, st);
     } else if (threads == 128) {
+        if (R == 16) return launch_bi_tr<128, 16>(a, grid, pdl, st);
         if (R == 8) return launch_bi_tr<128, 8>(a, grid, pdl, st);
         if (R == 4) return launch_bi_tr<128, 4>(a, grid, pdl, st);
     } else if (threads == 64) {

@@ -334,19 +334,24 @@ def main():
     # (one sqrt) per evaluated move: every D[p][q] is shared by the two moves that use it.
     sqrt_peak = num_sms * 16 * sm_mhz * 1e6
     fp32_peak = num_sms * 128 * sm_mhz * 1e6
+    R = eng.info("rows_per_thread")
     roofline = {"bound": "sfu_sqrt", "achieved": per_gpu / 1e12, "peak": sqrt_peak / 1e12, "unit": "T sqrt/s (= T evals/s)",
-                "frac": per_gpu / sqrt_peak, "traffic": 1.7e6, "kernel": "bi_scan_kernel",
-                "per_unit": "1 MUFU.SQRT per evaluated move (algorithmic minimum; the kernel issues 1.125)",
+                "frac": per_gpu / sqrt_peak, "traffic": 1.715e6, "kernel": "bi_scan_kernel",
+                "per_unit": f"1 MUFU.SQRT per evaluated move (algorithmic minimum: every distance serves two moves); the kernel "
+                            f"issues (R+1)/R = {(R + 1) / R:.4f} with R = {R} rows per thread",
                 "peak_source": f"{num_sms} SMs x 16 MUFU/clk x {sm_mhz:.0f} MHz (nvidia-smi median under load); "
                                f"MEASURED_PEAKS.json ({peaks_src}) holds HBM and bf16 figures only, neither bounds this kernel",
+                "ncu": "profiles/r1_ncu_full_bi_scan_128x16_and_matrix.txt: XU pipe 81 % of peak, issue slots 56 %, "
+                       "6.03 thread instructions per evaluated move, DRAM 1.7 MB read / 0 written per launch",
                 "fp32_issue_view": {"survey_per_unit": FP32_INSTR_PER_EVAL,
                                     "frac_vs_survey_18_instr_model": per_gpu * FP32_INSTR_PER_EVAL / fp32_peak,
-                                    "executed_fp32_lane_ops_per_eval": 9.9,
-                                    "frac_executed": per_gpu * 9.9 / fp32_peak,
-                                    "note": "SURVEY.md §8d's 18 lane-instr/eval model evaluates two fresh distances per move; "
-                                            "sharing each distance between its two moves halves that, so the 18-instr "
-                                            "fraction exceeds 1 and is reported for reference only"},
-                "traffic_note": "dram__bytes_read.sum per launch from profiles/ (tour records, 16 B/node); compute-bound"}
+                                    "executed_thread_instr_per_eval": 6.03,
+                                    "frac_issue_slots": per_gpu * 6.03 / fp32_peak,
+                                    "note": "SURVEY.md §8d's 18 lane-instr/eval model evaluates two fresh distances per move with "
+                                            "scalar FP32; sharing each distance between its two moves and packed FP32x2 arithmetic "
+                                            "bring the executed count to 6.03, so the 18-instr fraction exceeds 1 and is reported "
+                                            "for reference only"},
+                "traffic_note": "dram__bytes_read.sum per launch (ncu --set full, cold L2): the tour records once, 16 B/node; compute-bound"}
     # secondary kernel: distance matrix, HBM-store-bound (4*n*ld bytes written per launch)
     mat = None
     if world == 1:
@@ -365,14 +370,16 @@ def main():
         ms = float(np.median(ms_list))
         gbs = 4.0 * nm * ld / (ms * 1e-3) / 1e9
         mat = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
-               "traffic": None, "kernel": "dist_matrix_kernel", "n": nm, "ms": ms,
+               "traffic": None, "traffic_note": "ncu at n = 20000: 1.544 GB written of 1.600 GB algorithmic (the rest is still dirty in L2 at kernel end), "
+                                                "0.3 MB read; gpu__dram_throughput 82 % of peak (profiles/r1_ncu_full_bi_scan_128x16_and_matrix.txt)",
+               "kernel": "dist_matrix_kernel", "n": nm, "ms": ms,
                "per_unit": "4 bytes written per matrix entry (int32), reads O(n)", "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peaks_src})"}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": gpu_ms / max(1, done_passes), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"uni{n} EUC_2D (SURVEY.md §8c generator), GPU nearest-neighbour start, best-improvement "
                                    f"2-opt passes with on-the-fly distances (BASELINE configs[3])",
-                       "n": n, "pairs_per_step": pairs, "rows_per_thread": eng.info("rows_per_thread"),
+                       "n": n, "pairs_per_step": pairs, "block_threads": eng.info("block_threads"), "rows_per_thread": eng.info("rows_per_thread"),
                        "tile_cols": eng.info("tile_cols"), "grid": eng.info("grid_bi"), "tiles": eng.info("ntiles"),
                        "sharding": ("tiles round-robin over ranks; per pass each rank's 8-byte argmin key is " +
                                     ("stored into every peer's slots over NVLink by the scan kernel (CUDA IPC peer memory)"

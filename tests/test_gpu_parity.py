@@ -501,3 +501,41 @@ def test_tabu_search_iterations_replayed(engine, oracle):
             tl[pos(b, b1)] = it
         if it % 10 == 0:
             tenure = 18 if tenure == 4 else 4
+
+
+# ---- batched nearest neighbour (reference HEU_Greedy_iter, src/heuristics.c:168-205) -------------------------------
+@pytest.mark.parametrize("nm", ["berlin52", "pr299", "att532", "gr666", "dsj1000", "ulysses22"])
+def test_nn_batch_every_start_equals_oracle(engine, oracle, instances, nm):
+    xy, wt = instances[nm]
+    n = len(xy)
+    engine.set_instance(xy, wt)
+    starts = np.arange(n, dtype=np.int32) if n <= 300 else np.random.default_rng(1).choice(n, size=64, replace=False).astype(np.int32)
+    for use_matrix in (False, True):
+        if use_matrix:
+            engine.dist_matrix_build()
+        succ, costs = engine.nn_tour_batch(starts)
+        for b, s0 in enumerate(starts):
+            osucc, ocost = oracle.nn_tour(xy, wt, int(s0))
+            assert (succ[b] == osucc).all() and costs[b] == ocost, (nm, int(s0))
+    engine.dist_matrix_free()
+
+
+def test_greedy_iter_equals_reference_driver(engine, reflib, instances):
+    """best-of-n-starts == the reference's own HEU_Greedy_iter (first strictly better start wins)."""
+    for nm in ("berlin52", "pr299", "rd400"):
+        xy, wt = instances[nm]
+        engine.set_instance(xy, wt)
+        best, succ, cost = engine.greedy_iter()
+        st, rsucc, robj = reflib.run_method("HEU_Greedy_iter", xy, wt)
+        assert st == 0 and cost == robj and (succ == rsucc).all(), nm
+
+
+def test_nn_batch_duplicate_points_and_ties(engine, oracle):
+    rng = np.random.default_rng(9)
+    xy = rng.integers(0, 12, size=(200, 2)).astype(np.float64)  # many equal distances and coincident nodes
+    engine.set_instance(xy, 0)
+    starts = np.arange(200, dtype=np.int32)
+    succ, costs = engine.nn_tour_batch(starts)
+    for b in range(0, 200, 7):
+        osucc, ocost = oracle.nn_tour(xy, 0, b)
+        assert (succ[b] == osucc).all() and costs[b] == ocost

@@ -47,6 +47,17 @@ if "c4" in which:
         dt = time.perf_counter() - t0
         out(cfg="c4 GA batch uni1000 x1024 random tours -> local optimum", mode=name, wall_s=dt, gpu_ms=st.gpu_ms, passes=st.passes,
             moves=st.moves, evals=st.evals, evals_per_s=st.evals / st.gpu_ms * 1e3, mean_cost=float(o.mean()))
+if "nnb" in which:
+    for nm in ("pr1002", "gr666"):
+        xy, wt = z[nm + "__xy"], int(z[nm + "__wt"])
+        eng.set_instance(xy, wt)
+        if wt == 4:
+            eng.dist_matrix_build()
+        eng.greedy_iter()
+        t0 = time.perf_counter()
+        best, succ, cost = eng.greedy_iter()
+        out(cfg="greedy_iter (n NN runs)", inst=nm, wall_ms=(time.perf_counter() - t0) * 1e3, best_start=best, cost=cost)
+        eng.dist_matrix_free()
 if "nn" in which:
     for n in (10000, 100000):
         eng.set_instance(uniform_instance(n), 0)

@@ -37,6 +37,8 @@ cudaError_t launch_tour_cost(const InstDev &I, const int *tours, int as_order, l
 cudaError_t launch_nn_tour(const NnArgs &a, int grid, cudaStream_t st);
 cudaError_t launch_prep_points(const double2 *raw, double2 *pt64, float2 *pt32, int n, int metric, cudaStream_t st);
 int nn_max_grid(int num_sms);
+cudaError_t launch_nn_batch(const InstDev &I, const int *starts, int batch, int *succ_out, long long *cost_out, float eps,
+                            int num_sms, cudaStream_t st);
 cudaError_t launch_two_opt_batch(const InstDev &I, int mode, int *succ, long long *obj_delta, long long *counters,
                                  int batch, int num_sms, cudaStream_t st, int *launched);
 
@@ -985,6 +987,39 @@ int tspb200_nn_tour(tspb200_ctx *ctx, int start, int32_t *succ, double *cost) {
     cudaFree(d_succ); cudaFree(d_vis); cudaFree(d_slots); cudaFree(d_bar); cudaFree(d_cost);
     if (le != cudaSuccess) return fail(ctx, TSPB200_E_CUDA, "nearest-neighbour kernel failed: %s", cudaGetErrorString(le));
     if (cost) *cost = (double)c;
+    return TSPB200_OK;
+}
+
+// Batched nearest neighbour: `batch` independent greedy() runs, one thread block each (reference HEU_Greedy_iter,
+// src/heuristics.c:168-205, is this with starts = 0..n-1 followed by "keep the first strictly better tour").
+int tspb200_nn_tour_batch(tspb200_ctx *ctx, const int32_t *starts, int batch, int32_t *succ, double *costs) {
+    if (!ctx || !ctx->stream) return fail(ctx, TSPB200_E_CUDA, "context has no CUDA device");
+    if (ctx->n < 1) return fail(ctx, TSPB200_E_STATE, "no instance");
+    if (!starts || !costs || batch < 1) return fail(ctx, TSPB200_E_ARG, "bad arguments");
+    const int n = ctx->n;
+    for (int b = 0; b < batch; ++b)
+        if (starts[b] < 0 || starts[b] >= n) return fail(ctx, TSPB200_E_ARG, "start node %d out of range", starts[b]);  // WRONG_STARTING_NODE
+    CK(cudaSetDevice(ctx->device));
+    int path = select_path(ctx);
+    if (path == 2 && !ctx->d_mat) path = 1;
+    InstDev I = inst_for_path(ctx, path == 2 ? 2 : 1);
+    I.fp32_ok = ctx->inst.fp32_ok;  // the FP32 filter of the batched kernel is valid whenever the 2-opt filter is
+    const float eps = (ctx->inst.W - 2.0f) * 0.5f;
+    int *d_starts = nullptr, *d_succ = nullptr;
+    long long *d_cost = nullptr;
+    CK(cudaMalloc(&d_starts, sizeof(int) * (size_t)batch));
+    CK(cudaMalloc(&d_cost, sizeof(long long) * (size_t)batch));
+    if (succ) CK(cudaMalloc(&d_succ, sizeof(int) * (size_t)batch * n));
+    CK(cudaMemcpyAsync(d_starts, starts, sizeof(int) * (size_t)batch, cudaMemcpyHostToDevice, ctx->stream));
+    cudaError_t le = launch_nn_batch(I, d_starts, batch, d_succ, d_cost, eps, ctx->num_sms, ctx->stream);
+    std::vector<long long> h((size_t)batch);
+    if (le == cudaSuccess && succ) le = cudaMemcpyAsync(succ, d_succ, sizeof(int) * (size_t)batch * n, cudaMemcpyDeviceToHost, ctx->stream);
+    if (le == cudaSuccess) le = cudaMemcpyAsync(h.data(), d_cost, sizeof(long long) * (size_t)batch, cudaMemcpyDeviceToHost, ctx->stream);
+    if (le == cudaSuccess) le = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_starts); cudaFree(d_succ); cudaFree(d_cost);
+    if (le == cudaErrorInvalidValue) return fail(ctx, TSPB200_E_UNSUPPORTED, "batched nearest neighbour keeps the coordinates in shared memory: n=%d is too large", n);
+    if (le != cudaSuccess) return fail(ctx, TSPB200_E_CUDA, "batched nearest-neighbour kernel failed: %s", cudaGetErrorString(le));
+    for (int b = 0; b < batch; ++b) costs[b] = (double)h[(size_t)b];
     return TSPB200_OK;
 }
 

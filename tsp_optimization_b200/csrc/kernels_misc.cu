@@ -357,4 +357,109 @@ cudaError_t launch_nn_tour(const NnArgs &a, int grid, cudaStream_t st) {
     return cudaLaunchCooperativeKernel((const void *)nn_tour_kernel, dim3(grid), dim3(256), params, 0, st);
 }
 
+// ---- batched nearest neighbour: one block per start node (reference src/heuristics.c:168-205 HEU_Greedy_iter = n
+// independent greedy() runs; also multi-start seeds for VNS / tabu / GA) -----------------------------------------------
+// Per step the block finds argmin over the unvisited nodes of the exact integer distance, lowest index among equals
+// (strict '<' scan of reference heuristics.c:44-55).  FP32 is only a filter: pass 1 takes the block minimum m of the FP32
+// distances; an exact integer distance differs from the real one by less than 1, so only nodes with an FP32 distance
+// <= m + 1 + 2*eps can hold the minimum — pass 2 evaluates those exactly (FP64 / matrix) and reduces (distance, index).
+constexpr int NNB_THREADS = 256;
+
+__global__ void __launch_bounds__(NNB_THREADS) nn_batch_kernel(const InstDev I, const int *starts, int batch, int *succ_out,
+                                                               long long *cost_out, float eps) {
+    extern __shared__ __align__(16) unsigned char nnb_smem[];
+    __shared__ float s_min[NNB_THREADS / 32];
+    __shared__ unsigned long long s_key[NNB_THREADS / 32];
+    const int n = I.n;
+    float2 *sxy = reinterpret_cast<float2 *>(nnb_smem);
+    unsigned char *vis = reinterpret_cast<unsigned char *>(sxy + n);
+    const int tid = threadIdx.x;
+    const bool filter = I.fp32_ok != 0 && I.dmat == nullptr;
+    for (int b = blockIdx.x; b < batch; b += gridDim.x) {
+        const int start = starts[b];
+        for (int k = tid; k < n; k += NNB_THREADS) {
+            sxy[k] = I.pt32[k];
+            vis[k] = (k == start) ? 1 : 0;
+        }
+        __syncthreads();
+        int cur = start;
+        long long total = 0;
+        int *succ = succ_out ? succ_out + (long long)b * n : nullptr;
+        for (int step = 0; step < n - 1; ++step) {
+            float thr = 3.0e38f;
+            if (filter) {
+                const float2 pc = sxy[cur];
+                float m = 3.0e38f;
+                for (int k = tid; k < n; k += NNB_THREADS) {
+                    if (vis[k]) continue;
+                    const float dx = pc.x - sxy[k].x, dy = pc.y - sxy[k].y;
+                    float s2 = fmaf(dy, dy, dx * dx);
+                    if (I.metric == M_ATT) s2 *= 0.1f;
+                    m = fminf(m, sqrt_approx(s2));
+                }
+                for (int w = 16; w > 0; w >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, w));
+                if ((tid & 31) == 0) s_min[tid >> 5] = m;
+                __syncthreads();
+                m = s_min[0];
+#pragma unroll
+                for (int w = 1; w < NNB_THREADS / 32; ++w) m = fminf(m, s_min[w]);
+                thr = m + 1.0f + 2.0f * eps;
+            }
+            unsigned long long best = ~0ull;
+            {
+                const float2 pc = sxy[cur];
+                for (int k = tid; k < n; k += NNB_THREADS) {
+                    if (vis[k]) continue;
+                    if (filter) {
+                        const float dx = pc.x - sxy[k].x, dy = pc.y - sxy[k].y;
+                        float s2 = fmaf(dy, dy, dx * dx);
+                        if (I.metric == M_ATT) s2 *= 0.1f;
+                        if (sqrt_approx(s2) > thr) continue;
+                    }
+                    const unsigned long long key = ((unsigned long long)dist_nodes(I, cur, k) << 32) | (unsigned)k;
+                    best = key < best ? key : best;
+                }
+            }
+            for (int w = 16; w > 0; w >>= 1) {
+                const unsigned long long o = __shfl_xor_sync(0xffffffffu, best, w);
+                best = o < best ? o : best;
+            }
+            if ((tid & 31) == 0) s_key[tid >> 5] = best;
+            __syncthreads();
+            best = s_key[0];
+#pragma unroll
+            for (int w = 1; w < NNB_THREADS / 32; ++w) best = s_key[w] < best ? s_key[w] : best;
+            const int nxt = (int)(best & 0xffffffffu);
+            total += (long long)(best >> 32);
+            if (tid == 0) {
+                if (succ) succ[cur] = nxt;
+                vis[nxt] = 1;
+            }
+            cur = nxt;
+            __syncthreads();
+        }
+        if (tid == 0) {
+            if (succ) succ[cur] = start;  // closing edge, reference heuristics.c:59-62,74
+            cost_out[b] = total + dist_nodes(I, cur, start);
+        }
+        __syncthreads();
+    }
+}
+
+cudaError_t launch_nn_batch(const InstDev &I, const int *starts, int batch, int *succ_out, long long *cost_out, float eps,
+                            int num_sms, cudaStream_t st) {
+    const size_t smem = (size_t)I.n * (sizeof(float2) + 1) + 16;
+    if (smem > 200 * 1024) return cudaErrorInvalidValue;
+    cudaError_t e = cudaFuncSetAttribute(nn_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int occ = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, nn_batch_kernel, NNB_THREADS, smem);
+    if (e != cudaSuccess) return e;
+    if (occ < 1) return cudaErrorInvalidValue;
+    int grid = num_sms * occ;
+    if (grid > batch) grid = batch;
+    nn_batch_kernel<<<grid, NNB_THREADS, smem, st>>>(I, starts, batch, succ_out, cost_out, eps);
+    return cudaGetLastError();
+}
+
 }  // namespace tspb

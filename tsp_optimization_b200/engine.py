@@ -30,7 +30,7 @@ ABI_SYMBOLS = [
     "tspb200_create", "tspb200_destroy", "tspb200_last_error", "tspb200_set_option", "tspb200_get_info",
     "tspb200_set_instance", "tspb200_dist_matrix_build", "tspb200_dist_matrix_get", "tspb200_dist_matrix",
     "tspb200_dist_matrix_free", "tspb200_tour_upload", "tspb200_tour_download", "tspb200_tour_log",
-    "tspb200_bi_run", "tspb200_fi_run", "tspb200_two_opt", "tspb200_two_opt_tabu", "tspb200_two_opt_batch", "tspb200_nn_tour",
+    "tspb200_bi_run", "tspb200_fi_run", "tspb200_two_opt", "tspb200_two_opt_tabu", "tspb200_two_opt_batch", "tspb200_nn_tour", "tspb200_nn_tour_batch",
     "tspb200_tour_costs", "tspb200_comm_unique_id", "tspb200_comm_init", "tspb200_comm_destroy",
     "tspb200_debug_tile_plan",
 ]
@@ -106,6 +106,7 @@ def load_library() -> C.CDLL:
                                        C.POINTER(_Stats), C.c_void_p, i64, C.POINTER(i64)]
     L.tspb200_two_opt_batch.argtypes = [vp, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(_Stats)]
     L.tspb200_nn_tour.argtypes = [vp, C.c_int, C.c_void_p, C.POINTER(C.c_double)]
+    L.tspb200_nn_tour_batch.argtypes = [vp, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     L.tspb200_tour_costs.argtypes = [vp, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     L.tspb200_comm_unique_id.argtypes = [C.c_void_p]
     L.tspb200_comm_init.argtypes = [vp, C.c_void_p, C.c_int, C.c_int]
@@ -277,6 +278,23 @@ class Engine:
         cost = C.c_double(0)
         self._ck(self.L.tspb200_nn_tour(self.h, start, succ.ctypes.data, C.byref(cost)))
         return succ, cost.value
+
+    def nn_tour_batch(self, starts, want_tours: bool = True):
+        """`len(starts)` independent greedy() runs -> (succ[batch, n] or None, costs[batch])."""
+        starts = np.ascontiguousarray(starts, dtype=np.int32)
+        b = len(starts)
+        succ = np.empty((b, self.n), dtype=np.int32) if want_tours else None
+        costs = np.empty(b, dtype=np.float64)
+        self._ck(self.L.tspb200_nn_tour_batch(self.h, starts.ctypes.data, b, succ.ctypes.data if want_tours else None,
+                                              costs.ctypes.data))
+        return succ, costs
+
+    def greedy_iter(self):
+        """reference HEU_Greedy_iter (src/heuristics.c:168-205): NN from every node, the first strictly better tour wins."""
+        _, costs = self.nn_tour_batch(np.arange(self.n, dtype=np.int32), want_tours=False)
+        best = int(np.argmin(costs))  # argmin returns the first minimum == reference's strict '<' over increasing starts
+        succ, c = self.nn_tour_batch(np.array([best], dtype=np.int32))
+        return best, succ[0], float(c[0])
 
     def tour_costs(self, tours, as_order: bool) -> np.ndarray:
         tours = np.ascontiguousarray(tours, dtype=np.int32).reshape(-1, self.n)

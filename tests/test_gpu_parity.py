@@ -539,3 +539,86 @@ def test_nn_batch_duplicate_points_and_ties(engine, oracle):
     for b in range(0, 200, 7):
         osucc, ocost = oracle.nn_tour(xy, 0, b)
         assert (succ[b] == osucc).all() and costs[b] == ocost
+
+
+# ---- edge cases: tiny tours, caps, limits ------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 6, 7, 9, 33, 64, 65, 129])
+def test_tiny_instances_all_paths(engine, oracle, n):
+    """n < 4 has no non-adjacent pair at all (one empty pass / sweep); n = 4, 5 have 2 and 5.  Every entry point must agree
+    with the oracle: matrix, NN, BI (grid, exact, matrix and batched kernels), FI (grid and batched), tour costs."""
+    rng = np.random.default_rng(n)
+    xy = rng.integers(0, 50, size=(n, 2)).astype(np.float64)
+    engine.set_instance(xy, 0)
+    assert (engine.dist_matrix() == oracle.dist_matrix(xy, 0)).all()
+    engine.dist_matrix_free()
+    succ0 = order_to_succ(rng.permutation(n).astype(np.int32))
+    cost0 = oracle.succ_cost(xy, 0, succ0)
+    assert engine.tour_costs(succ0[None, :], as_order=False)[0] == cost0
+    nn, nnc = engine.nn_tour(0)
+    onn, onnc = oracle.nn_tour(xy, 0, 0)
+    assert (nn == onn).all() and nnc == onnc
+    es, eobj, est, elog = oracle.two_opt_bi(xy, 0, succ0, log_cap=1000)
+    for fp in (-1, 1, 2):
+        engine.set_option("force_path", fp)
+        if fp == 2:
+            engine.dist_matrix_build()
+        s, obj, st, log = engine.two_opt(BI, succ0, 0.0, log_cap=1000)
+        assert log.tolist() == elog.tolist() and (s == es).all() and obj == eobj and st.passes == est.passes, (n, fp)
+    engine.set_option("force_path", -1)
+    engine.dist_matrix_free()
+    fs, fobj, fst, flog = oracle.two_opt_fi(xy, 0, succ0, cost0, log_cap=1000)
+    s, obj, st, log = engine.two_opt(FI, succ0, cost0, log_cap=1000)
+    assert log.tolist() == flog.tolist() and (s == fs).all() and obj == fobj and st.passes == fst.passes
+    sb, ob, _ = engine.two_opt_batch(BI, np.stack([succ0, succ0]), np.array([0.0, 0.0]))
+    assert (sb[0] == es).all() and (sb[1] == es).all() and ob[0] == eobj
+    sb, ob, _ = engine.two_opt_batch(FI, np.stack([succ0]), np.array([cost0]))
+    assert (sb[0] == fs).all() and ob[0] == fobj
+
+
+def test_pass_and_move_caps_resume_where_they_stopped(engine, oracle):
+    """max_passes / max_moves stop early with status STOPPED_BY_CAP; repeated capped calls on the resident tour walk through
+    exactly the oracle's move sequence."""
+    xy = uniform_instance(700)
+    succ0, c0 = oracle.nn_tour(xy, 0, 0)
+    engine.set_instance(xy, 0)
+    _, _, est, elog = oracle.two_opt_bi(xy, 0, succ0, log_cap=100000)
+    engine.tour_upload(succ0, log_cap=100000)
+    total = 0
+    while True:
+        st = engine.bi_run(7)
+        total += st.passes
+        if st.status == eng.LOCAL_OPTIMUM:
+            break
+        assert st.status == eng.STOPPED_BY_CAP and st.passes == 7
+    assert total == est.passes and engine.tour_log(100000).tolist() == elog.tolist()
+    _, _, fst, flog = oracle.two_opt_fi(xy, 0, succ0, c0, log_cap=100000)
+    engine.tour_upload(succ0, log_cap=100000)
+    while True:
+        st = engine.fi_run(5)
+        if st.status == eng.LOCAL_OPTIMUM:
+            break
+        assert st.status == eng.STOPPED_BY_CAP and st.moves == 5
+    assert engine.tour_log(100000).tolist() == flog.tolist()
+
+
+def test_time_limit_returns_reference_status(engine):
+    """a 1 ms budget on a 20 000-node tour: status TIME_LIMIT_EXCEEDED (reference include/heuristics.h:7), tour still valid."""
+    xy = uniform_instance(20000)
+    engine.set_instance(xy, 0)
+    succ0, _ = engine.nn_tour(0)
+    engine.set_option("time_limit_ms", 1)
+    try:
+        s, obj, st, _ = engine.two_opt(BI, succ0, 0.0)
+        assert st.status == eng.TIME_LIMIT_EXCEEDED and is_tour(s)
+        assert obj == engine.tour_costs(s[None, :], as_order=False)[0]
+    finally:
+        engine.set_option("time_limit_ms", 0)
+
+
+def test_large_coordinates_take_the_exact_path(engine, oracle):
+    """pla85900-like coordinates (~1.4e6, beyond the FP32 filter's validity window dmax < 4e6 only just): parity on BI."""
+    rng = np.random.default_rng(77)
+    xy = rng.integers(0, 3_500_000, size=(400, 2)).astype(np.float64)
+    succ0, _ = oracle.nn_tour(xy, 3, 0)
+    _check_bi(engine, oracle, xy, 3, succ0)
+    assert engine.info("fp32_ok") == 0

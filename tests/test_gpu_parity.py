@@ -154,15 +154,23 @@ def test_matrix_large_checksum_property(engine, oracle):
 
 # ---- 2-opt, single tour --------------------------------------------------------------------------------------
 def _check_bi(engine, oracle, xy, wt, succ0, max_passes=-1, force_path=-1):
+    """grid kernels (single_block 0) AND, when the run goes to the local optimum and the tour fits, the one-block kernel
+    (single_block 1): both must reproduce the oracle's move log, tour, cost and counters."""
     engine.set_option("force_path", force_path)
     engine.set_instance(xy, wt)
     if force_path == 2 or (force_path == -1 and wt in (1, 2, 4)):
         engine.dist_matrix_build()
-    s, obj, st, log = engine.two_opt(BI, succ0, 0.0, max_iters=max_passes, log_cap=100000)
     os_, oobj, ost, olog = oracle.two_opt_bi(xy, wt, succ0, max_passes=max_passes, log_cap=100000)
-    assert log.tolist() == olog.tolist()
-    assert (s == os_).all() and obj == oobj
-    assert st.moves == ost.moves and st.passes == ost.passes and st.evals == ost.evals
+    st = None
+    for route in ((0, 1) if (max_passes < 0 and len(xy) <= 2000) else (0,)):
+        engine.set_option("single_block", route)
+        s, obj, st_r, log = engine.two_opt(BI, succ0, 0.0, max_iters=max_passes, log_cap=100000)
+        assert log.tolist() == olog.tolist(), route
+        assert (s == os_).all() and obj == oobj, route
+        assert st_r.moves == ost.moves and st_r.passes == ost.passes and st_r.evals == ost.evals, route
+        assert st_r.launches == 1 or route == 0
+        st = st or st_r
+    engine.set_option("single_block", -1)
     engine.set_option("force_path", -1)
     return st
 
@@ -172,11 +180,16 @@ def _check_fi(engine, oracle, xy, wt, succ0, obj0, force_path=-1):
     engine.set_instance(xy, wt)
     if force_path == 2 or (force_path == -1 and wt in (1, 2, 4)):
         engine.dist_matrix_build()
-    s, obj, st, log = engine.two_opt(FI, succ0, obj0, log_cap=100000)
     os_, oobj, ost, olog = oracle.two_opt_fi(xy, wt, succ0, obj0, log_cap=100000)
-    assert log.tolist() == olog.tolist()
-    assert (s == os_).all() and obj == oobj
-    assert st.moves == ost.moves and st.passes == ost.passes
+    st = None
+    for route in ((0, 1) if len(xy) <= 5000 else (0,)):
+        engine.set_option("single_block", route)
+        s, obj, st_r, log = engine.two_opt(FI, succ0, obj0, log_cap=100000)
+        assert log.tolist() == olog.tolist(), route
+        assert (s == os_).all() and obj == oobj, route
+        assert st_r.moves == ost.moves and st_r.passes == ost.passes, route
+        st = st or st_r
+    engine.set_option("single_block", -1)
     engine.set_option("force_path", -1)
     return st
 

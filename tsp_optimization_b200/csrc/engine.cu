@@ -40,7 +40,7 @@ int nn_max_grid(int num_sms);
 cudaError_t launch_nn_batch(const InstDev &I, const int *starts, int batch, int *succ_out, long long *cost_out, float eps,
                             int num_sms, cudaStream_t st);
 cudaError_t launch_two_opt_batch(const InstDev &I, int mode, int *succ, long long *obj_delta, long long *counters,
-                                 int batch, int num_sms, cudaStream_t st, int *launched);
+                                 int batch, int num_sms, cudaStream_t st, int *launched, MoveRec *log, long long log_cap);
 
 // ---- NCCL, loaded at run time (the torch-bundled or system libnccl.so.2) -------------------------------
 typedef struct { char internal[128]; } nccl_unique_id;
@@ -115,6 +115,7 @@ struct tspb200_ctx {
     long long opt_time_limit_ms = 0;
     int opt_seed_hint = 1;
     int opt_pdl = 1;
+    int opt_single_block = -1;  // -1 auto, 0 never, 1 whenever the tour fits in shared memory
     // benchmark hygiene: write this many bytes (> L2) before every pass and time each pass with its own event pair
     long long opt_flush_bytes = 0;
     unsigned char *d_flush = nullptr;
@@ -262,6 +263,9 @@ int tspb200_set_option(tspb200_ctx *ctx, const char *key, int64_t value) {
     } else if (k == "l2_flush_bytes") {
         if (value < 0) return fail(ctx, TSPB200_E_ARG, "l2_flush_bytes must be >= 0");
         ctx->opt_flush_bytes = value;
+    } else if (k == "single_block") {
+        if (value < -1 || value > 1) return fail(ctx, TSPB200_E_ARG, "single_block must be -1 (auto), 0 or 1");
+        ctx->opt_single_block = (int)value;
     } else if (k == "pdl") {
         ctx->opt_pdl = value ? 1 : 0;
     } else if (k == "seed_hint") {
@@ -612,6 +616,9 @@ int tspb200_tour_log(tspb200_ctx *ctx, tspb200_move *log, int64_t cap, int64_t *
     return TSPB200_OK;
 }
 
+static int run_batch(tspb200_ctx *ctx, int mode, int32_t *succ, double *obj, int batch, tspb200_stats *st, tspb200_move *log,
+                     int64_t log_cap, int64_t *log_count);
+
 static int sync_ctl(tspb200_ctx *ctx) {
     CK(cudaMemcpyAsync(ctx->h_ctl, ctx->d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -825,6 +832,25 @@ int tspb200_two_opt(tspb200_ctx *ctx, int mode, int32_t *succ, double *obj, int6
                     tspb200_move *log, int64_t log_cap, int64_t *log_count) {
     if (!ctx || !ctx->stream) return fail(ctx, TSPB200_E_CUDA, "context has no CUDA device");
     if (mode != TSPB200_FI && mode != TSPB200_BI) return fail(ctx, TSPB200_E_ARG, "mode must be TSPB200_FI or TSPB200_BI");
+    // TSPLIB-size tours run to their local optimum inside ONE thread block with the tour in shared memory: no launch per
+    // move, which is what a ~1000-node tour is bound by on the grid path (FI: ~30 us per move; BI: ~16 us per pass).
+    // Crossover measured on B200: FI up to 4096 nodes, BI up to 128 (pr299: grid 0.8 ms vs one block 1.9 ms).
+    {
+        const int n = ctx->n;
+        const int lim = mode == TSPB200_FI ? 4096 : 128;
+        const bool want = ctx->opt_single_block < 0 ? (n >= 1 && n <= lim) : (ctx->opt_single_block == 1 && n * 24 + 16 <= 200 * 1024);
+        if (want && max_iters < 0 && ctx->world == 1 && !ctx->tabu_on && ctx->opt_time_limit_ms <= 0 && succ) {
+            double o = obj ? *obj : 0.0;
+            tspb200_stats local;
+            int rc = run_batch(ctx, mode, succ, &o, 1, &local, log, log ? log_cap : 0, log_count);
+            if (rc) return rc;
+            if (obj) *obj = o;
+            local.cost = o;
+            if (st) *st = local;
+            ctx->has_tour = false;  // the resident-tour state was not touched; make a stale one unusable
+            return TSPB200_OK;
+        }
+    }
     int rc = tspb200_tour_upload(ctx, succ, log ? log_cap : 0);
     if (rc) return rc;
     tspb200_stats local;
@@ -896,7 +922,10 @@ int tspb200_two_opt_tabu(tspb200_ctx *ctx, int32_t *succ, double *obj, int32_t *
     return TSPB200_OK;
 }
 
-int tspb200_two_opt_batch(tspb200_ctx *ctx, int mode, int32_t *succ, double *obj, int batch, tspb200_stats *st) {
+// One thread block per tour, whole tour state in shared memory (csrc/kernels_batch.cu).  log / log_count: only for
+// batch == 1 (the single-tour route of tspb200_two_opt for TSPLIB-size instances).
+static int run_batch(tspb200_ctx *ctx, int mode, int32_t *succ, double *obj, int batch, tspb200_stats *st, tspb200_move *log,
+                     int64_t log_cap, int64_t *log_count) {
     if (!ctx || !ctx->stream) return fail(ctx, TSPB200_E_CUDA, "context has no CUDA device");
     if (ctx->n < 1) return fail(ctx, TSPB200_E_STATE, "no instance");
     if (mode != TSPB200_FI && mode != TSPB200_BI) return fail(ctx, TSPB200_E_ARG, "mode must be TSPB200_FI or TSPB200_BI");
@@ -908,17 +937,20 @@ int tspb200_two_opt_batch(tspb200_ctx *ctx, int mode, int32_t *succ, double *obj
     InstDev I = inst_for_path(ctx, path);
     int *d_succ = nullptr;
     long long *d_delta = nullptr, *d_cnt = nullptr;
+    MoveRec *d_log = nullptr;
+    const long long lcap = (log && batch == 1 && log_cap > 0) ? log_cap : 0;
     CK(cudaMalloc(&d_succ, sizeof(int) * (size_t)n * batch));
     CK(cudaMalloc(&d_delta, sizeof(long long) * (size_t)batch));
     CK(cudaMalloc(&d_cnt, sizeof(long long) * 4 * (size_t)batch));
+    if (lcap) CK(cudaMalloc(&d_log, sizeof(MoveRec) * (size_t)lcap));
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
     CK(cudaMemcpyAsync(d_succ, succ, sizeof(int) * (size_t)n * batch, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemsetAsync(d_delta, 0, sizeof(long long) * (size_t)batch, ctx->stream));
     CK(cudaMemsetAsync(d_cnt, 0, sizeof(long long) * 4 * (size_t)batch, ctx->stream));
     int launched = 0;
-    cudaError_t le = launch_two_opt_batch(I, mode, d_succ, d_delta, d_cnt, batch, ctx->num_sms, ctx->stream, &launched);
+    cudaError_t le = launch_two_opt_batch(I, mode, d_succ, d_delta, d_cnt, batch, ctx->num_sms, ctx->stream, &launched, d_log, lcap);
     if (le != cudaSuccess) {
-        cudaFree(d_succ); cudaFree(d_delta); cudaFree(d_cnt);
+        cudaFree(d_succ); cudaFree(d_delta); cudaFree(d_cnt); cudaFree(d_log);
         if (le == cudaErrorInvalidValue) return fail(ctx, TSPB200_E_UNSUPPORTED, "batched 2-opt keeps a tour in shared memory: n=%d is too large", n);
         return fail(ctx, TSPB200_E_CUDA, "batched 2-opt launch failed: %s", cudaGetErrorString(le));
     }
@@ -928,15 +960,22 @@ int tspb200_two_opt_batch(tspb200_ctx *ctx, int mode, int32_t *succ, double *obj
     CK(cudaMemcpyAsync(h_cnt.data(), d_cnt, sizeof(long long) * 4 * (size_t)batch, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    cudaFree(d_succ); cudaFree(d_delta); cudaFree(d_cnt);
+    if (lcap) {
+        long long have = h_cnt[0] < lcap ? h_cnt[0] : lcap;
+        static_assert(sizeof(tspb200_move) == sizeof(MoveRec), "log record layout");
+        if (have > 0) CK(cudaMemcpy(log, d_log, sizeof(MoveRec) * (size_t)have, cudaMemcpyDeviceToHost));
+    }
+    if (log_count) *log_count = batch == 1 ? h_cnt[0] : 0;
+    cudaFree(d_succ); cudaFree(d_delta); cudaFree(d_cnt); cudaFree(d_log);
     tspb200_stats local;
     memset(&local, 0, sizeof local);
     for (int b = 0; b < batch; ++b) {
         local.moves += h_cnt[4 * b + 0];
         local.passes += h_cnt[4 * b + 1];
         local.evals += h_cnt[4 * b + 2];
-        if (h_cnt[4 * b + 3]) return fail(ctx, TSPB200_E_DEVICE_CHECK, "batched 2-opt: tour %d failed its device-side check", b);
-        local.obj_delta += h_delta[b];
+        if (h_cnt[4 * b + 3]) return fail(ctx, mode >= 0 && batch == 1 ? TSPB200_E_ARG : TSPB200_E_DEVICE_CHECK,
+                                          "2-opt: succ[] of tour %d is not a single cycle over %d nodes", b, n);
+        if (mode == TSPB200_FI) local.obj_delta += h_delta[b];
         if (obj) {
             if (mode == TSPB200_BI) obj[b] = (double)h_delta[b];  // kernel stores the recomputed cost for BI
             else obj[b] += (double)h_delta[b];
@@ -947,8 +986,14 @@ int tspb200_two_opt_batch(tspb200_ctx *ctx, int mode, int32_t *succ, double *obj
     local.gpu_ms = ms;
     local.launches = launched;
     local.path = path;
+    local.status = TSPB200_LOCAL_OPTIMUM;
+    if (batch == 1) local.cost = obj ? obj[0] : 0.0;
     if (st) *st = local;
     return TSPB200_OK;
+}
+
+int tspb200_two_opt_batch(tspb200_ctx *ctx, int mode, int32_t *succ, double *obj, int batch, tspb200_stats *st) {
+    return run_batch(ctx, mode, succ, obj, batch, st, nullptr, 0, nullptr);
 }
 
 int tspb200_nn_tour(tspb200_ctx *ctx, int start, int32_t *succ, double *cost) {

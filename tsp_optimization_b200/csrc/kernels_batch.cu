@@ -81,7 +81,8 @@ __device__ __forceinline__ void bt_apply(const InstDev &I, const BatchSmem &S, b
 
 template <bool ATT, bool EXACT32, bool FP32_OK>
 __global__ void __launch_bounds__(BATCH_THREADS) two_opt_batch_kernel(const InstDev I, int mode, int *succ_all,
-                                                                      long long *obj_out, long long *counters, int batch) {
+                                                                      long long *obj_out, long long *counters, int batch,
+                                                                      MoveRec *log, long long log_cap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int s_minj;
     __shared__ int s_err;
@@ -152,6 +153,11 @@ __global__ void __launch_bounds__(BATCH_THREADS) two_opt_batch_kernel(const Inst
                     __syncthreads();
                     passes++;
                     if (best.delta >= 0) break;
+                    if (log && tid == 0 && moves < log_cap) {
+                        MoveRec mr;
+                        mr.i = best.i; mr.j = best.j; mr.delta = best.delta;
+                        log[moves] = mr;
+                    }
                     bt_apply(I, S, ex32, n, best.i, best.j);
                     moves++;
                     objd += best.delta;
@@ -166,6 +172,7 @@ __global__ void __launch_bounds__(BATCH_THREADS) two_opt_batch_kernel(const Inst
                     bool found = false;
                     int fi = 0, fj = 0;
                     long long fdelta = 0;
+                    const long long lin0 = (long long)ci * n + cj;  // statistics: linear pairs swept, like the grid kernel
                     for (int row = ci; row < n - 1 && !found; ++row) {
                         const float xi = S.sx[row], yi = S.sy[row], dsi = S.dsn[row];
                         const int si = S.succ[row];
@@ -192,7 +199,13 @@ __global__ void __launch_bounds__(BATCH_THREADS) two_opt_batch_kernel(const Inst
                         __syncthreads();
                     }
                     bool sweep_end = !found;
+                    evals += found ? ((long long)fi * n + fj - lin0 + 1) : ((long long)(n - 1) * n - lin0);
                     if (found) {
+                        if (log && tid == 0 && moves < log_cap) {
+                            MoveRec mr;
+                            mr.i = fi; mr.j = fj; mr.delta = fdelta;
+                            log[moves] = mr;
+                        }
                         bt_apply(I, S, ex32, n, fi, fj);
                         moves++; sweep_moves++;
                         objd += fdelta;
@@ -245,7 +258,7 @@ __global__ void __launch_bounds__(BATCH_THREADS) two_opt_batch_kernel(const Inst
 
 template <bool ATT, bool EXACT32, bool FP32_OK>
 static cudaError_t launch_batch_t(const InstDev &I, int mode, int *succ, long long *obj, long long *counters, int batch,
-                                  int num_sms, cudaStream_t st, int *launched) {
+                                  int num_sms, cudaStream_t st, int *launched, MoveRec *log, long long log_cap) {
     size_t smem = (size_t)I.n * 24 + 16;
     auto kern = two_opt_batch_kernel<ATT, EXACT32, FP32_OK>;
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
@@ -257,20 +270,20 @@ static cudaError_t launch_batch_t(const InstDev &I, int mode, int *succ, long lo
     if (occ < 1) return cudaErrorInvalidValue;
     int grid = num_sms * occ;
     if (grid > batch) grid = batch;
-    kern<<<grid, BATCH_THREADS, smem, st>>>(I, mode, succ, obj, counters, batch);
+    kern<<<grid, BATCH_THREADS, smem, st>>>(I, mode, succ, obj, counters, batch, batch == 1 ? log : nullptr, log_cap);
     if (launched) *launched = 1;
     return cudaGetLastError();
 }
 
 cudaError_t launch_two_opt_batch(const InstDev &I, int mode, int *succ, long long *obj, long long *counters, int batch,
-                                 int num_sms, cudaStream_t st, int *launched) {
+                                 int num_sms, cudaStream_t st, int *launched, MoveRec *log, long long log_cap) {
     const bool att = (I.metric == M_ATT);
     const bool ex = I.exact32 != 0;
-    if (!I.fp32_ok) return launch_batch_t<false, false, false>(I, mode, succ, obj, counters, batch, num_sms, st, launched);
-    if (att && ex) return launch_batch_t<true, true, true>(I, mode, succ, obj, counters, batch, num_sms, st, launched);
-    if (att) return launch_batch_t<true, false, true>(I, mode, succ, obj, counters, batch, num_sms, st, launched);
-    if (ex) return launch_batch_t<false, true, true>(I, mode, succ, obj, counters, batch, num_sms, st, launched);
-    return launch_batch_t<false, false, true>(I, mode, succ, obj, counters, batch, num_sms, st, launched);
+    if (!I.fp32_ok) return launch_batch_t<false, false, false>(I, mode, succ, obj, counters, batch, num_sms, st, launched, log, log_cap);
+    if (att && ex) return launch_batch_t<true, true, true>(I, mode, succ, obj, counters, batch, num_sms, st, launched, log, log_cap);
+    if (att) return launch_batch_t<true, false, true>(I, mode, succ, obj, counters, batch, num_sms, st, launched, log, log_cap);
+    if (ex) return launch_batch_t<false, true, true>(I, mode, succ, obj, counters, batch, num_sms, st, launched, log, log_cap);
+    return launch_batch_t<false, false, true>(I, mode, succ, obj, counters, batch, num_sms, st, launched, log, log_cap);
 }
 
 }  // namespace tspb

@@ -838,7 +838,7 @@ int tspb200_two_opt(tspb200_ctx *ctx, int mode, int32_t *succ, double *obj, int6
     {
         const int n = ctx->n;
         const int lim = mode == TSPB200_FI ? 4096 : 128;
-        const bool want = ctx->opt_single_block < 0 ? (n >= 1 && n <= lim) : (ctx->opt_single_block == 1 && n * 24 + 16 <= 200 * 1024);
+        const bool want = ctx->opt_single_block < 0 ? (n >= 1 && n <= lim) : (ctx->opt_single_block == 1 && (long long)n * 28 + 16 <= 200 * 1024);
         if (want && max_iters < 0 && ctx->world == 1 && !ctx->tabu_on && ctx->opt_time_limit_ms <= 0 && succ) {
             double o = obj ? *obj : 0.0;
             tspb200_stats local;

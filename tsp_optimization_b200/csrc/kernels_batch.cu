@@ -1,5 +1,5 @@
 // kernels_batch.cu — batched 2-opt: one thread block drives one tour to its 2-opt local optimum with the
-// whole tour state in shared memory (24 bytes per node), no host round trips.  This is the path for
+// whole tour state in shared memory (28 bytes per node), no host round trips.  This is the path for
 // independent tour batches (GA offspring repair — reference src/genetic.c:426-443 calls alg_2opt on a
 // mutated offspring; multi-start; VNS src/vns.c:143 and tabu restarts) and for small TSPLIB instances,
 // where a grid-wide launch per move would be pure latency.
@@ -18,7 +18,8 @@ namespace tspb {
 constexpr int BATCH_THREADS = 256;
 
 struct BatchSmem {
-    float *sx, *sy, *dsn;
+    float *sx, *sy, *dsn;  // node space: coordinates, d(k, succ k)
+    float *dsp;            // position space: d(order[p], order[p+1]) — what a reversal permutes without recomputing
     int *succ, *order, *pos;
 };
 
@@ -52,29 +53,42 @@ __device__ __forceinline__ bool bt_eval(const InstDev &I, const BatchSmem &S, in
     return true;
 }
 
-// block-wide application of move (i,j) on the shared-memory tour (same orientation rule as apply_move_block)
+// block-wide application of move (i,j) on the shared-memory tour (same orientation rule as apply_swap_range): the forward
+// path a1..b is reversed in place.  Edge lengths inside the path are only PERMUTED (position-space dsp[] reversed among
+// themselves); just the two new edges (a,b) and (a1,b1) are evaluated.
 __device__ __forceinline__ void bt_apply(const InstDev &I, const BatchSmem &S, bool exact32, int n, int i, int j) {
     const int tid = threadIdx.x, nt = blockDim.x;
     const int pa = S.pos[i], pb = S.pos[j];
+    const int a1 = S.succ[i], b1 = S.succ[j];
     __syncthreads();
     int s = pa + 1; if (s >= n) s -= n;
     int len = pb - pa; if (len < 0) len += n;
     const int e = pb;
-    for (int t = tid; t < (len >> 1); t += nt) {
+    const int half = len >> 1, mhalf = (len - 1) >> 1;
+    for (int t = tid; t < half; t += nt) {
         int A = s + t; if (A >= n) A -= n;
         int B = e - t; if (B < 0) B += n;
-        int ua = S.order[A], ub = S.order[B];
+        const int ua = S.order[A], ub = S.order[B];
         S.order[A] = ub; S.order[B] = ua;
         S.pos[ub] = A; S.pos[ua] = B;
+        if (t < mhalf) {
+            int Bm = B - 1; if (Bm < 0) Bm += n;
+            const float za = S.dsp[A], zc = S.dsp[Bm];
+            S.dsp[A] = zc; S.dsp[Bm] = za;
+        }
+    }
+    if (tid == 0) {
+        S.dsp[pa] = (float)bt_exact(I, S, exact32, i, j);
+        S.dsp[pb] = (float)bt_exact(I, S, exact32, a1, b1);
     }
     __syncthreads();
     // nodes at positions pa .. pb got a new successor
     for (int t = tid; t <= len; t += nt) {
         int P = pa + t; if (P >= n) P -= n;
         int Pn = P + 1; if (Pn >= n) Pn -= n;
-        int k = S.order[P], kn = S.order[Pn];
-        S.succ[k] = kn;
-        S.dsn[k] = (float)bt_exact(I, S, exact32, k, kn);
+        const int k = S.order[P];
+        S.succ[k] = S.order[Pn];
+        S.dsn[k] = S.dsp[P];
     }
     __syncthreads();
 }
@@ -84,7 +98,7 @@ __global__ void __launch_bounds__(BATCH_THREADS) two_opt_batch_kernel(const Inst
                                                                       long long *obj_out, long long *counters, int batch,
                                                                       MoveRec *log, long long log_cap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ int s_minj;
+    __shared__ int s_hits[BATCH_THREADS / 32];
     __shared__ int s_err;
     __shared__ MoveKey s_keys[BATCH_THREADS / 32];
     const int n = I.n;
@@ -93,7 +107,8 @@ __global__ void __launch_bounds__(BATCH_THREADS) two_opt_batch_kernel(const Inst
     S.sx = reinterpret_cast<float *>(smem_raw);
     S.sy = S.sx + n;
     S.dsn = S.sy + n;
-    S.succ = reinterpret_cast<int *>(S.dsn + n);
+    S.dsp = S.dsn + n;
+    S.succ = reinterpret_cast<int *>(S.dsp + n);
     S.order = S.succ + n;
     S.pos = S.order + n;
     const bool ex32 = FP32_OK && EXACT32;
@@ -121,7 +136,11 @@ __global__ void __launch_bounds__(BATCH_THREADS) two_opt_batch_kernel(const Inst
         __syncthreads();
         long long moves = 0, passes = 0, evals = 0, objd = 0;
         if (!s_err && n >= 4) {
-            for (int k = tid; k < n; k += BATCH_THREADS) S.dsn[k] = (float)bt_exact(I, S, ex32, k, S.succ[k]);
+            for (int k = tid; k < n; k += BATCH_THREADS) {
+                const float d = (float)bt_exact(I, S, ex32, k, S.succ[k]);
+                S.dsn[k] = d;
+                S.dsp[S.pos[k]] = d;
+            }
             __syncthreads();
             if (mode == 1) {
                 // ---------------- best improvement ----------------
@@ -165,42 +184,65 @@ __global__ void __launch_bounds__(BATCH_THREADS) two_opt_batch_kernel(const Inst
                 evals = passes * ((long long)n * (n - 3) / 2);
             } else {
                 // ---------------- first improvement ----------------
-                int ci = 0, cj = 1;
+                // The reference's sweep is a linear scan of the pairs in row-major order from a cursor.  The block scans a
+                // WINDOW of that linear order per step: chunks of 32 consecutive pairs (crossing row ends) are dealt to the
+                // 8 warps round-robin, K chunks per warp, each warp stopping at its first improving pair; the smallest
+                // linear offset over the warps is the reference's "first improving pair at or after the cursor".  K
+                // doubles while nothing is found (long quiet stretches cost few barriers) and resets after a move (tours
+                // far from the optimum improve every few hundred pairs), so the work past the hit is bounded by the gap.
+                constexpr int NW = BATCH_THREADS / 32;
+                const int warp = tid >> 5, lane = tid & 31;
+                int ci = 0, cj = 1;      // cursor (row, column)
+                long long lin_prev = 1;  // statistics: linear index i*n+j of the cursor after the last move / sweep start
                 long long sweep_moves = 0;
+                int K = 1;
                 const float thr = -1.0f + W;
-                for (;;) {
-                    bool found = false;
-                    int fi = 0, fj = 0;
-                    long long fdelta = 0;
-                    const long long lin0 = (long long)ci * n + cj;  // statistics: linear pairs swept, like the grid kernel
-                    for (int row = ci; row < n - 1 && !found; ++row) {
-                        const float xi = S.sx[row], yi = S.sy[row], dsi = S.dsn[row];
-                        const int si = S.succ[row];
-                        const float xsi = S.sx[si], ysi = S.sy[si];
-                        const int jstart = (row == ci) ? cj : row + 1;
-                        if (tid == 0) s_minj = 0x7fffffff;
-                        __syncthreads();
-                        for (int jb = jstart; jb < n; jb += BATCH_THREADS) {
-                            const int j = jb + tid;
-                            bool hit = false;
-                            if (j < n) {
-                                long long delta;
-                                if (bt_eval<ATT, EXACT32, FP32_OK>(I, S, row, j, xi, yi, si, xsi, ysi, dsi, thr, delta)) hit = delta < 0;
-                            }
-                            if (hit) atomicMin(&s_minj, j);
-                            if (__syncthreads_or((int)hit)) { found = true; break; }
-                        }
-                        if (found) {
-                            fi = row;
-                            fj = s_minj;
-                            const int sj = S.succ[fj];
-                            fdelta = bt_exact(I, S, ex32, fi, fj) + bt_exact(I, S, ex32, si, sj) - (long long)dsi - (long long)S.dsn[fj];
-                        }
-                        __syncthreads();
+                // (row, column) of the pair `k` places after the cursor; row >= n-1 means "past the end of the sweep"
+                auto locate = [&](int k, int &row, int &j) {
+                    row = ci;
+                    long long jj = (long long)cj + k;
+                    while (row < n - 1 && jj >= n) {
+                        jj -= n;
+                        row += 1;
+                        jj += row + 1;
                     }
-                    bool sweep_end = !found;
-                    evals += found ? ((long long)fi * n + fj - lin0 + 1) : ((long long)(n - 1) * n - lin0);
-                    if (found) {
+                    j = (int)jj;
+                };
+                for (;;) {
+                    int myhit = 0x7fffffff;
+                    for (int q = 0; q < K; ++q) {
+                        const int k = 32 * (warp + q * NW) + lane;
+                        int row, j;
+                        locate(k, row, j);
+                        bool hit = false;
+                        const bool valid = row < n - 1;
+                        if (valid) {
+                            const int si = S.succ[row];
+                            long long delta;
+                            if (bt_eval<ATT, EXACT32, FP32_OK>(I, S, row, j, S.sx[row], S.sy[row], si, S.sx[si], S.sy[si], S.dsn[row], thr, delta))
+                                hit = delta < 0;
+                        }
+                        const unsigned m = __ballot_sync(0xffffffffu, hit);
+                        if (m) {
+                            myhit = 32 * (warp + q * NW) + __ffs(m) - 1;
+                            break;
+                        }
+                        if (!__any_sync(0xffffffffu, valid)) break;  // the whole chunk lies past the end of the sweep
+                    }
+                    if (lane == 0) s_hits[warp] = myhit;
+                    __syncthreads();
+                    int first = s_hits[0];
+#pragma unroll
+                    for (int w = 1; w < NW; ++w) first = min(first, s_hits[w]);
+                    __syncthreads();  // s_hits[] is rewritten by the next step
+                    bool sweep_end = false;
+                    if (first != 0x7fffffff) {
+                        int fi, fj;
+                        locate(first, fi, fj);
+                        const int si = S.succ[fi], sj = S.succ[fj];
+                        const long long fdelta = bt_exact(I, S, ex32, fi, fj) + bt_exact(I, S, ex32, si, sj) - (long long)S.dsn[fi] -
+                                                 (long long)S.dsn[fj];
+                        evals += (long long)fi * n + fj - lin_prev + 1;  // linear pairs swept, like the grid kernel
                         if (log && tid == 0 && moves < log_cap) {
                             MoveRec mr;
                             mr.i = fi; mr.j = fj; mr.delta = fdelta;
@@ -211,13 +253,26 @@ __global__ void __launch_bounds__(BATCH_THREADS) two_opt_batch_kernel(const Inst
                         objd += fdelta;
                         ci = fi; cj = fj + 1;
                         if (cj >= n) { ci = fi + 1; cj = ci + 1; }
+                        lin_prev = (long long)ci * n + cj;
                         if (ci >= n - 1) sweep_end = true;
+                        K = 1;
+                    } else {
+                        int nr, nj;
+                        locate(32 * NW * K, nr, nj);
+                        ci = nr; cj = nj;
+                        if (ci >= n - 1) {
+                            sweep_end = true;
+                            evals += (long long)(n - 1) * n - lin_prev;
+                        }
+                        if (K < 16) K *= 2;
                     }
                     if (sweep_end) {
                         passes++;
                         if (sweep_moves == 0) break;  // reference heuristics.c:492
                         sweep_moves = 0;
                         ci = 0; cj = 1;
+                        lin_prev = 1;
+                        K = 1;
                     }
                 }
             }
@@ -259,7 +314,7 @@ __global__ void __launch_bounds__(BATCH_THREADS) two_opt_batch_kernel(const Inst
 template <bool ATT, bool EXACT32, bool FP32_OK>
 static cudaError_t launch_batch_t(const InstDev &I, int mode, int *succ, long long *obj, long long *counters, int batch,
                                   int num_sms, cudaStream_t st, int *launched, MoveRec *log, long long log_cap) {
-    size_t smem = (size_t)I.n * 24 + 16;
+    size_t smem = (size_t)I.n * 28 + 16;
     auto kern = two_opt_batch_kernel<ATT, EXACT32, FP32_OK>;
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

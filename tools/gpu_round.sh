@@ -1,2 +1,3 @@
-timeout 900 python bench.py > gpurun_out/bench_r1e.json 2> gpurun_out/bench_r1e.err; echo "rc=$?"
-timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "rc=$?"
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1
+timeout 600 python tools/shardtime.py > gpurun_out/shardtime.jsonl 2>&1
+timeout 600 python tools/autoshape.py > gpurun_out/autoshape.jsonl 2>&1

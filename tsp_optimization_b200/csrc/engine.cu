@@ -115,7 +115,8 @@ struct tspb200_ctx {
     long long opt_time_limit_ms = 0;
     int opt_seed_hint = 1;
     int opt_pdl = 1;
-    int opt_single_block = -1;  // -1 auto, 0 never, 1 whenever the tour fits in shared memory
+    int opt_single_block = -1;
+    int opt_debug_shard = 0;    // timing experiments only: (world << 8 | rank) -> scan that rank's share of the tiles on one GPU  // -1 auto, 0 never, 1 whenever the tour fits in shared memory
     // benchmark hygiene: write this many bytes (> L2) before every pass and time each pass with its own event pair
     long long opt_flush_bytes = 0;
     unsigned char *d_flush = nullptr;
@@ -263,6 +264,9 @@ int tspb200_set_option(tspb200_ctx *ctx, const char *key, int64_t value) {
     } else if (k == "l2_flush_bytes") {
         if (value < 0) return fail(ctx, TSPB200_E_ARG, "l2_flush_bytes must be >= 0");
         ctx->opt_flush_bytes = value;
+    } else if (k == "debug_shard") {
+        ctx->opt_debug_shard = (int)value;
+        ctx->has_tour = false;
     } else if (k == "single_block") {
         if (value < -1 || value > 1) return fail(ctx, TSPB200_E_ARG, "single_block must be -1 (auto), 0 or 1");
         ctx->opt_single_block = (int)value;
@@ -488,11 +492,12 @@ static void choose_tile_shape(int n, int num_sms, int world, int opt_T, int opt_
 }
 
 static void plan_tiles(tspb200_ctx *ctx, std::vector<int> &row_start, std::vector<int> &row_j0) {
-    choose_tile_shape(ctx->n, ctx->num_sms, ctx->world, ctx->opt_T, ctx->opt_R, ctx->opt_TJ, &ctx->T, &ctx->R, &ctx->TJ);
+    const int world_eff = ctx->opt_debug_shard ? (ctx->opt_debug_shard >> 8) : ctx->world;
+    choose_tile_shape(ctx->n, ctx->num_sms, world_eff, ctx->opt_T, ctx->opt_R, ctx->opt_TJ, &ctx->T, &ctx->R, &ctx->TJ);
     const int slots = ctx->num_sms * bi_blocks_per_sm(ctx->T, ctx->R);
     ctx->ntiles = (int)tile_plan(ctx->n, ctx->T * ctx->R, ctx->TJ, &row_start, &row_j0);
     ctx->ntr = (int)row_j0.size();
-    long long per_rank = (ctx->ntiles + ctx->world - 1) / ctx->world;
+    long long per_rank = (ctx->ntiles + world_eff - 1) / world_eff;
     int grid = ctx->opt_grid > 0 ? ctx->opt_grid : slots;
     if (grid > per_rank) grid = (int)(per_rank > 0 ? per_rank : 1);
     if (grid > 4096) grid = 4096;  // block_best[] capacity
@@ -651,6 +656,10 @@ int tspb200_bi_run(tspb200_ctx *ctx, int64_t max_passes, tspb200_stats *st) {
     a.TJ = ctx->TJ;
     a.rank = ctx->rank;
     a.world = ctx->world;
+    if (ctx->opt_debug_shard && ctx->world == 1) {  // timing experiment: a rank's share of the tiles, everything else single-GPU
+        a.world = ctx->opt_debug_shard >> 8;
+        a.rank = ctx->opt_debug_shard & 0xff;
+    }
     // 2 = the scan kernel's last block also applies the move (mid-size tours: a launch costs more than the swap)
     const bool fuse_in_kernel = ctx->world == 1 && path == 0 && !ctx->tabu_on &&
                                 (ctx->opt_fuse_apply >= 0 ? ctx->opt_fuse_apply == 1 : false);

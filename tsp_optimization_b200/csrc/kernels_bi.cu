@@ -50,15 +50,15 @@ __device__ __forceinline__ void column_dists(const f32x2 (&xr2)[R / 2], const f3
 // ---- cold path ------------------------------------------------------------------------------------------
 // Exact re-evaluation of one filter hit: the R x BI_CB pairs (rows p0..p0+R-1) x (columns Q0+jj0 .. +BI_CB-1) of ONE
 // thread whose FP32 block minimum passed the threshold.  WARP-COOPERATIVE: the whole warp is converged at the call (the
-// hot loop has no divergent branch, the hit test is a ballot), so the 32 lanes take one pair each — row and column
-// records come from shared memory — re-apply the FP32 filter, evaluate the survivors exactly (FP64 with the reference's
+// hot loop has no divergent branch, the hit test is a ballot), so the 32 lanes take one pair each — column records
+// from shared memory, row records from L2 — re-apply the FP32 filter, evaluate the survivors exactly (FP64 with the reference's
 // operation order, reference src/tabusearch.c:150 / src/distutil.c) and reduce the best exact (delta, i, j) key with
 // shuffles.  A hit costs a few hundred cycles instead of a serial walk over 32 pairs by a single lane.
 constexpr int BI_CB = 4;  // columns per filter check
 
 template <int R, bool ATT, bool EXACT32>
-__device__ __noinline__ MoveKey bi_cold_warp(const InstDev I, const float4 *srow, const float4 *sc, int n, int P0, int p0,
-                                             int Q0, int jj0, float thr) {
+__device__ __noinline__ MoveKey bi_cold_warp(const InstDev I, const float4 *rec, const float4 *sc, int n, int p0, int Q0,
+                                             int jj0, float thr) {
     const int lane = threadIdx.x & 31;
     MoveKey best = key_none();
 #pragma unroll 1
@@ -67,7 +67,7 @@ __device__ __noinline__ MoveKey bi_cold_warp(const InstDev I, const float4 *srow
         const int r = idx / BI_CB, c = idx % BI_CB;
         const int p = p0 + r, q = Q0 + jj0 + c;
         if (idx < R * BI_CB && q >= p + 2 && q <= n - 1 && !(p == 0 && q == n - 1)) {  // reference tabusearch.c:134
-            const float4 rp = srow[p - P0], rp1 = srow[p - P0 + 1];
+            const float4 rp = __ldg(&rec[p]), rp1 = __ldg(&rec[p + 1]);  // row records: one L2 round trip for the warp
             const float4 c0 = sc[jj0 + c], c1 = sc[jj0 + c + 1];
             const float qv = (dist32<ATT>(rp.x, rp.y, c0.x, c0.y) - rp.z) + dist32<ATT>(rp1.x, rp1.y, c1.x, c1.y);
             if (qv <= thr + c0.z) {
@@ -97,8 +97,9 @@ __device__ __noinline__ MoveKey bi_cold_warp(const InstDev I, const float4 *srow
 // mid-size instances (n ~ 10^4: only ~20 k evaluations per warp and pass) enough tiles to fill 148 SMs while keeping
 // R = 8 rows per thread, i.e. 1.125 sqrt per evaluated move.
 //
-// Shared memory per block (dynamic): two column buffers (TJ+2 records) and two row buffers (BI_THREADS*R+1 records),
-// each pair filled by TMA bulk copies on one mbarrier per stage, plus the tile tables.
+// Shared memory per block (dynamic): two column buffers (TJ+2 records) filled by TMA bulk copies, one mbarrier per stage,
+// plus the tile tables.  Row records go straight from L2 into registers: a thread's R+1 rows are 16*(R+1) contiguous bytes,
+// and reading them through shared memory would put all lanes of a quarter-warp on the same banks (stride 16*R bytes).
 template <int BI_THREADS, int R, bool ATT, bool EXACT32>
 __global__ void __launch_bounds__(BI_THREADS, (R >= 16 ? (BI_THREADS == 256 ? 1 : 384 / BI_THREADS) : 512 / BI_THREADS)) bi_scan_kernel(const BiArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -120,13 +121,10 @@ __global__ void __launch_bounds__(BI_THREADS, (R >= 16 ? (BI_THREADS == 256 ? 1 
     const float4 *rec = A.tour.rec;
     float4 *scols0 = reinterpret_cast<float4 *>(smem_raw);
     float4 *scols1 = scols0 + (TJ + 2);
-    float4 *srows0 = scols1 + (TJ + 2);
-    float4 *srows1 = srows0 + (TI + 2);
     const unsigned col_bytes = (unsigned)(TJ + 1) * 16u;
-    constexpr unsigned row_bytes = (unsigned)(TI + 1) * 16u;
 
     // tile tables -> shared memory (one coalesced L2 round trip instead of a dependent chain per binary-search step)
-    int *s_rs = reinterpret_cast<int *>(srows1 + (TI + 2));  // [ntr+1] prefix sums of tiles per tile-row
+    int *s_rs = reinterpret_cast<int *>(scols1 + (TJ + 2));  // [ntr+1] prefix sums of tiles per tile-row
     int *s_rj = s_rs + (A.ntr + 1);                          // [ntr]   first tile column of each tile-row
     for (int k = tid; k <= A.ntr; k += BI_THREADS) {
         s_rs[k] = A.tile_row_start[k];
@@ -175,33 +173,29 @@ __global__ void __launch_bounds__(BI_THREADS, (R >= 16 ? (BI_THREADS == 256 ? 1 
         P0 = lo * TI;
         Q0 = (s_rj[lo] + (t - s_rs[lo])) * TJ;
     };
-    auto stage = [&](int b, int P0, int Q0) {  // thread 0: both bulk copies of one stage on one mbarrier
-        mbar_expect_tx(&bars[b], col_bytes + row_bytes);
+    auto stage = [&](int b, int Q0) {  // thread 0: the bulk copy of one stage's column records
+        mbar_expect_tx(&bars[b], col_bytes);
         tma_load_1d(b ? scols1 : scols0, rec + Q0, col_bytes, &bars[b]);
-        tma_load_1d(b ? srows1 : srows0, rec + P0, row_bytes, &bars[b]);
     };
 
     int t = first;
     int P0 = 0, Q0 = 0;
     if (t < A.ntiles) {
         decode(t, P0, Q0);
-        if (tid == 0) stage(0, P0, Q0);
+        if (tid == 0) stage(0, Q0);
     }
 
     for (int it = 0; t < A.ntiles; ++it) {
         const int buf = it & 1;
         const unsigned parity = (unsigned)(it >> 1) & 1u;
         const float4 *sc = buf ? scols1 : scols0;
-        const float4 *srow = buf ? srows1 : srows0;
         // prefetch the next tile into the other stage
         const int tn = t + stride;
         int P0n = 0, Q0n = 0;
         if (tn < A.ntiles) {
             decode(tn, P0n, Q0n);
-            if (tid == 0) stage(buf ^ 1, P0n, Q0n);
+            if (tid == 0) stage(buf ^ 1, Q0n);
         }
-
-        mbar_wait(&bars[buf], parity);
 
         // rows of this thread: p0 .. p0+R-1 in packed pairs (+ successor row p0+R, scalar)
         const int p0 = P0 + tid * R;
@@ -209,7 +203,7 @@ __global__ void __launch_bounds__(BI_THREADS, (R >= 16 ? (BI_THREADS == 256 ? 1 
         float xrl, yrl;
 #pragma unroll
         for (int k = 0; k < R / 2; ++k) {
-            const float4 v0 = srow[tid * R + 2 * k], v1 = srow[tid * R + 2 * k + 1];
+            const float4 v0 = __ldg(&rec[p0 + 2 * k]), v1 = __ldg(&rec[p0 + 2 * k + 1]);
             // "+ 0" is a real FADD2 (not an identity for -0.0, so it is never folded): its 64-bit result is an aligned
             // register pair that stays live across the column loop, instead of being re-packed with MOVs per step
             const f32x2 zero2 = f2pack(0.f, 0.f);
@@ -218,11 +212,13 @@ __global__ void __launch_bounds__(BI_THREADS, (R >= 16 ? (BI_THREADS == 256 ? 1 
             cp2[k] = f2sub(zero2, f2pack(v0.z, v1.z));  // padding rows carry ds = -BIG -> cp = +BIG -> never a candidate
         }
         {
-            const float4 v = srow[tid * R + R];
+            const float4 v = __ldg(&rec[p0 + R]);
             xrl = v.x;
             yrl = v.y;
         }
         thr = fminf(thr, (float)(*((volatile int *)&s_hint)) + W);
+
+        mbar_wait(&bars[buf], parity);
 
         // pairs with q < p+2 exist in this tile?  (mask them; they are mirrored / adjacent pairs)
         const bool diag = (Q0 < P0 + TI + 1);
@@ -265,7 +261,7 @@ __global__ void __launch_bounds__(BI_THREADS, (R >= 16 ? (BI_THREADS == 256 ? 1 
         while (hits) {                                                                                 \
             const int L = __ffs(hits) - 1;                                                             \
             const float thrL = __shfl_sync(0xffffffffu, thr, L);                                       \
-            const MoveKey nb = bi_cold_warp<R, ATT, EXACT32>(A.inst, srow, sc, n, P0, P0 + ((tid & ~31) + L) * R, Q0, jj, thrL); \
+            const MoveKey nb = bi_cold_warp<R, ATT, EXACT32>(A.inst, rec, sc, n, P0 + ((tid & ~31) + L) * R, Q0, jj, thrL); \
             if ((tid & 31) == L) {                                                                     \
                 atomicAdd(&ctl->cold_calls, 1ull);                                                     \
                 if (key_less(nb, best)) {                                                              \
@@ -596,8 +592,7 @@ __global__ void __launch_bounds__(256) bi_scan_exact_kernel(const InstDev inst, 
 // ---- host-side launchers -----------------------------------------------------------------------------
 template <int T, int R>
 static cudaError_t launch_bi_tr(const BiArgs &a, int grid, bool pdl, cudaStream_t st) {
-    const size_t smem = (size_t)2 * (a.TJ + 2) * sizeof(float4) + (size_t)2 * (T * R + 2) * sizeof(float4) +
-                        (size_t)(2 * a.ntr + 2) * sizeof(int);
+    const size_t smem = (size_t)2 * (a.TJ + 2) * sizeof(float4) + (size_t)(2 * a.ntr + 2) * sizeof(int);
     const bool att = (a.inst.metric == M_ATT);
     const bool ex = a.inst.exact32 != 0;
     auto go = [&](auto kern) -> cudaError_t {

@@ -27,8 +27,8 @@ cudaError_t launch_bi_scan_tabu(const InstDev &inst, const TourDev &tour, int *s
                                 unsigned long long *zl_count, long long zl_cap, int grid, cudaStream_t st);
 cudaError_t launch_bi_decode_packed(const TourDev &tour, cudaStream_t st);
 cudaError_t launch_apply_move(const InstDev &inst, const TourDev &tour, int num_sms, int seed, bool pdl, cudaStream_t st);
-cudaError_t launch_refresh_node_space(const TourDev &tour, int num_sms, cudaStream_t st);
-cudaError_t launch_fi_search(const InstDev &I, const TourDev &T, int grid, cudaStream_t st);
+cudaError_t launch_refresh_node_space(const TourDev &tour, int num_sms, bool pdl, cudaStream_t st);
+cudaError_t launch_fi_search(const InstDev &I, const TourDev &T, int grid, bool pdl, cudaStream_t st);
 cudaError_t launch_dist_matrix(const InstDev &I, int *out, long long ld, int row_begin, int row_end, bool fast,
                                cudaStream_t st);
 cudaError_t launch_build_state(const InstDev &I, const TourDev &T, const int *order, cudaStream_t st);
@@ -804,9 +804,9 @@ int tspb200_fi_run(tspb200_ctx *ctx, int64_t max_moves, tspb200_stats *st) {
         if (ctx->h_ctl->done && cap != -1 && ctx->h_ctl->moves < cap) CK(cudaMemcpyAsync(&ctx->d_ctl->done, &zero, sizeof zero, cudaMemcpyHostToDevice, ctx->stream));
         while (!done) {
             for (long long q = 0; q < batch; ++q) {
-                CK(launch_fi_search(I, ctx->tour, grid, ctx->stream));
-                CK(launch_apply_move(I, ctx->tour, ctx->num_sms, 0, false, ctx->stream));
-                CK(launch_refresh_node_space(ctx->tour, ctx->num_sms, ctx->stream));
+                CK(launch_fi_search(I, ctx->tour, grid, ctx->opt_pdl != 0, ctx->stream));
+                CK(launch_apply_move(I, ctx->tour, ctx->num_sms, 0, ctx->opt_pdl != 0, ctx->stream));
+                CK(launch_refresh_node_space(ctx->tour, ctx->num_sms, ctx->opt_pdl != 0, ctx->stream));
                 host_launches += 3;
             }
             rc = sync_ctl(ctx);

@@ -466,6 +466,8 @@ __global__ void __launch_bounds__(256) apply_move_kernel(const InstDev inst, con
 
 __global__ void __launch_bounds__(256) refresh_node_space_kernel(const TourDev tour) {
     const Ctl *ctl = tour.ctl;
+    pdl_launch_dependents();
+    pdl_wait();
     if (!ctl->ap_valid) return;
     refresh_node_space(tour, ctl->ap_pa, ctl->ap_pb, blockIdx.x * 256 + threadIdx.x, gridDim.x * 256);
 }
@@ -694,12 +696,11 @@ cudaError_t launch_apply_move(const InstDev &inst, const TourDev &tour, int num_
     return cudaLaunchKernelEx(&cfg, apply_move_kernel, inst, tour, seed);
 }
 
-cudaError_t launch_refresh_node_space(const TourDev &tour, int num_sms, cudaStream_t st) {
-    int grid = (tour.n + 1023) / 1024;
+cudaError_t launch_refresh_node_space(const TourDev &tour, int num_sms, bool pdl, cudaStream_t st) {
+    int grid = (tour.n + 255) / 256;  // one node per thread
     if (grid < 1) grid = 1;
-    if (grid > 2 * num_sms) grid = 2 * num_sms;
-    refresh_node_space_kernel<<<grid, 256, 0, st>>>(tour);
-    return cudaGetLastError();
+    if (grid > 4 * num_sms) grid = 4 * num_sms;
+    return launch_maybe_pdl(refresh_node_space_kernel, dim3(grid), dim3(256), 0, st, pdl, tour);
 }
 
 }  // namespace tspb

@@ -29,6 +29,8 @@ __global__ void __launch_bounds__(FI_THREADS) fi_search_kernel(const InstDev I, 
     __shared__ int s_last;
     __shared__ unsigned long long s_found;
     Ctl *ctl = T.ctl;
+    pdl_launch_dependents();  // the apply launch may queue up behind this kernel
+    pdl_wait();               // the refresh launch of the previous move is complete
     if (ctl->done) {
         // a capped run stops right after publishing a move: make sure later apply launches are no-ops
         if (blockIdx.x == 0 && threadIdx.x == 0) ctl->ap_valid = 0;
@@ -145,15 +147,15 @@ __global__ void __launch_bounds__(FI_THREADS) fi_search_kernel(const InstDev I, 
     }
 }
 
-cudaError_t launch_fi_search(const InstDev &I, const TourDev &T, int grid, cudaStream_t st) {
+cudaError_t launch_fi_search(const InstDev &I, const TourDev &T, int grid, bool pdl, cudaStream_t st) {
     const bool att = (I.metric == M_ATT);
     const bool ex = I.exact32 != 0;
-    if (!I.fp32_ok) fi_search_kernel<false, false, false><<<grid, FI_THREADS, 0, st>>>(I, T);
-    else if (att && ex) fi_search_kernel<true, true, true><<<grid, FI_THREADS, 0, st>>>(I, T);
-    else if (att) fi_search_kernel<true, false, true><<<grid, FI_THREADS, 0, st>>>(I, T);
-    else if (ex) fi_search_kernel<false, true, true><<<grid, FI_THREADS, 0, st>>>(I, T);
-    else fi_search_kernel<false, false, true><<<grid, FI_THREADS, 0, st>>>(I, T);
-    return cudaGetLastError();
+    const dim3 g(grid), b(FI_THREADS);
+    if (!I.fp32_ok) return launch_maybe_pdl(fi_search_kernel<false, false, false>, g, b, 0, st, pdl, I, T);
+    if (att && ex) return launch_maybe_pdl(fi_search_kernel<true, true, true>, g, b, 0, st, pdl, I, T);
+    if (att) return launch_maybe_pdl(fi_search_kernel<true, false, true>, g, b, 0, st, pdl, I, T);
+    if (ex) return launch_maybe_pdl(fi_search_kernel<false, true, true>, g, b, 0, st, pdl, I, T);
+    return launch_maybe_pdl(fi_search_kernel<false, false, true>, g, b, 0, st, pdl, I, T);
 }
 
 }  // namespace tspb

@@ -1021,11 +1021,11 @@ int tspb200_nn_tour(tspb200_ctx *ctx, int start, int32_t *succ, double *cost) {
     long long *d_cost = nullptr;
     CK(cudaMalloc(&d_succ, sizeof(int) * (size_t)n));
     CK(cudaMalloc(&d_vis, (size_t)n));
-    CK(cudaMalloc(&d_slots, sizeof(unsigned long long) * 2));
+    CK(cudaMalloc(&d_slots, sizeof(unsigned long long) * 3));
     CK(cudaMalloc(&d_bar, sizeof(unsigned)));
     CK(cudaMalloc(&d_cost, sizeof(long long)));
     CK(cudaMemsetAsync(d_vis, 0, (size_t)n, ctx->stream));
-    CK(cudaMemsetAsync(d_slots, 0xff, sizeof(unsigned long long) * 2, ctx->stream));
+    CK(cudaMemsetAsync(d_slots, 0xff, sizeof(unsigned long long) * 3, ctx->stream));
     CK(cudaMemsetAsync(d_bar, 0, sizeof(unsigned), ctx->stream));
     NnArgs a;
     a.inst = I; a.start = start; a.succ = d_succ; a.visited = d_vis; a.slots = d_slots; a.barrier = d_bar; a.cost = d_cost;

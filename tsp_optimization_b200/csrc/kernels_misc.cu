@@ -305,8 +305,12 @@ __global__ void __launch_bounds__(256) nn_tour_kernel(const NnArgs A) {
     unsigned epoch = 0;
     if (gtid == 0) A.visited[cur] = 1;
     grid_barrier(A.barrier, (++epoch) * gridDim.x);
+    // ONE grid barrier per step.  The winner of step s goes through slots[s % 3]; every thread reads it after the barrier
+    // and treats `nxt` as visited from its own registers, so the visited[] flag written by thread 0 only has to be
+    // visible one barrier later; slots[(s+2) % 3] (last read before this barrier, next used after the following one)
+    // is re-armed by thread 0 in the meantime.
     for (int step = 0; step < n - 1; ++step) {
-        unsigned long long *slot = &A.slots[step & 1];
+        unsigned long long *slot = &A.slots[step % 3];
         unsigned long long best = ~0ull;
         const double2 pc = I.dmat ? make_double2(0, 0) : I.pt64[cur];
         for (int k = gtid; k < n; k += gsz) {
@@ -332,10 +336,9 @@ __global__ void __launch_bounds__(256) nn_tour_kernel(const NnArgs A) {
         if (gtid == 0) {
             A.succ[cur] = nxt;
             A.visited[nxt] = 1;
-            A.slots[(step + 1) & 1] = ~0ull;  // reset the other slot for the next step
+            A.slots[(step + 2) % 3] = ~0ull;
         }
         cur = nxt;
-        grid_barrier(A.barrier, (++epoch) * gridDim.x);
     }
     if (gtid == 0) {
         A.succ[cur] = A.start;  // closing edge, reference heuristics.c:59-62,74

@@ -277,7 +277,7 @@ struct NnArgs {
     int start;
     int *succ;                       // out
     unsigned char *visited;          // n bytes, zeroed by the launcher
-    unsigned long long *slots;       // [2] packed (dist << 32 | idx) winners, double-buffered; init to ~0
+    unsigned long long *slots;       // [3] packed (dist << 32 | idx) winners, rotating; init to ~0
     unsigned *barrier;               // grid barrier counter, zeroed by the launcher
     long long *cost;                 // out: accumulated cost
 };

@@ -20,3 +20,15 @@ def test_sharded_bi_equals_single_gpu():
            "--master-port", "29517", os.path.join(ROOT, "tools", "mgpu_check.py"), "6000", "60"]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_sharded_tour_batches_equal_single_gpu():
+    """independent tour batches (GA population, multi-start): contiguous shards per rank, no collective on the data path;
+    every shard's tours and costs must equal the same tours pushed through one GPU."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29518", os.path.join(ROOT, "tools", "batch_mgpu.py"), "FI"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and '"shards_equal_single_gpu": true' in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

@@ -635,3 +635,14 @@ def test_large_coordinates_take_the_exact_path(engine, oracle):
     succ0, _ = oracle.nn_tour(xy, 3, 0)
     _check_bi(engine, oracle, xy, 3, succ0)
     assert engine.info("fp32_ok") == 0
+
+
+def test_nn_uni100000_equals_committed_fixture(engine):
+    """the headline instance's start tour: GPU nearest neighbour (10^10 exact distances, 0.4 s) == the oracle's tour
+    committed as tests/golden/nn_uni100000.npz (2 min of CPU, tests/golden/make_nn_uni100000.py)."""
+    import os
+    from conftest import GOLD_DIR
+    z = np.load(os.path.join(GOLD_DIR, "nn_uni100000.npz"))
+    engine.set_instance(uniform_instance(100000), 0)
+    succ, cost = engine.nn_tour(0)
+    assert (succ == z["succ"]).all() and cost == float(z["cost"])

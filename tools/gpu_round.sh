@@ -1,4 +1,3 @@
-python tools/batch_mgpu.py FI > gpurun_out/batch_g1.jsonl 2>&1
-python tools/batch_mgpu.py BI >> gpurun_out/batch_g1.jsonl 2>&1
-python -m torch.distributed.run --nnodes=1 --nproc-per-node=2 --master-addr 127.0.0.1 --master-port 29521 tools/batch_mgpu.py FI > gpurun_out/batch_g2.jsonl 2>&1
-python -m torch.distributed.run --nnodes=1 --nproc-per-node=2 --master-addr 127.0.0.1 --master-port 29522 tools/batch_mgpu.py BI >> gpurun_out/batch_g2.jsonl 2>&1
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1
+timeout 900 python tools/fi100k.py > gpurun_out/fi100k.jsonl 2>&1
+timeout 600 python tools/configs_bench.py c2 > gpurun_out/configs_c2.jsonl 2>&1

@@ -4,9 +4,7 @@
 // carries on from (i, j+1) with the modified tour; sweeps repeat until one brings no gain (:492).
 // Exact replay on a GPU: one launch = "find the first pair at or after the cursor, in that same order,
 // whose exact delta is negative" (a grid-wide min over the linear index i*n+j), apply it, advance the
-// cursor.  Blocks take rows i = cursor_row + blockIdx, +gridDim, ...; a row stops at its first hit and
-// rows that start after an already published hit are skipped, so the work wasted past the hit is
-// bounded by gridDim rows.  The scan is in NODE space (nrec/nds/nsucc) because the order that matters
+// cursor.  The scan is in NODE space (nrec/nds/nsucc) because the order that matters
 // is the node-index order.  FP32 filter + FP64 exact check exactly as in the BI kernel.
 #include "tsp_state.cuh"
 
@@ -23,9 +21,35 @@ __device__ __forceinline__ float fi_dist32(float ax, float ay, float bx, float b
 }
 
 // FP32_OK = false: no filter, every pair is evaluated exactly (GEO, matrix mode, oversized coordinates).
+//
+// Work distribution: the sweep's pairs in row-major order, counted from the cursor, are cut into SEGMENTS of
+// FI_SEG_CHUNKS x 256 consecutive pairs (crossing row ends).  Blocks draw segments in increasing order from an atomic
+// counter; a block scans its segment chunk by chunk (256 pairs at a time, so the first hit inside a segment is found in
+// order), publishes a hit with atomicMin on the (row*n + j) index and stops; blocks whose next segment starts behind a
+// published hit stop as well.  Every segment before the winning one has been scanned to its end without a hit, so the
+// minimum is exactly the reference's "first improving pair at or after the cursor", and the work past the hit is
+// bounded by the segments in flight instead of by whole rows (at n = 100 000 a row is 25x the average gap between moves).
+constexpr int FI_SEG_CHUNKS = 16;
+
+// number of pairs (i<j) in rows 0..r-1 of the row-major enumeration: sum_{q<r} (n-1-q)
+__device__ __forceinline__ long long fi_pairs_before_row(long long r, long long n) { return r * (n - 1) - r * (r - 1) / 2; }
+
+// (row, column) of the pair with absolute index A in the row-major enumeration of all i<j; A < n(n-1)/2
+__device__ __forceinline__ void fi_locate(long long A, int n, int &row, int &j) {
+    const double b = 2.0 * n - 1.0;
+    long long r = (long long)((b - sqrt(b * b - 8.0 * (double)A)) * 0.5);
+    if (r < 0) r = 0;
+    if (r > n - 2) r = n - 2;
+    while (r > 0 && fi_pairs_before_row(r, n) > A) --r;
+    while (r < n - 2 && fi_pairs_before_row(r + 1, n) <= A) ++r;
+    row = (int)r;
+    j = (int)(r + 1 + (A - fi_pairs_before_row(r, n)));
+}
+
 template <bool ATT, bool EXACT32, bool FP32_OK>
 __global__ void __launch_bounds__(FI_THREADS) fi_search_kernel(const InstDev I, const TourDev T) {
-    __shared__ int s_minj;
+    __shared__ int s_seg;
+    __shared__ int s_minhit;
     __shared__ int s_last;
     __shared__ unsigned long long s_found;
     Ctl *ctl = T.ctl;
@@ -40,23 +64,41 @@ __global__ void __launch_bounds__(FI_THREADS) fi_search_kernel(const InstDev I, 
     const int tid = threadIdx.x;
     const int i0 = ctl->cur_i, j0 = ctl->cur_j;
     const float thrW = -1.0f + I.W;  // candidates: exact delta <= -1
+    const long long total = (long long)n * (n - 1) / 2;
+    const long long A0 = fi_pairs_before_row(i0, n) + (j0 - i0 - 1);  // absolute index of the cursor pair
+    constexpr long long SEG = (long long)FI_SEG_CHUNKS * FI_THREADS;
 
-    for (int row = i0 + (int)blockIdx.x; row < n - 1; row += (int)gridDim.x) {
+    for (;;) {
         if (tid == 0) {
-            s_found = *((volatile unsigned long long *)&ctl->fi_found);
-            s_minj = 0x7fffffff;
+            s_seg = (int)atomicAdd(&ctl->fi_seg, 1u);
+            s_minhit = 0x7fffffff;
+            s_found = *((volatile unsigned long long *)&ctl->fi_found);  // one read per block: the exit below must be uniform
         }
         __syncthreads();
-        if (s_found < (unsigned long long)row * (unsigned long long)n) break;  // an earlier pair already won
-        const float4 ri = T.nrec[row];
-        const float dsi = T.nds[row];
-        const int si = T.nsucc[row];
-        const int jstart = (row == i0) ? j0 : row + 1;
+        const long long Abase = A0 + (long long)s_seg * SEG;
+        if (Abase >= total) break;  // past the end of the sweep
+        {
+            int rb, jb;
+            fi_locate(Abase, n, rb, jb);
+            if (s_found < (unsigned long long)rb * (unsigned long long)n + (unsigned long long)jb) break;  // an earlier pair already won
+        }
+        // this thread's first pair of the segment, then +256 per chunk
+        long long A = Abase + tid;
+        int row = n, j = 0;
+        if (A < total) fi_locate(A, n, row, j);
+        int crow = -1, si = 0;
+        float4 ri = make_float4(0.f, 0.f, 0.f, 0.f);
+        float dsi = 0.f;
         bool stop = false;
-        for (int jb = jstart; jb < n && !stop; jb += FI_THREADS) {
-            const int j = jb + tid;
+        for (int c = 0; c < FI_SEG_CHUNKS && !stop; ++c) {
             bool hit = false;
-            if (j < n) {
+            if (A < total) {
+                if (row != crow) {
+                    crow = row;
+                    ri = T.nrec[row];
+                    dsi = T.nds[row];
+                    si = T.nsucc[row];
+                }
                 const int sj = T.nsucc[j];
                 // reference heuristics.c:471: skip a1==b1 (impossible in a tour), a==b1, b==a1
                 if (sj != row && si != j && si != sj) {
@@ -84,19 +126,26 @@ __global__ void __launch_bounds__(FI_THREADS) fi_search_kernel(const InstDev I, 
                     }
                 }
             }
-            // also leave the row when somebody else published an earlier pair (polled every 8 chunks)
-            bool bail = false;
-            if (tid == 0 && (((jb - jstart) / FI_THREADS) & 7) == 7)
-                bail = *((volatile unsigned long long *)&ctl->fi_found) < (unsigned long long)row * (unsigned long long)n;
-            if (hit) atomicMin(&s_minj, j);
-            if (__syncthreads_or((int)(hit || bail))) stop = true;
+            if (hit) atomicMin(&s_minhit, c * FI_THREADS + tid);  // offset inside the segment == row-major order
+            if (__syncthreads_or((int)hit)) {
+                stop = true;
+            } else {
+                // next chunk: 256 pairs further
+                A += FI_THREADS;
+                long long jn = (long long)j + FI_THREADS;
+                while (row < n - 1 && jn >= n) { jn -= n; row += 1; jn += row + 1; }
+                j = (int)jn;
+            }
         }
         if (stop) {
-            if (tid == 0 && s_minj != 0x7fffffff)
-                atomicMin(&ctl->fi_found, (unsigned long long)row * (unsigned long long)n + (unsigned long long)s_minj);
+            if (tid == 0) {
+                int hr, hj;
+                fi_locate(Abase + s_minhit, n, hr, hj);
+                atomicMin(&ctl->fi_found, (unsigned long long)hr * (unsigned long long)n + (unsigned long long)hj);
+            }
             break;
         }
-        __syncthreads();
+        __syncthreads();  // s_seg / s_minhit are rewritten by the next round
     }
 
     // ---- last block: apply the winning move / close the sweep ------------------------------------
@@ -143,6 +192,7 @@ __global__ void __launch_bounds__(FI_THREADS) fi_search_kernel(const InstDev I, 
         ctl->cur_i = ci;
         ctl->cur_j = cj;
         ctl->fi_found = FI_NONE;
+        ctl->fi_seg = 0;
         ctl->ticket = 0;
     }
 }

@@ -53,9 +53,9 @@ struct Ctl {
     MoveKey last;                   // last selected key
     int ap_pa, ap_pb, ap_valid;     // move to apply: positions of a and b (published by the selecting kernel)
     unsigned apply_ticket;          // block completion counter of the apply launch
+    unsigned fi_seg;                // FI: next segment of the row-major pair order to hand to a block
     MoveKey cand[4];                // runner-up moves of the last BI pass: re-evaluated after the apply to seed `hint`
     int ncand;
-    int pad1;
     unsigned long long cold_calls;  // statistics: filter hits that went through the exact (cold) path
 };
 constexpr int CTL_NCAND = 4;

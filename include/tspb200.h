@@ -14,6 +14,7 @@
  *   reverse_path     include/utility.h:334, src/utility.c:708        -> applied on the device inside two_opt
  *   greedy           include/heuristics.h, src/heuristics.c:18       -> tspb200_nn_tour
  *   HEU_Greedy_iter  src/heuristics.c:168-205                        -> tspb200_nn_tour_batch
+ *   HEU_extramileage src/heuristics.c:208-314                        -> tspb200_extra_mileage
  *   fitness          src/genetic.c:51-60                             -> tspb200_tour_costs
  * The reference-named drop-in symbols themselves (calc_dist, alg_2opt, alg_2opt_tabu, reverse_path on the
  * reference's `instance` struct) live in libtspb200_dropin.so, see tspb200_dropin.h and INTEGRATION.md.
@@ -149,6 +150,10 @@ int tspb200_nn_tour(tspb200_ctx *ctx, int start, int32_t *succ, double *cost);
  * runs greedy() from every node and keeps the first strictly better tour).  succ = batch*n successors out (may be NULL
  * when only the costs are wanted), costs = batch doubles out. */
 int tspb200_nn_tour_batch(tspb200_ctx *ctx, const int32_t *starts, int batch, int32_t *succ, double *costs);
+
+/* Extra-mileage construction (reference HEU_extramileage, src/heuristics.c:208-314): farthest pair, then cheapest
+ * insertion with the reference's scan order as tie-break.  succ = n successors out. */
+int tspb200_extra_mileage(tspb200_ctx *ctx, int32_t *succ, double *cost);
 
 /* Costs of `batch` tours: as_order != 0 -> tours are visiting orders (GA chromosomes, genetic.c:51-60),
  * else successor arrays. */

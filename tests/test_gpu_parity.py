@@ -646,3 +646,46 @@ def test_nn_uni100000_equals_committed_fixture(engine):
     engine.set_instance(uniform_instance(100000), 0)
     succ, cost = engine.nn_tour(0)
     assert (succ == z["succ"]).all() and cost == float(z["cost"])
+
+
+# ---- extra mileage (reference HEU_extramileage, src/heuristics.c:208-314) and the remaining published CSV columns ------
+@pytest.mark.parametrize("nm", ["berlin52", "pr299", "att532", "gr666", "dsj1000", "ulysses22", "eil51"])
+def test_extra_mileage_equals_reference_driver(engine, reflib, instances, nm):
+    xy, wt = instances[nm]
+    engine.set_instance(xy, wt)
+    if wt == 4:
+        engine.dist_matrix_build()
+    succ, cost = engine.extra_mileage()
+    st, rsucc, robj = reflib.run_method("HEU_extramileage", xy, wt)
+    assert st == 0 and cost == robj and (succ == rsucc).all(), nm
+    engine.dist_matrix_free()
+
+
+def test_extra_mileage_ties_and_duplicates(engine, reflib):
+    rng = np.random.default_rng(21)
+    for n in (2, 3, 4, 9, 40, 150):
+        xy = rng.integers(0, 9, size=(n, 2)).astype(np.float64)  # few distinct points: ties everywhere, zero distances
+        engine.set_instance(xy, 0)
+        succ, cost = engine.extra_mileage()
+        st, rsucc, robj = reflib.run_method("HEU_extramileage", xy, 0)
+        assert cost == robj and (succ == rsucc).all(), n
+
+
+def test_reference_csv_all_deterministic_columns(engine, instances, goldens):
+    """GREEDY_ITER, EXTR_MILE (results/constructive_heuristics_new.csv) and 2OPT_GREEDY_ITER, 2OPT_EXTR_MIL
+    (results/constructive_heuristics_2opt_new.csv), 18 instances: construction on the GPU, then alg_2opt on the GPU, must
+    land on the reference's published objective values."""
+    for nm, row in sorted(goldens["reference_csv"].items()):
+        xy, wt = instances[nm]
+        engine.set_instance(xy, wt)
+        if wt == 4:
+            engine.dist_matrix_build()
+        _, s_gi, c_gi = engine.greedy_iter()
+        assert c_gi == row["GREEDY_ITER"], nm
+        _, o_gi, _, _ = engine.two_opt(FI, s_gi, c_gi)
+        assert o_gi == row["2OPT_GREEDY_ITER"], nm
+        s_em, c_em = engine.extra_mileage()
+        assert c_em == row["EXTR_MILE"], nm
+        _, o_em, _, _ = engine.two_opt(FI, s_em, c_em)
+        assert o_em == row["2OPT_EXTR_MIL"], nm
+        engine.dist_matrix_free()

@@ -148,3 +148,11 @@ def test_bi_scan_rows_mt_matches_first_move(oracle, instances):
     _, _, st, log = oracle.two_opt_bi(xy, wt, succ, max_passes=1, log_cap=1)
     assert ev == 299 * 296 // 2 == st.evals
     assert [key[1], key[2], key[0]] == log[0].tolist()
+
+
+def test_csv_goldens_cover_every_deterministic_column(goldens):
+    """18 instances x {GREEDY, GREEDY_ITER, EXTR_MILE, 2OPT_GREEDY, 2OPT_GREEDY_ITER, 2OPT_EXTR_MIL}: every cell was re-derived
+    with the compiled reference when the fixture was made (tests/golden/make_goldens.py, make_csv_goldens.py)."""
+    assert len(goldens["reference_csv"]) == 18
+    for nm, row in goldens["reference_csv"].items():
+        assert set(row) == {"GREEDY", "GREEDY_ITER", "EXTR_MILE", "2OPT_GREEDY", "2OPT_GREEDY_ITER", "2OPT_EXTR_MIL"}, nm

@@ -37,6 +37,7 @@ cudaError_t launch_tour_cost(const InstDev &I, const int *tours, int as_order, l
 cudaError_t launch_nn_tour(const NnArgs &a, int grid, cudaStream_t st);
 cudaError_t launch_prep_points(const double2 *raw, double2 *pt64, float2 *pt32, int n, int metric, cudaStream_t st);
 int nn_max_grid(int num_sms);
+cudaError_t launch_extra_mileage(const InstDev &I, int *succ_out, long long *cost_out, cudaStream_t st);
 cudaError_t launch_nn_batch(const InstDev &I, const int *starts, int batch, int *succ_out, long long *cost_out, float eps,
                             int num_sms, cudaStream_t st);
 cudaError_t launch_two_opt_batch(const InstDev &I, int mode, int *succ, long long *obj_delta, long long *counters,
@@ -1074,6 +1075,32 @@ int tspb200_nn_tour_batch(tspb200_ctx *ctx, const int32_t *starts, int batch, in
     if (le == cudaErrorInvalidValue) return fail(ctx, TSPB200_E_UNSUPPORTED, "batched nearest neighbour keeps the coordinates in shared memory: n=%d is too large", n);
     if (le != cudaSuccess) return fail(ctx, TSPB200_E_CUDA, "batched nearest-neighbour kernel failed: %s", cudaGetErrorString(le));
     for (int b = 0; b < batch; ++b) costs[b] = (double)h[(size_t)b];
+    return TSPB200_OK;
+}
+
+// Extra-mileage construction (reference HEU_extramileage, src/heuristics.c:208-314).
+int tspb200_extra_mileage(tspb200_ctx *ctx, int32_t *succ, double *cost) {
+    if (!ctx || !ctx->stream) return fail(ctx, TSPB200_E_CUDA, "context has no CUDA device");
+    if (ctx->n < 2) return fail(ctx, TSPB200_E_ARG, "extra mileage needs at least 2 nodes");
+    if (!succ) return fail(ctx, TSPB200_E_ARG, "null succ");
+    CK(cudaSetDevice(ctx->device));
+    const int n = ctx->n;
+    int path = select_path(ctx);
+    if (path == 2 && !ctx->d_mat) path = 1;
+    InstDev I = inst_for_path(ctx, path == 2 ? 2 : 1);
+    int *d_succ = nullptr;
+    long long *d_cost = nullptr;
+    CK(cudaMalloc(&d_succ, sizeof(int) * (size_t)n));
+    CK(cudaMalloc(&d_cost, sizeof(long long)));
+    cudaError_t le = launch_extra_mileage(I, d_succ, d_cost, ctx->stream);
+    long long c = 0;
+    if (le == cudaSuccess) le = cudaMemcpyAsync(succ, d_succ, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream);
+    if (le == cudaSuccess) le = cudaMemcpyAsync(&c, d_cost, sizeof c, cudaMemcpyDeviceToHost, ctx->stream);
+    if (le == cudaSuccess) le = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_succ); cudaFree(d_cost);
+    if (le == cudaErrorInvalidValue) return fail(ctx, TSPB200_E_UNSUPPORTED, "extra mileage keeps its state in shared memory: n=%d is too large", n);
+    if (le != cudaSuccess) return fail(ctx, TSPB200_E_CUDA, "extra-mileage kernel failed: %s", cudaGetErrorString(le));
+    if (cost) *cost = (double)c;
     return TSPB200_OK;
 }
 

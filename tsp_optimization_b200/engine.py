@@ -30,7 +30,7 @@ ABI_SYMBOLS = [
     "tspb200_create", "tspb200_destroy", "tspb200_last_error", "tspb200_set_option", "tspb200_get_info",
     "tspb200_set_instance", "tspb200_dist_matrix_build", "tspb200_dist_matrix_get", "tspb200_dist_matrix",
     "tspb200_dist_matrix_free", "tspb200_tour_upload", "tspb200_tour_download", "tspb200_tour_log",
-    "tspb200_bi_run", "tspb200_fi_run", "tspb200_two_opt", "tspb200_two_opt_tabu", "tspb200_two_opt_batch", "tspb200_nn_tour", "tspb200_nn_tour_batch",
+    "tspb200_bi_run", "tspb200_fi_run", "tspb200_two_opt", "tspb200_two_opt_tabu", "tspb200_two_opt_batch", "tspb200_nn_tour", "tspb200_nn_tour_batch", "tspb200_extra_mileage",
     "tspb200_tour_costs", "tspb200_comm_unique_id", "tspb200_comm_init", "tspb200_comm_destroy",
     "tspb200_debug_tile_plan",
 ]
@@ -107,6 +107,7 @@ def load_library() -> C.CDLL:
     L.tspb200_two_opt_batch.argtypes = [vp, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(_Stats)]
     L.tspb200_nn_tour.argtypes = [vp, C.c_int, C.c_void_p, C.POINTER(C.c_double)]
     L.tspb200_nn_tour_batch.argtypes = [vp, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    L.tspb200_extra_mileage.argtypes = [vp, C.c_void_p, C.POINTER(C.c_double)]
     L.tspb200_tour_costs.argtypes = [vp, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     L.tspb200_comm_unique_id.argtypes = [C.c_void_p]
     L.tspb200_comm_init.argtypes = [vp, C.c_void_p, C.c_int, C.c_int]
@@ -295,6 +296,13 @@ class Engine:
         best = int(np.argmin(costs))  # argmin returns the first minimum == reference's strict '<' over increasing starts
         succ, c = self.nn_tour_batch(np.array([best], dtype=np.int32))
         return best, succ[0], float(c[0])
+
+    def extra_mileage(self):
+        """reference HEU_extramileage (src/heuristics.c:208-314) -> (succ, cost)."""
+        succ = np.empty(self.n, dtype=np.int32)
+        cost = C.c_double(0)
+        self._ck(self.L.tspb200_extra_mileage(self.h, succ.ctypes.data, C.byref(cost)))
+        return succ, cost.value
 
     def tour_costs(self, tours, as_order: bool) -> np.ndarray:
         tours = np.ascontiguousarray(tours, dtype=np.int32).reshape(-1, self.n)

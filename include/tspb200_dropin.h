@@ -89,6 +89,12 @@ int alg_2opt(tspb200_ref_instance *inst);
 int alg_2opt_tabu(tspb200_ref_instance *inst, int *skip_edge, int *stored_prev, const int iter, const int tenure);
 void reverse_path(tspb200_ref_instance *inst, int start_node, int end_node, int *prev);
 
+/* Optional, same signatures as the reference (include/heuristics.h:16,32,40): the constructive callers next to the path.
+ * They only take effect when the integrator weakens the reference's definitions of these symbols as well. */
+int greedy(tspb200_ref_instance *inst, int starting_node);
+int HEU_Greedy_iter(tspb200_ref_instance *inst);
+int HEU_extramileage(tspb200_ref_instance *inst);
+
 /* sizeof / offsets of the mirror, same order as oracle/ref_shim.c:refshim_layout (for the ABI test). */
 int tspb200_dropin_layout(long long *out, int cap);
 /* Releases the cached device contexts (optional; they are also released at process exit). */

@@ -24,6 +24,15 @@ def test_strong_symbols_come_from_the_dropin(gpulib):
     # tspb200_dropin_layout only exists in csrc/dropin.cpp: its presence next to the reference's HEU_* drivers shows
     # which definitions the link picked
     assert hasattr(gpulib.L, "tspb200_dropin_layout") and hasattr(gpulib.L, "HEU_2opt_greedy")
+    # the drop-in's definitions are laid out contiguously (one object file): the weakened reference symbols greedy,
+    # HEU_Greedy_iter and HEU_extramileage must resolve into that range, HEU_2opt_greedy (reference code) must not
+    import ctypes as C
+    addr = lambda nm: C.cast(getattr(gpulib.L, nm), C.c_void_p).value
+    lo = min(addr(nm) for nm in ("alg_2opt", "calc_dist", "reverse_path", "tspb200_dropin_layout"))
+    hi = max(addr(nm) for nm in ("alg_2opt", "calc_dist", "reverse_path", "tspb200_dropin_layout", "tspb200_dropin_reset"))
+    for nm in ("greedy", "HEU_Greedy_iter", "HEU_extramileage", "alg_2opt_tabu"):
+        assert lo - 4096 <= addr(nm) <= hi + 4096, nm
+    assert not (lo - 4096 <= addr("HEU_2opt_greedy") <= hi + 4096)
 
 
 @pytest.mark.parametrize("nm", ["berlin52", "pr299", "att532", "gr666", "dsj1000", "pr1002", "ulysses22"])
@@ -40,7 +49,9 @@ def test_reference_2opt_greedy_on_cuda_path(gpulib, reflib, instances, goldens, 
 
 @pytest.mark.parametrize("method,nm", [("HEU_2opt_extramileage", "lin318"), ("HEU_2opt_extramileage", "att532"),
                                        ("HEU_2opt_greedy_iter", "berlin52"), ("HEU_greedy", "gr666"),
-                                       ("HEU_extramileage", "pr299")])
+                                       ("HEU_extramileage", "pr299"), ("HEU_2opt_greedy_iter", "gr431"),
+                                       ("HEU_Greedy_iter", "dsj1000"), ("HEU_extramileage", "gr666"),
+                                       ("HEU_2opt_extramileage", "dsj1000")])
 def test_other_reference_drivers_on_cuda_path(gpulib, reflib, instances, method, nm):
     xy, wt = instances[nm]
     st_g, succ_g, obj_g = gpulib.run_method(method, xy, wt)

@@ -1,1 +1,1 @@
-timeout 900 python -m pytest tests -m gpu -x -q -k "extra_mileage or csv_all" > gpurun_out/pytest_gpu.log 2>&1
+timeout 900 python -m pytest tests/test_gpu_dropin_link.py -m gpu -x -q > gpurun_out/pytest_link.log 2>&1

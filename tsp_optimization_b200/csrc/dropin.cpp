@@ -145,6 +145,64 @@ void reverse_path(tspb200_ref_instance *inst, int start_node, int end_node, int 
     for (int k = 0; k < inst->num_nodes; ++k) prev[ed[k].j] = k;
 }
 
+// ---- optional: the constructive callers next to the path ------------------------------------------------------------
+// These replace reference functions only if the integrator ALSO weakens their symbols ("extended"
+// list); the four symbols above are the boundary proper.  Same contracts as the reference: solution.edges[] and
+// solution.obj_best are filled in place, return codes as in include/heuristics.h:6-7.
+
+// reference src/heuristics.c:18-78: nearest neighbour from `starting_node`
+int greedy(tspb200_ref_instance *inst, int starting_node) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (starting_node >= inst->num_nodes) return 1;  // WRONG_STARTING_NODE
+    tspb200_ctx *ctx = context_for(inst, true);
+    if (!inst->solution.edges) die("instance has no solution.edges");
+    const int n = inst->num_nodes;
+    std::vector<int32_t> succ((size_t)n);
+    double cost = 0;
+    int rc = tspb200_nn_tour(ctx, starting_node, succ.data(), &cost);
+    if (rc) die("nearest neighbour failed: ", tspb200_last_error(ctx));
+    for (int k = 0; k < n; ++k) { inst->solution.edges[k].i = k; inst->solution.edges[k].j = succ[k]; }
+    inst->solution.obj_best = cost;
+    return 0;
+}
+
+// reference src/heuristics.c:168-205: nearest neighbour from every node, the first strictly better tour is kept
+int HEU_Greedy_iter(tspb200_ref_instance *inst) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    tspb200_ctx *ctx = context_for(inst, true);
+    if (!inst->solution.edges) die("instance has no solution.edges");
+    const int n = inst->num_nodes;
+    std::vector<int32_t> starts((size_t)n), succ((size_t)n);
+    std::vector<double> costs((size_t)n);
+    for (int k = 0; k < n; ++k) starts[k] = k;
+    int rc = tspb200_nn_tour_batch(ctx, starts.data(), n, nullptr, costs.data());
+    if (rc) die("batched nearest neighbour failed: ", tspb200_last_error(ctx));
+    int best = 0;
+    for (int k = 1; k < n; ++k)
+        if (costs[k] < costs[best]) best = k;  // strict '<' over increasing start nodes (heuristics.c:195)
+    double cost = 0;
+    rc = tspb200_nn_tour(ctx, best, succ.data(), &cost);
+    if (rc) die("nearest neighbour failed: ", tspb200_last_error(ctx));
+    for (int k = 0; k < n; ++k) { inst->solution.edges[k].i = k; inst->solution.edges[k].j = succ[k]; }
+    inst->solution.obj_best = cost;
+    return 0;
+}
+
+// reference src/heuristics.c:208-314: extra-mileage insertion from the farthest pair
+int HEU_extramileage(tspb200_ref_instance *inst) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    tspb200_ctx *ctx = context_for(inst, true);
+    if (!inst->solution.edges) die("instance has no solution.edges");
+    const int n = inst->num_nodes;
+    std::vector<int32_t> succ((size_t)n);
+    double cost = 0;
+    int rc = tspb200_extra_mileage(ctx, succ.data(), &cost);
+    if (rc) die("extra mileage failed: ", tspb200_last_error(ctx));
+    for (int k = 0; k < n; ++k) { inst->solution.edges[k].i = k; inst->solution.edges[k].j = succ[k]; }
+    inst->solution.obj_best = cost;
+    return 0;
+}
+
 int tspb200_dropin_layout(long long *out, int cap) {
     long long v[] = {
         (long long)sizeof(tspb200_ref_instance),

@@ -1,1 +1,1 @@
-timeout 900 python -m pytest tests/test_gpu_dropin_link.py -m gpu -x -q > gpurun_out/pytest_link.log 2>&1
+timeout 1500 python tools/dropin_e2e.py > gpurun_out/dropin_e2e.jsonl 2>&1

@@ -156,3 +156,18 @@ def test_csv_goldens_cover_every_deterministic_column(goldens):
     assert len(goldens["reference_csv"]) == 18
     for nm, row in goldens["reference_csv"].items():
         assert set(row) == {"GREEDY", "GREEDY_ITER", "EXTR_MILE", "2OPT_GREEDY", "2OPT_GREEDY_ITER", "2OPT_EXTR_MIL"}, nm
+
+
+def test_large_fixture_spot_check(oracle):
+    """tests/golden/large.npz / goldens_large.json (decimal and 10^6-range coordinates): the cheap cells re-derived here."""
+    import json
+    import os
+    from conftest import GOLD_DIR
+    z = np.load(os.path.join(GOLD_DIR, "large.npz"))
+    g = json.load(open(os.path.join(GOLD_DIR, "goldens_large.json")))["instances"]
+    assert set(g) == {"fl3795", "pla7397", "usa13509", "stefano_8k"}
+    xy, wt = z["fl3795__xy"], int(z["fl3795__wt"])
+    succ, cost = oracle.nn_tour(xy, wt, 0)
+    assert cost == g["fl3795"]["nn_cost"]
+    s, obj, st, log = oracle.two_opt_bi(xy, wt, succ, max_passes=3, log_cap=8)
+    assert log.tolist() == g["fl3795"]["bi_log"][:3]

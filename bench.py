@@ -212,6 +212,10 @@ def main():
         run_reference(args, rank)
         return
 
+    # stdout carries exactly one JSON line: keep NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION in this image) off it
+    # (every level from VERSION up prints it, so the variable is dropped rather than raised to WARN)
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        del os.environ["NCCL_DEBUG"]
     import torch
     import torch.distributed as dist
 

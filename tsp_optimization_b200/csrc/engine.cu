@@ -674,8 +674,7 @@ int tspb200_bi_run(tspb200_ctx *ctx, int64_t max_passes, tspb200_stats *st) {
     const bool pdl = path == 0 && !ctx->tabu_on && ctx->opt_pdl && (ctx->world == 1 || use_xchg);
     int rc = sync_ctl(ctx);
     if (rc) return rc;
-    const long long passes0 = ctx->h_ctl->passes, moves0 = ctx->h_ctl->moves, launches0 = ctx->h_ctl->launches,
-                    delta0 = ctx->h_ctl->obj_delta;
+    const long long passes0 = ctx->h_ctl->passes, moves0 = ctx->h_ctl->moves, delta0 = ctx->h_ctl->obj_delta;
     int exact_grid = ctx->opt_grid > 0 ? ctx->opt_grid : 4 * ctx->num_sms;
     if (exact_grid > n) exact_grid = n > 0 ? n : 1;
     // passes per host round trip: large instances run for milliseconds per pass, small ones for microseconds
@@ -781,8 +780,8 @@ int tspb200_fi_run(tspb200_ctx *ctx, int64_t max_moves, tspb200_stats *st) {
     InstDev I = inst_for_path(ctx, path);
     int rc = sync_ctl(ctx);
     if (rc) return rc;
-    const long long passes0 = ctx->h_ctl->passes, moves0 = ctx->h_ctl->moves, launches0 = ctx->h_ctl->launches,
-                    delta0 = ctx->h_ctl->obj_delta, swept0 = ctx->h_ctl->pairs_swept;
+    const long long passes0 = ctx->h_ctl->passes, moves0 = ctx->h_ctl->moves, delta0 = ctx->h_ctl->obj_delta,
+                    swept0 = ctx->h_ctl->pairs_swept;
     // max_moves is an absolute cap on the device counter
     long long cap = max_moves >= 0 ? moves0 + max_moves : -1;
     CK(cudaMemcpyAsync(&ctx->d_ctl->max_moves, &cap, sizeof cap, cudaMemcpyHostToDevice, ctx->stream));

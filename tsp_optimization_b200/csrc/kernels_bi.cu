@@ -160,8 +160,11 @@ __global__ void __launch_bounds__(BI_THREADS, (R >= 16 ? (BI_THREADS == 256 ? 1 
     float thr = (float)s_hint + W;
     int pend_hint = 0;  // tid 0: value of ctl->hint fetched 64 columns ago
 
-    const int first = A.rank + A.world * (int)blockIdx.x;
-    const int stride = A.world * (int)gridDim.x;
+    // Tiles are DRAWN, not dealt: ctl->tile_next counts this rank's tiles handed out beyond the first wave (rank r owns
+    // the tile ids r, r + world, ...; every tile costs the same — masked and padded pairs are computed too), so the blocks
+    // run dry within one tile of each other whatever slows some of them down (exact-path calls, the far die's L2
+    // latency).  Static dealing left the SMs idle ~10 % of a pass once a pass is only ~5 tiles deep (8 ranks).
+    __shared__ int s_tile[2][3];  // [stage] = {P0, Q0, valid}, written by thread 0 one tile ahead
 
     // tile id -> (tile row I, tile column J)
     auto decode = [&](int t, int &P0, int &Q0) {
@@ -173,29 +176,36 @@ __global__ void __launch_bounds__(BI_THREADS, (R >= 16 ? (BI_THREADS == 256 ? 1 
         P0 = lo * TI;
         Q0 = (s_rj[lo] + (t - s_rs[lo])) * TJ;
     };
-    auto stage = [&](int b, int Q0) {  // thread 0: the bulk copy of one stage's column records
-        mbar_expect_tx(&bars[b], col_bytes);
-        tma_load_1d(b ? scols1 : scols0, rec + Q0, col_bytes, &bars[b]);
+    // thread 0: take the next tile, start the bulk copy of its column records, publish it for stage b.  A block's first
+    // tile is its block index (no atomic on the critical path of the prologue); the following ones are drawn from the
+    // counter, which therefore counts from gridDim.x.  tiles_rank <= gridDim.x (one wave, n <~ 10^4) never touches it.
+    const long long tiles_rank = ((long long)A.ntiles - A.rank + A.world - 1) / A.world;
+    auto draw = [&](int b, bool first) {
+        long long kl = first ? (long long)blockIdx.x : tiles_rank;
+        if (!first && tiles_rank > (long long)gridDim.x) kl = (long long)gridDim.x + (long long)atomicAdd(&ctl->tile_next, 1u);
+        int P = 0, Q = 0, valid = 0;
+        if (kl < tiles_rank) {
+            decode((int)((long long)A.rank + (long long)A.world * kl), P, Q);
+            valid = 1;
+            mbar_expect_tx(&bars[b], col_bytes);
+            tma_load_1d(b ? scols1 : scols0, rec + Q, col_bytes, &bars[b]);
+        }
+        s_tile[b][0] = P;
+        s_tile[b][1] = Q;
+        s_tile[b][2] = valid;
     };
 
-    int t = first;
-    int P0 = 0, Q0 = 0;
-    if (t < A.ntiles) {
-        decode(t, P0, Q0);
-        if (tid == 0) stage(0, Q0);
-    }
+    if (tid == 0) draw(0, true);
+    __syncthreads();
+    int P0 = s_tile[0][0], Q0 = s_tile[0][1];
+    bool have = s_tile[0][2] != 0;
 
-    for (int it = 0; t < A.ntiles; ++it) {
+    for (int it = 0; have; ++it) {
         const int buf = it & 1;
         const unsigned parity = (unsigned)(it >> 1) & 1u;
         const float4 *sc = buf ? scols1 : scols0;
-        // prefetch the next tile into the other stage
-        const int tn = t + stride;
-        int P0n = 0, Q0n = 0;
-        if (tn < A.ntiles) {
-            decode(tn, P0n, Q0n);
-            if (tid == 0) stage(buf ^ 1, Q0n);
-        }
+        // prefetch the next tile into the other stage (its slot in s_tile / scols was last read two tiles ago)
+        if (tid == 0) draw(buf ^ 1, false);
 
         // rows of this thread: p0 .. p0+R-1 in packed pairs (+ successor row p0+R, scalar)
         const int p0 = P0 + tid * R;
@@ -304,9 +314,9 @@ __global__ void __launch_bounds__(BI_THREADS, (R >= 16 ? (BI_THREADS == 256 ? 1 
             int g = atomicMin(&ctl->hint, h);
             if (g < h) s_hint = g;
         }
-        t = tn;
-        P0 = P0n;
-        Q0 = Q0n;
+        P0 = s_tile[buf ^ 1][0];
+        Q0 = s_tile[buf ^ 1][1];
+        have = s_tile[buf ^ 1][2] != 0;
     }
 
     // ---- block argmin -> grid argmin ("last block done") -------------------------------------------
@@ -335,8 +345,8 @@ __global__ void __launch_bounds__(BI_THREADS, (R >= 16 ? (BI_THREADS == 256 ? 1 
     // CTL_NCAND rounds of "block-wide minimum, then retire it": round 0 is the winner of the pass, the rest are
     // runner-ups kept as seeds for the next pass's filter (seed_hint_from_candidates)
     MoveKey k = key_none();
-#pragma unroll 1
     const int rounds = (A.seed_hint >= 2) ? CTL_NCAND : 1;
+#pragma unroll 1
     for (int round = 0; round < rounds; ++round) {
         MoveKey m = key_warp_min(mine);
         if ((tid & 31) == 0) s_keys[tid >> 5] = m;
@@ -355,6 +365,7 @@ __global__ void __launch_bounds__(BI_THREADS, (R >= 16 ? (BI_THREADS == 256 ? 1 
         ctl->ncand = rounds;
         ctl->last = k;
         ctl->ticket = 0;
+        ctl->tile_next = 0;
         ctl->hint = 0;
         ctl->launches += 1;
         if (!A.fuse_apply) {

@@ -24,7 +24,6 @@ __device__ __forceinline__ long long em_delta(unsigned long long k) { return (lo
 __global__ void __launch_bounds__(EM_THREADS) extra_mileage_kernel(const InstDev I, int *succ_out, long long *cost_out) {
     extern __shared__ __align__(16) unsigned char em_smem[];
     __shared__ unsigned long long s_red[EM_THREADS / 32];
-    __shared__ unsigned long long s_win;
     __shared__ int s_qn;
     const int n = I.n;
     unsigned long long *key = reinterpret_cast<unsigned long long *>(em_smem);  // [n] best (delta, slot) of an unvisited node
@@ -89,15 +88,13 @@ __global__ void __launch_bounds__(EM_THREADS) extra_mileage_kernel(const InstDev
     while (cnt < n) {
         // ---- selection: lexicographic min of (delta, node, slot) ----
         unsigned long long best = EM_NONE;
-        int besti = -1;
         for (int i = tid; i < n; i += EM_THREADS) {
             const unsigned long long k = key[i];
             if (k == EM_NONE) continue;
-            // compare (delta, i, slot): delta is the high word of k
+            // compare (delta, i): delta is the high word of k; the slot comes from key[i*] afterwards
             const unsigned long long c = (k & 0xffffffff00000000ull) | (unsigned)i;
-            if (c < best) { best = c; besti = i; }
+            best = c < best ? c : best;
         }
-        (void)besti;
         best = block_min(best);
         if (best == EM_NONE) break;
         const int istar = (int)(best & 0xffffffffu);

@@ -32,13 +32,13 @@ __device__ __forceinline__ f32x2 f2pack(float lo, float hi) {
     return r;
 }
 __device__ __forceinline__ float f2lo(f32x2 v) {
-    float lo, hi;
-    asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+    float lo;
+    asm("{ .reg .b32 t; mov.b64 {%0,t}, %1; }" : "=f"(lo) : "l"(v));
     return lo;
 }
 __device__ __forceinline__ float f2hi(f32x2 v) {
-    float lo, hi;
-    asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+    float hi;
+    asm("{ .reg .b32 t; mov.b64 {t,%0}, %1; }" : "=f"(hi) : "l"(v));
     return hi;
 }
 __device__ __forceinline__ f32x2 f2sub(f32x2 a, f32x2 b) {

@@ -54,6 +54,7 @@ struct Ctl {
     int ap_pa, ap_pb, ap_valid;     // move to apply: positions of a and b (published by the selecting kernel)
     unsigned apply_ticket;          // block completion counter of the apply launch
     unsigned fi_seg;                // FI: next segment of the row-major pair order to hand to a block
+    unsigned tile_next;             // BI: this rank's tiles handed out so far in the current pass
     MoveKey cand[4];                // runner-up moves of the last BI pass: re-evaluated after the apply to seed `hint`
     int ncand;
     unsigned long long cold_calls;  // statistics: filter hits that went through the exact (cold) path

@@ -61,7 +61,7 @@ def test_auto_tile_shape():
     for n, world in ((10000, 1), (20000, 1), (50000, 2), (100000, 1), (100000, 8)):
         T, R, TJ, rs, rj = tile_plan(n, world=world)
         assert R >= 8, (n, world, T, R, TJ)
-    assert tile_plan(100000)[:3] == (128, 16, 256)
+    assert tile_plan(100000)[:3] == (64, 8, 256)
     assert tile_plan(52)[:2] == (64, 2)
 
 

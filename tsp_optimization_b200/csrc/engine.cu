@@ -459,17 +459,19 @@ static long long tile_plan(int n, int TI, int TJ, std::vector<int> *row_start, s
     return total;
 }
 
-// Picks (T, R, TJ) by a small cost model.  A pass takes `waves` = ceil(tiles per rank / resident blocks) rounds of tiles;
-// in one round an SM runs (resident blocks per SM) x T threads, each doing (TJ + OV) column steps of R+1 square roots
-// (OV ~ the row loads, first column and end-of-tile barrier), and the SFU is what those threads share.  So
-//   time ~ waves x threads per SM x (TJ + OV) x (R + 1).
-// R = 16 (1.0625 sqrt per move, 150 registers -> 3 blocks of 128 threads per SM) wins on big instances, R = 8 with
-// 64-thread blocks (8 per SM) on mid-size ones (n ~ 10^4: ~700 evaluations per thread and pass, one wave of narrow tiles).
+// Picks (T, R, TJ) by a small cost model.  One round of tiles keeps an SM busy with (resident blocks per SM) x T threads,
+// each doing (TJ + OV) column steps of R+1 square roots (OV ~ the row loads, first column and end-of-tile barrier), and the
+// SFU is what those threads share.  A pass whose tiles fit the resident blocks is one such round; a deeper pass draws its
+// tiles dynamically and ends within about one tile of the ideal, so
+//   time ~ rounds x threads per SM x (TJ + OV) x (R + 1),   rounds = 1  or  tiles per rank / resident blocks + 1.
+// The per-shape factors are measured on B200 at n = 100 000 (tools/shardshape.py): 64-thread blocks (8 per SM, 16 warps)
+// hide latency best; R = 16 (1.0625 sqrt per move) pays with 150 registers, i.e. 12 warps per SM; R = 4 and 2 spend more
+// instructions per move than their sqrt count alone says.
 static int bi_blocks_per_sm(int t, int r) { return r >= 16 ? (t == 256 ? 1 : 384 / t) : 512 / t; }
 
 static void choose_tile_shape(int n, int num_sms, int world, int opt_T, int opt_R, int opt_TJ, int *T, int *R, int *TJ) {
     struct Shape { int t, r; double penalty; };
-    const Shape cand[] = {{128, 16, 1.02}, {256, 8, 1.0}, {128, 8, 1.02}, {64, 8, 1.04}, {64, 4, 1.04}, {64, 2, 1.04}};
+    const Shape cand[] = {{64, 8, 1.0}, {128, 16, 1.04}, {128, 8, 1.015}, {256, 8, 1.05}, {64, 4, 1.15}, {64, 2, 1.3}};
     const double OV = 16.0;
     double best = 1e300;
     int bt = 64, br = 2, btj = 32;
@@ -482,9 +484,9 @@ static void choose_tile_shape(int n, int num_sms, int world, int opt_T, int opt_
             const int tjj = opt_TJ ? opt_TJ : tj;
             const long long nt = tile_plan(n, t * r, tjj, nullptr, nullptr);
             const long long per_rank = (nt + world - 1) / world;
-            const long long waves = (per_rank + slots - 1) / slots;
-            if (r >= 16 && waves < 4 && !opt_R) continue;  // 12 warps per SM hide the per-tile prologue only over several waves
-            const double cost = (double)waves * (bps * t) * (tjj + OV) * (r + 1) * c.penalty;
+            const double rounds = per_rank <= slots ? 1.0 : (double)per_rank / (double)slots + 1.0;
+            if (r >= 16 && rounds < 4.0 && !opt_R) continue;  // 12 warps per SM hide the per-tile prologue only over several rounds
+            const double cost = rounds * (bps * t) * (tjj + OV) * (r + 1) * c.penalty;
             if (cost < best) { best = cost; bt = t; br = r; btj = tjj; }
             if (opt_TJ) break;
         }

@@ -345,20 +345,20 @@ def main():
     fp32_peak = num_sms * 128 * sm_mhz * 1e6
     R = eng.info("rows_per_thread")
     roofline = {"bound": "sfu_sqrt", "achieved": per_gpu / 1e12, "peak": sqrt_peak / 1e12, "unit": "T sqrt/s (= T evals/s)",
-                "frac": per_gpu / sqrt_peak, "traffic": 1.715e6, "kernel": "bi_scan_kernel",
+                "frac": per_gpu / sqrt_peak, "traffic": 1.726e6, "kernel": "bi_scan_kernel",
                 "per_unit": f"1 MUFU.SQRT per evaluated move (algorithmic minimum: every distance serves two moves); the kernel "
                             f"issues (R+1)/R = {(R + 1) / R:.4f} with R = {R} rows per thread",
                 "peak_source": f"{num_sms} SMs x 16 MUFU/clk x {sm_mhz:.0f} MHz (nvidia-smi median under load); "
                                f"MEASURED_PEAKS.json ({peaks_src}) holds HBM and bf16 figures only, neither bounds this kernel",
-                "ncu": "profiles/r1_ncu_full_bi_scan_128x16_and_matrix.txt: XU pipe 81 % of peak, issue slots 56 %, "
-                       "6.03 thread instructions per evaluated move, DRAM 1.7 MB read / 0 written per launch",
+                "ncu": "profiles/r1_ncu_full_bi_scan_64x8_final.txt (bi_scan_kernel<64,8>, n = 100 000): XU pipe 89 % of peak, "
+                       "issue slots 66 %, 6.66 thread instructions per evaluated move, DRAM 1.7 MB read / 0 written per launch",
                 "fp32_issue_view": {"survey_per_unit": FP32_INSTR_PER_EVAL,
                                     "frac_vs_survey_18_instr_model": per_gpu * FP32_INSTR_PER_EVAL / fp32_peak,
-                                    "executed_thread_instr_per_eval": 6.03,
-                                    "frac_issue_slots": per_gpu * 6.03 / fp32_peak,
+                                    "executed_thread_instr_per_eval": 6.66,
+                                    "frac_issue_slots": per_gpu * 6.66 / fp32_peak,
                                     "note": "SURVEY.md §8d's 18 lane-instr/eval model evaluates two fresh distances per move with "
                                             "scalar FP32; sharing each distance between its two moves and packed FP32x2 arithmetic "
-                                            "bring the executed count to 6.03, so the 18-instr fraction exceeds 1 and is reported "
+                                            "bring the executed count to 6.66, so the 18-instr fraction exceeds 1 and is reported "
                                             "for reference only"},
                 "traffic_note": "dram__bytes_read.sum per launch (ncu --set full, cold L2): the tour records once, 16 B/node; compute-bound"}
     # secondary kernel: distance matrix, HBM-store-bound (4*n*ld bytes written per launch)

@@ -850,7 +850,10 @@ int tspb200_two_opt(tspb200_ctx *ctx, int mode, int32_t *succ, double *obj, int6
         const int n = ctx->n;
         const int lim = mode == TSPB200_FI ? 4096 : 128;
         const bool want = ctx->opt_single_block < 0 ? (n >= 1 && n <= lim) : (ctx->opt_single_block == 1 && (long long)n * 28 + 16 <= 200 * 1024);
-        if (want && max_iters < 0 && ctx->world == 1 && !ctx->tabu_on && ctx->opt_time_limit_ms <= 0 && succ) {
+        // (the block kernel cannot poll the clock; a tour this small is done within milliseconds, so any limit of a second
+        // or more — the reference's CLI default is 900 s — is honoured trivially)
+        const bool time_ok = ctx->opt_time_limit_ms <= 0 || ctx->opt_time_limit_ms >= 1000;
+        if (want && max_iters < 0 && ctx->world == 1 && !ctx->tabu_on && time_ok && succ) {
             double o = obj ? *obj : 0.0;
             tspb200_stats local;
             int rc = run_batch(ctx, mode, succ, &o, 1, &local, log, log ? log_cap : 0, log_count);

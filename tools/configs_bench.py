@@ -13,9 +13,14 @@ def out(**kw):
     print(json.dumps(kw), flush=True)
 
 if "small" in which:
-    for nm in ("berlin52", "pr299", "pr1002"):
+    for nm in ("berlin52", "pr299", "att532", "gr666", "pr1002", "dsj1000"):
         xy, wt = z[nm + "__xy"], int(z[nm + "__wt"])
         eng.set_instance(xy, wt)
+        eng.dist_matrix_build()
+        ms = [eng.dist_matrix_build() for _ in range(5)]
+        out(cfg="tsplib", inst=nm, n=len(xy), weight_type=wt, matrix_kernel_us=float(np.median(ms)) * 1e3)
+        if wt != 4:
+            eng.dist_matrix_free()  # GEO (all-FP64 trig) runs its 2-opt on the resident matrix
         succ, cost = eng.nn_tour(0)
         for mode, name in ((BI, "BI"), (FI, "FI")):
             eng.two_opt(mode, succ, cost)

@@ -13,7 +13,7 @@ from tsp_optimization_b200 import engine as eng
 def _declared(header):
     txt = open(os.path.join(ROOT, "include", header)).read()
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
-    return sorted(set(re.findall(r"\b(tspb200_[a-z0-9_]+|calc_dist|alg_2opt_tabu|alg_2opt|reverse_path)\s*\(", txt)))
+    return sorted(set(re.findall(r"\b(tspb200_[a-z0-9_]+|calc_dist|alg_2opt_tabu|alg_2opt|reverse_path|greedy|HEU_Greedy_iter|HEU_extramileage)\s*\(", txt)))
 
 
 def test_libtspb200_exports_every_declared_symbol():
@@ -28,8 +28,8 @@ def test_dropin_exports_reference_symbols():
     L = C.CDLL(eng.DROPIN_PATH)
     for nm in _declared("tspb200_dropin.h"):
         assert hasattr(L, nm), nm
-    for nm in ("calc_dist", "alg_2opt", "alg_2opt_tabu", "reverse_path"):
-        assert hasattr(L, nm)
+    for nm in ("calc_dist", "alg_2opt", "alg_2opt_tabu", "reverse_path", "greedy", "HEU_Greedy_iter", "HEU_extramileage"):
+        assert hasattr(L, nm) and nm in _declared("tspb200_dropin.h")
 
 
 def test_instance_mirror_matches_reference_layout(reflib):

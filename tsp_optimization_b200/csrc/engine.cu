@@ -98,8 +98,14 @@ struct tspb200_ctx {
     long long mat_ld = 0;
     double dmax = 0;
 
-    // tour
+    // tour (device buffers are kept across set_instance / tour_upload calls while they are big enough: cudaMalloc is
+    // a synchronising call, and a slow one once peer access is enabled)
     bool has_tour = false;
+    int inst_cap = 0;                 // nodes the instance arrays can hold
+    int tour_cap_n = 0;               // nodes the per-node tour arrays can hold
+    int tour_cap_rec = 0;             // records allocated in tour.rec
+    long long tour_cap_log = 0;       // move-log entries allocated
+    int tile_cap = 0;                 // ints allocated in each tile table
     TourDev tour{};
     int *d_order = nullptr, *d_succ = nullptr;
     unsigned long long *d_cost = nullptr;
@@ -171,6 +177,8 @@ static void free_tour(tspb200_ctx *c) {
     c->d_order = c->d_succ = nullptr; c->d_cost = nullptr;
     c->d_tile_row_start = c->d_tile_row_j0 = nullptr;
     c->has_tour = false;
+    c->tour_cap_n = c->tour_cap_rec = c->tile_cap = 0;
+    c->tour_cap_log = 0;
 }
 
 static void free_xchg(tspb200_ctx *c) {
@@ -199,6 +207,7 @@ static void free_instance(tspb200_ctx *c) {
     cudaFree(c->d_raw); cudaFree(c->d_pt64); cudaFree(c->d_pt32); cudaFree(c->d_mat);
     c->d_raw = c->d_pt64 = nullptr; c->d_pt32 = nullptr; c->d_mat = nullptr;
     c->n = 0;
+    c->inst_cap = 0;
 }
 
 extern "C" {
@@ -322,7 +331,15 @@ int tspb200_set_instance(tspb200_ctx *ctx, const double *xy, int n, int weight_t
     if (!ctx || !ctx->stream) return fail(ctx, TSPB200_E_CUDA, "context has no CUDA device");
     if (!xy || n < 1) return fail(ctx, TSPB200_E_ARG, "bad instance (n=%d)", n);
     CK(cudaSetDevice(ctx->device));
-    free_instance(ctx);
+    if (n > ctx->inst_cap) {
+        free_instance(ctx);
+    } else {  // same buffers, new contents: whatever was derived from the old instance is void
+        CK(cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->d_mat);
+        ctx->d_mat = nullptr;
+        ctx->mat_ld = 0;
+        ctx->has_tour = false;
+    }
     ctx->n = n;
     ctx->metric = weight_type;
     // host-side scan: FP32 representability, bounding box -> filter window
@@ -354,9 +371,12 @@ int tspb200_set_instance(tspb200_ctx *ctx, const double *xy, int n, int weight_t
     ctx->inst.int_coords = (int_coords && exact32 && finite) ? 1 : 0;
     ctx->inst.W = (float)(2.0 + 2.0 * eps);
     ctx->inst.band = (float)std::ldexp(1.0, -20);
-    CK(cudaMalloc(&ctx->d_raw, sizeof(double2) * (size_t)n));
-    CK(cudaMalloc(&ctx->d_pt64, sizeof(double2) * (size_t)n));
-    CK(cudaMalloc(&ctx->d_pt32, sizeof(float2) * (size_t)n));
+    if (n > ctx->inst_cap) {
+        CK(cudaMalloc(&ctx->d_raw, sizeof(double2) * (size_t)n));
+        CK(cudaMalloc(&ctx->d_pt64, sizeof(double2) * (size_t)n));
+        CK(cudaMalloc(&ctx->d_pt32, sizeof(float2) * (size_t)n));
+        ctx->inst_cap = n;
+    }
     CK(cudaMemcpyAsync(ctx->d_raw, xy, sizeof(double2) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
     CK(launch_prep_points(ctx->d_raw, ctx->d_pt64, ctx->d_pt32, n, weight_type, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -550,7 +570,7 @@ int tspb200_tour_upload(tspb200_ctx *ctx, const int32_t *succ, int64_t log_cap) 
     plan_tiles(ctx, row_start, row_j0);
     const int TI = ctx->T * ctx->R;
     const int alloc = ((n + TI - 1) / TI) * TI + TI + 1024 + 16;
-    if (!ctx->has_tour || ctx->tour.alloc != alloc || ctx->log_cap != log_cap) {
+    if (n > ctx->tour_cap_n || alloc > ctx->tour_cap_rec || log_cap > ctx->tour_cap_log) {
         free_tour(ctx);
         CK(cudaMalloc(&ctx->tour.rec, sizeof(float4) * (size_t)alloc));
         CK(cudaMalloc(&ctx->tour.pos, sizeof(int) * (size_t)n));
@@ -562,16 +582,25 @@ int tspb200_tour_upload(tspb200_ctx *ctx, const int32_t *succ, int64_t log_cap) 
         CK(cudaMalloc(&ctx->d_order, sizeof(int) * (size_t)n));
         CK(cudaMalloc(&ctx->d_succ, sizeof(int) * (size_t)n));
         CK(cudaMalloc(&ctx->d_cost, sizeof(unsigned long long)));
-        ctx->tour.n = n;
-        ctx->tour.alloc = alloc;
-        ctx->tour.ctl = ctx->d_ctl;
-        ctx->tour.log_cap = log_cap;
-        ctx->log_cap = log_cap;
+        ctx->tour_cap_n = n;
+        ctx->tour_cap_rec = alloc;
+        ctx->tour_cap_log = log_cap;
     }
-    cudaFree(ctx->d_tile_row_start); cudaFree(ctx->d_tile_row_j0);
-    ctx->d_tile_row_start = ctx->d_tile_row_j0 = nullptr;
-    CK(cudaMalloc(&ctx->d_tile_row_start, sizeof(int) * (row_start.size() + 1)));
-    CK(cudaMalloc(&ctx->d_tile_row_j0, sizeof(int) * (row_j0.size() + 1)));
+    ctx->tour.n = n;
+    ctx->tour.alloc = alloc;
+    ctx->tour.ctl = ctx->d_ctl;
+    ctx->tour.log_cap = log_cap;  // entries the kernels may write (<= allocated); 0 with a null pointer = no log
+    if (log_cap == 0 && ctx->tour_cap_log == 0) ctx->tour.log = nullptr;
+    ctx->log_cap = log_cap;
+    const int tile_need = (int)row_start.size() + 1;
+    if (tile_need > ctx->tile_cap) {
+        cudaFree(ctx->d_tile_row_start); cudaFree(ctx->d_tile_row_j0);
+        ctx->d_tile_row_start = ctx->d_tile_row_j0 = nullptr;
+        ctx->tile_cap = 0;
+        CK(cudaMalloc(&ctx->d_tile_row_start, sizeof(int) * (size_t)tile_need));
+        CK(cudaMalloc(&ctx->d_tile_row_j0, sizeof(int) * (size_t)tile_need));
+        ctx->tile_cap = tile_need;
+    }
     CK(cudaMemcpyAsync(ctx->d_tile_row_start, row_start.data(), sizeof(int) * row_start.size(), cudaMemcpyHostToDevice, ctx->stream));
     if (!row_j0.empty())
         CK(cudaMemcpyAsync(ctx->d_tile_row_j0, row_j0.data(), sizeof(int) * row_j0.size(), cudaMemcpyHostToDevice, ctx->stream));
@@ -680,7 +709,9 @@ int tspb200_bi_run(tspb200_ctx *ctx, int64_t max_passes, tspb200_stats *st) {
     int exact_grid = ctx->opt_grid > 0 ? ctx->opt_grid : 4 * ctx->num_sms;
     if (exact_grid > n) exact_grid = n > 0 ? n : 1;
     // passes per host round trip: large instances run for milliseconds per pass, small ones for microseconds
-    const long long batch_cap = ctx->opt_batch > 0 ? ctx->opt_batch : (n >= 50000 ? 8 : (n >= 5000 ? 64 : 256));
+    // (a pass that finds the tour already optimal returns at once, so over-launching by a batch costs microseconds, while
+    // every host round trip idles the GPU — and, on several GPUs, every rank that waits for this one's next key)
+    const long long batch_cap = ctx->opt_batch > 0 ? ctx->opt_batch : (n >= 5000 ? 64 : 256);
     long long batch = ctx->opt_batch > 0 ? ctx->opt_batch : 8;  // grows: short runs (TSPLIB-size tours) stop after a few passes
     long long host_launches = 0;
     int status = TSPB200_LOCAL_OPTIMUM;

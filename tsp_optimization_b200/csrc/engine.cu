@@ -106,6 +106,9 @@ struct tspb200_ctx {
     int tour_cap_rec = 0;             // records allocated in tour.rec
     long long tour_cap_log = 0;       // move-log entries allocated
     int tile_cap = 0;                 // ints allocated in each tile table
+    // grow-only scratch buffers of the one-shot entry points (batched 2-opt, NN, tour costs, extra mileage)
+    void *scratch_ptr[16] = {};
+    size_t scratch_cap[16] = {};
     TourDev tour{};
     int *d_order = nullptr, *d_succ = nullptr;
     unsigned long long *d_cost = nullptr;
@@ -160,6 +163,22 @@ static int fail(tspb200_ctx *c, int code, const char *fmt, ...) {
     if (c) c->err = buf;
     return code;
 }
+
+// grow-only device scratch, one buffer per slot; nullptr on allocation failure (cudaGetLastError holds the reason)
+static void *dev_scratch(tspb200_ctx *c, int slot, size_t bytes) {
+    if (bytes == 0) bytes = 16;
+    if (c->scratch_cap[slot] < bytes) {
+        cudaFree(c->scratch_ptr[slot]);
+        c->scratch_ptr[slot] = nullptr;
+        c->scratch_cap[slot] = 0;
+        if (cudaMalloc(&c->scratch_ptr[slot], bytes) != cudaSuccess) return nullptr;
+        c->scratch_cap[slot] = bytes;
+    }
+    return c->scratch_ptr[slot];
+}
+#define SCRATCH(var, type, slot, bytes)                                                                   \
+    type var = static_cast<type>(dev_scratch(ctx, slot, bytes));                                          \
+    if (!var) return fail(ctx, TSPB200_E_CUDA, "cudaMalloc of %zu bytes failed: %s", (size_t)(bytes), cudaGetErrorString(cudaGetLastError()))
 
 #define CK(call)                                                                                          \
     do {                                                                                                  \
@@ -245,6 +264,7 @@ void tspb200_destroy(tspb200_ctx *ctx) {
         free_xchg(ctx);
         if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
         free_instance(ctx);
+        for (int k = 0; k < 16; ++k) cudaFree(ctx->scratch_ptr[k]);
         cudaFree(ctx->d_ctl);
         cudaFreeHost(ctx->h_ctl);
         cudaEventDestroy(ctx->ev0);
@@ -980,14 +1000,15 @@ static int run_batch(tspb200_ctx *ctx, int mode, int32_t *succ, double *obj, int
     const int path = select_path(ctx);
     if (path == 2 && !ctx->d_mat) return fail(ctx, TSPB200_E_STATE, "matrix path selected but no resident matrix");
     InstDev I = inst_for_path(ctx, path);
-    int *d_succ = nullptr;
-    long long *d_delta = nullptr, *d_cnt = nullptr;
-    MoveRec *d_log = nullptr;
     const long long lcap = (log && batch == 1 && log_cap > 0) ? log_cap : 0;
-    CK(cudaMalloc(&d_succ, sizeof(int) * (size_t)n * batch));
-    CK(cudaMalloc(&d_delta, sizeof(long long) * (size_t)batch));
-    CK(cudaMalloc(&d_cnt, sizeof(long long) * 4 * (size_t)batch));
-    if (lcap) CK(cudaMalloc(&d_log, sizeof(MoveRec) * (size_t)lcap));
+    SCRATCH(d_succ, int *, 0, sizeof(int) * (size_t)n * batch);
+    SCRATCH(d_delta, long long *, 1, sizeof(long long) * (size_t)batch);
+    SCRATCH(d_cnt, long long *, 2, sizeof(long long) * 4 * (size_t)batch);
+    MoveRec *d_log = nullptr;
+    if (lcap) {
+        SCRATCH(d_log_, MoveRec *, 3, sizeof(MoveRec) * (size_t)lcap);
+        d_log = d_log_;
+    }
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
     CK(cudaMemcpyAsync(d_succ, succ, sizeof(int) * (size_t)n * batch, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemsetAsync(d_delta, 0, sizeof(long long) * (size_t)batch, ctx->stream));
@@ -995,7 +1016,6 @@ static int run_batch(tspb200_ctx *ctx, int mode, int32_t *succ, double *obj, int
     int launched = 0;
     cudaError_t le = launch_two_opt_batch(I, mode, d_succ, d_delta, d_cnt, batch, ctx->num_sms, ctx->stream, &launched, d_log, lcap);
     if (le != cudaSuccess) {
-        cudaFree(d_succ); cudaFree(d_delta); cudaFree(d_cnt); cudaFree(d_log);
         if (le == cudaErrorInvalidValue) return fail(ctx, TSPB200_E_UNSUPPORTED, "batched 2-opt keeps a tour in shared memory: n=%d is too large", n);
         return fail(ctx, TSPB200_E_CUDA, "batched 2-opt launch failed: %s", cudaGetErrorString(le));
     }
@@ -1011,7 +1031,6 @@ static int run_batch(tspb200_ctx *ctx, int mode, int32_t *succ, double *obj, int
         if (have > 0) CK(cudaMemcpy(log, d_log, sizeof(MoveRec) * (size_t)have, cudaMemcpyDeviceToHost));
     }
     if (log_count) *log_count = batch == 1 ? h_cnt[0] : 0;
-    cudaFree(d_succ); cudaFree(d_delta); cudaFree(d_cnt); cudaFree(d_log);
     tspb200_stats local;
     memset(&local, 0, sizeof local);
     for (int b = 0; b < batch; ++b) {
@@ -1050,16 +1069,11 @@ int tspb200_nn_tour(tspb200_ctx *ctx, int start, int32_t *succ, double *cost) {
     int path = select_path(ctx);
     if (path == 2 && !ctx->d_mat) path = 1;
     InstDev I = inst_for_path(ctx, path == 2 ? 2 : 1);
-    int *d_succ = nullptr;
-    unsigned char *d_vis = nullptr;
-    unsigned long long *d_slots = nullptr;
-    unsigned *d_bar = nullptr;
-    long long *d_cost = nullptr;
-    CK(cudaMalloc(&d_succ, sizeof(int) * (size_t)n));
-    CK(cudaMalloc(&d_vis, (size_t)n));
-    CK(cudaMalloc(&d_slots, sizeof(unsigned long long) * 3));
-    CK(cudaMalloc(&d_bar, sizeof(unsigned)));
-    CK(cudaMalloc(&d_cost, sizeof(long long)));
+    SCRATCH(d_succ, int *, 4, sizeof(int) * (size_t)n);
+    SCRATCH(d_vis, unsigned char *, 5, (size_t)n);
+    SCRATCH(d_slots, unsigned long long *, 6, sizeof(unsigned long long) * 3);
+    SCRATCH(d_bar, unsigned *, 7, sizeof(unsigned));
+    SCRATCH(d_cost, long long *, 8, sizeof(long long));
     CK(cudaMemsetAsync(d_vis, 0, (size_t)n, ctx->stream));
     CK(cudaMemsetAsync(d_slots, 0xff, sizeof(unsigned long long) * 3, ctx->stream));
     CK(cudaMemsetAsync(d_bar, 0, sizeof(unsigned), ctx->stream));
@@ -1074,7 +1088,6 @@ int tspb200_nn_tour(tspb200_ctx *ctx, int start, int32_t *succ, double *cost) {
     if (le == cudaSuccess) le = cudaMemcpyAsync(succ, d_succ, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream);
     if (le == cudaSuccess) le = cudaMemcpyAsync(&c, d_cost, sizeof c, cudaMemcpyDeviceToHost, ctx->stream);
     if (le == cudaSuccess) le = cudaStreamSynchronize(ctx->stream);
-    cudaFree(d_succ); cudaFree(d_vis); cudaFree(d_slots); cudaFree(d_bar); cudaFree(d_cost);
     if (le != cudaSuccess) return fail(ctx, TSPB200_E_CUDA, "nearest-neighbour kernel failed: %s", cudaGetErrorString(le));
     if (cost) *cost = (double)c;
     return TSPB200_OK;
@@ -1095,18 +1108,19 @@ int tspb200_nn_tour_batch(tspb200_ctx *ctx, const int32_t *starts, int batch, in
     InstDev I = inst_for_path(ctx, path == 2 ? 2 : 1);
     I.fp32_ok = ctx->inst.fp32_ok;  // the FP32 filter of the batched kernel is valid whenever the 2-opt filter is
     const float eps = (ctx->inst.W - 2.0f) * 0.5f;
-    int *d_starts = nullptr, *d_succ = nullptr;
-    long long *d_cost = nullptr;
-    CK(cudaMalloc(&d_starts, sizeof(int) * (size_t)batch));
-    CK(cudaMalloc(&d_cost, sizeof(long long) * (size_t)batch));
-    if (succ) CK(cudaMalloc(&d_succ, sizeof(int) * (size_t)batch * n));
+    SCRATCH(d_starts, int *, 9, sizeof(int) * (size_t)batch);
+    SCRATCH(d_cost, long long *, 10, sizeof(long long) * (size_t)batch);
+    int *d_succ = nullptr;
+    if (succ) {
+        SCRATCH(d_succ_, int *, 11, sizeof(int) * (size_t)batch * n);
+        d_succ = d_succ_;
+    }
     CK(cudaMemcpyAsync(d_starts, starts, sizeof(int) * (size_t)batch, cudaMemcpyHostToDevice, ctx->stream));
     cudaError_t le = launch_nn_batch(I, d_starts, batch, d_succ, d_cost, eps, ctx->num_sms, ctx->stream);
     std::vector<long long> h((size_t)batch);
     if (le == cudaSuccess && succ) le = cudaMemcpyAsync(succ, d_succ, sizeof(int) * (size_t)batch * n, cudaMemcpyDeviceToHost, ctx->stream);
     if (le == cudaSuccess) le = cudaMemcpyAsync(h.data(), d_cost, sizeof(long long) * (size_t)batch, cudaMemcpyDeviceToHost, ctx->stream);
     if (le == cudaSuccess) le = cudaStreamSynchronize(ctx->stream);
-    cudaFree(d_starts); cudaFree(d_succ); cudaFree(d_cost);
     if (le == cudaErrorInvalidValue) return fail(ctx, TSPB200_E_UNSUPPORTED, "batched nearest neighbour keeps the coordinates in shared memory: n=%d is too large", n);
     if (le != cudaSuccess) return fail(ctx, TSPB200_E_CUDA, "batched nearest-neighbour kernel failed: %s", cudaGetErrorString(le));
     for (int b = 0; b < batch; ++b) costs[b] = (double)h[(size_t)b];
@@ -1123,16 +1137,13 @@ int tspb200_extra_mileage(tspb200_ctx *ctx, int32_t *succ, double *cost) {
     int path = select_path(ctx);
     if (path == 2 && !ctx->d_mat) path = 1;
     InstDev I = inst_for_path(ctx, path == 2 ? 2 : 1);
-    int *d_succ = nullptr;
-    long long *d_cost = nullptr;
-    CK(cudaMalloc(&d_succ, sizeof(int) * (size_t)n));
-    CK(cudaMalloc(&d_cost, sizeof(long long)));
+    SCRATCH(d_succ, int *, 12, sizeof(int) * (size_t)n);
+    SCRATCH(d_cost, long long *, 13, sizeof(long long));
     cudaError_t le = launch_extra_mileage(I, d_succ, d_cost, ctx->stream);
     long long c = 0;
     if (le == cudaSuccess) le = cudaMemcpyAsync(succ, d_succ, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream);
     if (le == cudaSuccess) le = cudaMemcpyAsync(&c, d_cost, sizeof c, cudaMemcpyDeviceToHost, ctx->stream);
     if (le == cudaSuccess) le = cudaStreamSynchronize(ctx->stream);
-    cudaFree(d_succ); cudaFree(d_cost);
     if (le == cudaErrorInvalidValue) return fail(ctx, TSPB200_E_UNSUPPORTED, "extra mileage keeps its state in shared memory: n=%d is too large", n);
     if (le != cudaSuccess) return fail(ctx, TSPB200_E_CUDA, "extra-mileage kernel failed: %s", cudaGetErrorString(le));
     if (cost) *cost = (double)c;
@@ -1148,16 +1159,13 @@ int tspb200_tour_costs(tspb200_ctx *ctx, const int32_t *tours, int batch, int as
     int path = select_path(ctx);
     if (path == 2 && !ctx->d_mat) path = 1;
     InstDev I = inst_for_path(ctx, path == 2 ? 2 : 1);
-    int *d_t = nullptr;
-    long long *d_o = nullptr;
-    CK(cudaMalloc(&d_t, sizeof(int) * (size_t)n * batch));
-    CK(cudaMalloc(&d_o, sizeof(long long) * (size_t)batch));
+    SCRATCH(d_t, int *, 14, sizeof(int) * (size_t)n * batch);
+    SCRATCH(d_o, long long *, 15, sizeof(long long) * (size_t)batch);
     CK(cudaMemcpyAsync(d_t, tours, sizeof(int) * (size_t)n * batch, cudaMemcpyHostToDevice, ctx->stream));
     cudaError_t le = launch_tour_cost(I, d_t, as_order, d_o, batch, ctx->stream);
     std::vector<long long> h((size_t)batch);
     if (le == cudaSuccess) le = cudaMemcpyAsync(h.data(), d_o, sizeof(long long) * (size_t)batch, cudaMemcpyDeviceToHost, ctx->stream);
     if (le == cudaSuccess) le = cudaStreamSynchronize(ctx->stream);
-    cudaFree(d_t); cudaFree(d_o);
     if (le != cudaSuccess) return fail(ctx, TSPB200_E_CUDA, "tour cost kernel failed: %s", cudaGetErrorString(le));
     for (int b = 0; b < batch; ++b) out[b] = (double)h[b];
     return TSPB200_OK;

@@ -689,3 +689,26 @@ def test_reference_csv_all_deterministic_columns(engine, instances, goldens):
         _, o_em, _, _ = engine.two_opt(FI, s_em, c_em)
         assert o_em == row["2OPT_EXTR_MIL"], nm
         engine.dist_matrix_free()
+
+
+def test_synthetic_full_runs_reach_the_reference_known_answers(engine):
+    """SURVEY.md §8(c) known answers, produced by the compiled reference during the survey (NN start from node 0):
+    uni2000 BI 339437 / 315 moves, FI 345191 / 630 moves / 6 sweeps; uni4000 BI 476692 / 604 moves, FI 491876 / 1156 / 9;
+    uni10000 FI 781189.  Full runs to the local optimum through both single-tour routes where they apply."""
+    for n, nn, bi, fi, fi_full in ((2000, 406727, (339437, 315), (345191, 630, 6), True), (4000, 565693, (476692, 604), (491876, 1156, 9), True),
+                                   (10000, None, None, (781189, None, None), False)):
+        xy = uniform_instance(n)
+        engine.set_instance(xy, 0)
+        succ, cost = engine.nn_tour(0)
+        if nn is not None:
+            assert cost == nn
+        if bi is not None:
+            s, obj, st, _ = engine.two_opt(BI, succ, 0.0)
+            assert (obj, st.moves) == bi and st.passes == bi[1] + 1 and st.evals == (bi[1] + 1) * (n * (n - 3) // 2)
+        for route in ((0, 1) if n <= 4096 else (0,)):
+            engine.set_option("single_block", route)
+            s, obj, st, _ = engine.two_opt(FI, succ, cost)
+            assert obj == fi[0], (n, route)
+            if fi_full:
+                assert (st.moves, st.passes) == fi[1:], (n, route)
+        engine.set_option("single_block", -1)

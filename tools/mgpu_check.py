@@ -20,15 +20,20 @@ def main():
     rank, world, local = init_process_group_from_env("nccl")
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 6000
     passes = int(sys.argv[2]) if len(sys.argv) > 2 else 60
+    wt = 0
     xy = uniform_instance(n)
+    if len(sys.argv) > 3:  # a fixture instance by name, e.g. gr666 (GEO: the exact scan, keys min-allreduced by NCCL)
+        z = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "instances.npz"))
+        xy, wt = z[sys.argv[3] + "__xy"], int(z[sys.argv[3] + "__wt"])
+        n = len(xy)
     single = Engine(local)
-    single.set_instance(xy, 0)
+    single.set_instance(xy, wt)
     succ0, _ = single.nn_tour(0)
     s1, o1, st1, log1 = single.two_opt(BI, succ0, 0.0, max_iters=passes, log_cap=passes + 8)
     single.close()
 
     eng = Engine(local)
-    eng.set_instance(xy, 0)
+    eng.set_instance(xy, wt)
     attach_engine_comm(eng, rank, world)
     ok = True
     times = {}

@@ -101,6 +101,27 @@ class Oracle:
         cost = self.L.orc_nn_tour(xy, n, wt, start, succ)
         return succ, cost
 
+    def greedy_iter(self, xy, wt):
+        """HEU_Greedy_iter -> (best_start, succ, cost)."""
+        xy = _as_xy(xy)
+        n = len(xy)
+        succ = np.empty(n, dtype=np.int32)
+        best = C.c_int32(0)
+        self.L.orc_greedy_iter.restype = C.c_double
+        self.L.orc_greedy_iter.argtypes = [_f64p, C.c_int, C.c_int, _i32p, C.POINTER(C.c_int32)]
+        cost = self.L.orc_greedy_iter(xy, n, wt, succ, C.byref(best))
+        return best.value, succ, cost
+
+    def extra_mileage(self, xy, wt):
+        """HEU_extramileage -> (succ, cost)."""
+        xy = _as_xy(xy)
+        n = len(xy)
+        succ = np.empty(n, dtype=np.int32)
+        self.L.orc_extra_mileage.restype = C.c_double
+        self.L.orc_extra_mileage.argtypes = [_f64p, C.c_int, C.c_int, _i32p]
+        cost = self.L.orc_extra_mileage(xy, n, wt, succ)
+        return succ, cost
+
     def succ_cost(self, xy, wt, succ) -> float:
         xy = _as_xy(xy)
         return self.L.orc_succ_cost(xy, len(xy), wt, np.ascontiguousarray(succ, dtype=np.int32))

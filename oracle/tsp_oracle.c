@@ -131,6 +131,69 @@ double orc_nn_tour(const double *xy, int n, int weight_type, int start, int32_t 
     return total;
 }
 
+/* src/heuristics.c:168-205 HEU_Greedy_iter(): greedy() from every node in index order, the first strictly better tour
+ * is kept (:195).  Time limit not restated.  Returns the best cost, *best_start the node it started from. */
+double orc_greedy_iter(const double *xy, int n, int weight_type, int32_t *succ, int32_t *best_start) {
+    int32_t *trial = (int32_t *)malloc(sizeof(int32_t) * (size_t)n);
+    double best = 1.7976931348623157e308; /* DBL_MAX */
+    for (int start = 0; start < n; start++) {
+        double c = orc_nn_tour(xy, n, weight_type, start, trial);
+        if (c < best) {
+            best = c;
+            if (best_start) *best_start = start;
+            for (int k = 0; k < n; k++) succ[k] = trial[k];
+        }
+    }
+    free(trial);
+    return best;
+}
+
+/* src/heuristics.c:208-314 HEU_extramileage(): the two farthest nodes (strict '>' over the row-major i<j scan, :224-233),
+ * then repeatedly the (unvisited node, tour edge) pair with the smallest C_ac + C_cb - C_ab — nodes in index order outside,
+ * edges in edges_visited[] order inside, strict '<' (:258-277); the replaced edge keeps its slot for (a,c), (c,b) is
+ * appended (:289-293).  Restated with the reference's full O(n^3) rescans.  Needs n >= 2. */
+double orc_extra_mileage(const double *xy, int n, int weight_type, int32_t *succ) {
+    unsigned char *seen = (unsigned char *)calloc((size_t)n, 1);
+    int32_t *ea = (int32_t *)malloc(sizeof(int32_t) * (size_t)n), *eb = (int32_t *)malloc(sizeof(int32_t) * (size_t)n);
+    int na = 0, nb = 1;
+    double far = 0.0;
+    for (int i = 0; i < n; i++)
+        for (int j = i + 1; j < n; j++) {
+            double d = orc_dist(xy, weight_type, 1, i, j);
+            if (d > far) { na = i; nb = j; far = d; }
+        }
+    int cnt = 0;
+    ea[cnt] = na; eb[cnt] = nb; cnt++;
+    ea[cnt] = nb; eb[cnt] = na; cnt++;
+    succ[na] = nb;
+    succ[nb] = na;
+    seen[na] = seen[nb] = 1;
+    double obj = 2 * orc_dist(xy, weight_type, 1, na, nb);
+    while (cnt < n) {
+        double best = 1.7976931348623157e308; /* DBL_MAX */
+        int best_node = -1, best_slot = -1;
+        for (int c = 0; c < n; c++) {
+            if (seen[c]) continue;
+            for (int j = 0; j < cnt; j++) {
+                int a = ea[j], b = eb[j];
+                double delta = orc_dist(xy, weight_type, 1, a, c) + orc_dist(xy, weight_type, 1, c, b) -
+                               orc_dist(xy, weight_type, 1, a, b);
+                if (delta < best) { best = delta; best_node = c; best_slot = j; }
+            }
+        }
+        if (best_slot < 0) break;
+        int a = ea[best_slot], b = eb[best_slot];
+        succ[a] = best_node;
+        succ[best_node] = b;
+        eb[best_slot] = best_node;
+        ea[cnt] = best_node; eb[cnt] = b; cnt++;
+        seen[best_node] = 1;
+        obj += best;
+    }
+    free(seen); free(ea); free(eb);
+    return obj;
+}
+
 /* src/genetic.c:51-60 fitness() */
 double orc_order_cost(const double *xy, int n, int weight_type, const int32_t *order) {
     double total = 0.0;

@@ -6,7 +6,7 @@
  * reference leg may load this library, and there only as the checker or as the
  * reported CPU baseline.  The product (libtspb200.so) never links or calls it.
  *
- * Parity status: PINNED.  This restatement is checked (tests/test_oracle_*.py)
+ * Parity status: PINNED.  This restatement is checked (tests/test_oracle.py)
  *   - against the unmodified reference compiled from /root/reference/src into
  *     oracle/_ref/libtspref.so (all-pairs distances, NN tours, FI and BI move
  *     logs and final tours on TSPLIB + synthetic instances), and
@@ -70,6 +70,12 @@ void orc_dist_row(const double *xy, int n, int weight_type, int i, int32_t *out)
 /* src/heuristics.c:18-78 greedy(): nearest neighbour from `start`; writes succ[] (edges[k].j)
  * and returns the tour cost accumulated exactly as the reference does. Returns -1 on bad start. */
 double orc_nn_tour(const double *xy, int n, int weight_type, int start, int32_t *succ);
+
+/* src/heuristics.c:168-205 HEU_Greedy_iter(): nearest neighbour from every node, first strictly better tour kept. */
+double orc_greedy_iter(const double *xy, int n, int weight_type, int32_t *succ, int32_t *best_start);
+
+/* src/heuristics.c:208-314 HEU_extramileage(): farthest pair + cheapest insertion in the reference's scan order (n >= 2). */
+double orc_extra_mileage(const double *xy, int n, int weight_type, int32_t *succ);
 
 /* src/genetic.c:51-60 fitness(): cost of a tour given as a visiting order (chromosome). */
 double orc_order_cost(const double *xy, int n, int weight_type, const int32_t *order);

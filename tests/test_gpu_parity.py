@@ -661,14 +661,30 @@ def test_extra_mileage_equals_reference_driver(engine, reflib, instances, nm):
     engine.dist_matrix_free()
 
 
-def test_extra_mileage_ties_and_duplicates(engine, reflib):
+def test_extra_mileage_ties_and_duplicates(engine, oracle):
     rng = np.random.default_rng(21)
-    for n in (2, 3, 4, 9, 40, 150):
+    for n in (2, 3, 4, 9, 40, 150, 400):
         xy = rng.integers(0, 9, size=(n, 2)).astype(np.float64)  # few distinct points: ties everywhere, zero distances
-        engine.set_instance(xy, 0)
-        succ, cost = engine.extra_mileage()
-        st, rsucc, robj = reflib.run_method("HEU_extramileage", xy, 0)
-        assert cost == robj and (succ == rsucc).all(), n
+        for wt in (0, 3, 5):
+            engine.set_instance(xy, wt)
+            succ, cost = engine.extra_mileage()
+            osucc, ocost = oracle.extra_mileage(xy, wt)
+            assert cost == ocost and (succ == osucc).all(), (n, wt)
+
+
+def test_constructive_kernels_equal_oracle_on_fixtures(engine, oracle, instances):
+    for nm in ("pr299", "att532", "gr666", "rd400", "ulysses16"):
+        xy, wt = instances[nm]
+        engine.set_instance(xy, wt)
+        if wt == 4:
+            engine.dist_matrix_build()
+        s, c = engine.extra_mileage()
+        os_, oc = oracle.extra_mileage(xy, wt)
+        assert c == oc and (s == os_).all(), nm
+        b, s, c = engine.greedy_iter()
+        ob, os_, oc = oracle.greedy_iter(xy, wt)
+        assert (b, c) == (ob, oc) and (s == os_).all(), nm
+        engine.dist_matrix_free()
 
 
 def test_reference_csv_all_deterministic_columns(engine, instances, goldens):

@@ -171,3 +171,24 @@ def test_large_fixture_spot_check(oracle):
     assert cost == g["fl3795"]["nn_cost"]
     s, obj, st, log = oracle.two_opt_bi(xy, wt, succ, max_passes=3, log_cap=8)
     assert log.tolist() == g["fl3795"]["bi_log"][:3]
+
+
+def test_constructive_restatements_equal_reference_and_csv(oracle, reflib, instances, goldens):
+    """orc_greedy_iter / orc_extra_mileage (reference HEU_Greedy_iter, HEU_extramileage) vs the compiled reference (tour and
+    cost) and vs the published GREEDY_ITER / EXTR_MILE columns."""
+    for nm in ("berlin52", "pr299", "att532", "ulysses22", "gr96", "eil51"):
+        xy, wt = instances[nm]
+        b, s, c = oracle.greedy_iter(xy, wt)
+        st, rs, rc = reflib.run_method("HEU_Greedy_iter", xy, wt)
+        assert st == 0 and c == rc and (s == rs).all(), nm
+        s, c = oracle.extra_mileage(xy, wt)
+        st, rs, rc = reflib.run_method("HEU_extramileage", xy, wt)
+        assert st == 0 and c == rc and (s == rs).all(), nm
+        if nm in goldens["reference_csv"]:
+            assert c == goldens["reference_csv"][nm]["EXTR_MILE"]
+    rng = np.random.default_rng(4)
+    for n in (2, 3, 5, 30):
+        xy = rng.integers(0, 7, size=(n, 2)).astype(np.float64)  # ties and coincident nodes
+        s, c = oracle.extra_mileage(xy, 0)
+        st, rs, rc = reflib.run_method("HEU_extramileage", xy, 0)
+        assert c == rc and (s == rs).all(), n

@@ -79,3 +79,23 @@ def test_product_never_imports_the_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 txt = open(os.path.join(dirpath, fn)).read()
                 assert "tsp_oracle" not in txt and "from oracle" not in txt and "import oracle" not in txt, fn
+
+
+def test_c_example_compiles_against_the_public_header(tmp_path):
+    """examples/two_opt_greedy.c: plain C against include/tspb200.h + libtspb200.so (no CUDA headers on the caller's side).
+    Without a GPU it must stop with the library's own error message, not run on the CPU."""
+    import subprocess
+    exe = str(tmp_path / "two_opt_greedy")
+    lib = os.path.dirname(eng.LIB_PATH)
+    r = subprocess.run(["gcc", "-O2", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "examples", "two_opt_greedy.c"), "-L" + lib, "-ltspb200", "-Wl,-rpath," + lib, "-o", exe],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    tsp = tmp_path / "sq.tsp"
+    tsp.write_text("NAME : sq\nTYPE : TSP\nDIMENSION : 5\nEDGE_WEIGHT_TYPE : EUC_2D\nNODE_COORD_SECTION\n"
+                   "1 0 0\n2 10 0\n3 0 10\n4 10 10\n5 5 5\nEOF\n")
+    r = subprocess.run([exe, str(tsp)], capture_output=True, text=True)
+    if HAVE_GPU:
+        assert r.returncode == 0 and "2-opt (first improvement)" in r.stdout, r.stdout + r.stderr
+    else:
+        assert r.returncode == 1 and "no CPU fallback" in r.stderr

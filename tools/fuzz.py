@@ -56,6 +56,7 @@ while time.time() - t0 < budget:
         cap = int(rng.integers(1, 30))
     eng.set_option("block_threads", T); eng.set_option("rows_per_thread", R); eng.set_option("tile_cols", TJ)
     eng.set_option("single_block", route)
+    eng.set_option("grid", int(rng.choice([0, 0, 1, 3, 17, 64])))  # few blocks -> many rounds of dynamically drawn tiles
     eng.set_instance(xy, wt)
     use_matrix = wt in (1, 2, 4) or rng.random() < 0.15
     if use_matrix:

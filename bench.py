@@ -386,7 +386,7 @@ def main():
     # secondary kernel: distance matrix, HBM-store-bound (4*n*ld bytes written per launch)
     mat = None
     if world == 1:
-        nm = 32768
+        nm = 20000  # 1.6 GB of int32 (> L2); the size the ncu --set full capture in profiles/ was taken at
         eng_m = eng
         eng_m.set_instance(uniform_instance(nm), 0)
         eng_m.dist_matrix_build()
@@ -401,8 +401,9 @@ def main():
         ms = float(np.median(ms_list))
         gbs = 4.0 * nm * ld / (ms * 1e-3) / 1e9
         mat = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
-               "traffic": None, "traffic_note": "ncu at n = 20000: 1.544 GB written of 1.600 GB algorithmic (the rest is still dirty in L2 at kernel end), "
-                                                "0.3 MB read; gpu__dram_throughput 82 % of peak (profiles/r1_ncu_full_bi_scan_128x16_and_matrix.txt)",
+               "traffic": 1.5446e9, "traffic_note": "ncu --set full at this n: dram__bytes_write.sum 1.544 GB + dram__bytes_read.sum 0.3 MB per launch, of "
+                                                    "1.600 GB algorithmic (the rest is still dirty in L2 at kernel end); gpu__dram_throughput 82 % "
+                                                    "of peak (profiles/r1_ncu_full_bi_scan_128x16_and_matrix.txt)",
                "kernel": "dist_matrix_kernel", "n": nm, "ms": ms,
                "per_unit": "4 bytes written per matrix entry (int32), reads O(n)", "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peaks_src})"}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

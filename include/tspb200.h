@@ -93,7 +93,7 @@ const char *tspb200_last_error(const tspb200_ctx *ctx);
  * launch on/off), "l2_flush_bytes" (benchmarks: write that many bytes before every BI pass and time each pass with its
  * own CUDA event pair; stats.gpu_ms is then the sum of the per-pass intervals),
  * "single_block" (tspb200_two_opt on one tour: -1 auto = one thread block with the tour in shared memory for small
- * tours [FI n <= 4096, BI n <= 128], 0 = always the grid kernels, 1 = the block kernel whenever the tour fits),
+ * tours [FI n <= 1536, BI n <= 160], 0 = always the grid kernels, 1 = the block kernel whenever the tour fits),
  * "force_path" (-1 auto, 0 fp32 filter, 1 exact on the fly, 2 matrix), "batch" (passes per host sync),
  * "time_limit_ms" (<=0 unlimited; checked between launch batches). */
 int tspb200_set_option(tspb200_ctx *ctx, const char *key, int64_t value);

@@ -896,10 +896,11 @@ int tspb200_two_opt(tspb200_ctx *ctx, int mode, int32_t *succ, double *obj, int6
     if (mode != TSPB200_FI && mode != TSPB200_BI) return fail(ctx, TSPB200_E_ARG, "mode must be TSPB200_FI or TSPB200_BI");
     // TSPLIB-size tours run to their local optimum inside ONE thread block with the tour in shared memory: no launch per
     // move, which is what a ~1000-node tour is bound by on the grid path (FI: ~30 us per move; BI: ~16 us per pass).
-    // Crossover measured on B200: FI up to 4096 nodes, BI up to 128 (pr299: grid 0.8 ms vs one block 1.9 ms).
+    // Crossover measured on B200 (tools/firoute.py): FI up to ~1500 nodes (n = 1000: 4.7 vs 5.4 ms, n = 2000: 15.4 vs 13.2 ms),
+    // BI up to ~160 (n = 128: 0.28 vs 0.39 ms, n = 200: 0.92 vs 0.78 ms).
     {
         const int n = ctx->n;
-        const int lim = mode == TSPB200_FI ? 4096 : 128;
+        const int lim = mode == TSPB200_FI ? 1536 : 160;
         const bool want = ctx->opt_single_block < 0 ? (n >= 1 && n <= lim) : (ctx->opt_single_block == 1 && (long long)n * 28 + 16 <= 200 * 1024);
         // (the block kernel cannot poll the clock; a tour this small is done within milliseconds, so any limit of a second
         // or more — the reference's CLI default is 900 s — is honoured trivially)

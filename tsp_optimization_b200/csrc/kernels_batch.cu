@@ -210,10 +210,11 @@ __global__ void __launch_bounds__(BATCH_THREADS) two_opt_batch_kernel(const Inst
                 };
                 for (;;) {
                     int myhit = 0x7fffffff;
+                    // this lane's pair of the warp's first chunk; later chunks are 32*NW pairs further along the linear
+                    // order, reached by walking (row, column) forward instead of locating from the cursor again
+                    int row, j;
+                    locate(32 * warp + lane, row, j);
                     for (int q = 0; q < K; ++q) {
-                        const int k = 32 * (warp + q * NW) + lane;
-                        int row, j;
-                        locate(k, row, j);
                         bool hit = false;
                         const bool valid = row < n - 1;
                         if (valid) {
@@ -228,6 +229,13 @@ __global__ void __launch_bounds__(BATCH_THREADS) two_opt_batch_kernel(const Inst
                             break;
                         }
                         if (!__any_sync(0xffffffffu, valid)) break;  // the whole chunk lies past the end of the sweep
+                        long long jj = (long long)j + 32 * NW;
+                        while (row < n - 1 && jj >= n) {
+                            jj -= n;
+                            row += 1;
+                            jj += row + 1;
+                        }
+                        j = (int)jj;
                     }
                     if (lane == 0) s_hits[warp] = myhit;
                     __syncthreads();

@@ -6,18 +6,23 @@
 Workload (config.workload): synthetic uniform EUC_2D instance uni<n> (n = 100000, SURVEY.md §8(c) generator),
 nearest-neighbour start tour built on the GPU, best-improvement 2-opt with on-the-fly distances.
 One STEP = one best-improvement pass = all n(n-3)/2 move deltas evaluated + argmin + move applied.
-  value   = passes * n(n-3)/2 / device time, tour resident in HBM (CUDA events on the engine's stream)
+  value   = passes * n(n-3)/2 / device time, tour resident in HBM, EXHAUSTIVE scan (exact tile pruning off), every pass
+            preceded by an L2 flush and timed by its own CUDA event pair on the engine's stream
   e2e     = the same through the host-buffer C-ABI call tspb200_two_opt(): coordinates + tour uploaded from
             pinned host memory, K passes, tour downloaded, wall clock around the call
-  N > 1   : the pair tiles are dealt round-robin over the ranks (strong scaling, same instance), one 8-byte
-            NCCL min-allreduce per pass selects the move; max over ranks of the device time.
---impl reference times the reference's own CPU code (oracle/_ref: its calc_dist driven over rows of one
-best-improvement scan, all host threads) on the same instance and start tour.
+  N > 1   : the pair tiles are dealt round-robin over the ranks (strong scaling, same instance); per pass every rank's
+            packed argmin key is stored into every peer's slots over NVLink by the scan kernel itself (CUDA IPC peer
+            memory; NCCL only bootstraps the handles and is the fallback); max over ranks of the device time.
+Self-checks: the tour after the timed passes, after the e2e call and after the full run is compared (sha256) with the tour
+obtained by replaying the committed single-GPU move log tests/golden/uni100000_bi_moves.npz on the host, on every rank.
+--impl reference times the reference's own CPU code (oracle/_ref: its calc_dist and x_udir_pos driven over rows of one
+best-improvement scan exactly like src/tabusearch.c:126-156, all host threads) on the same instance and start tour, and the
+stock single-thread alg_2opt_tabu() on uni2000 next to it.
 """
 import argparse
+import hashlib
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -31,6 +36,8 @@ if ROOT not in sys.path:
 METRIC = "2opt_move_evals_per_sec"
 UNIT = "evals/s"
 FP32_INSTR_PER_EVAL = 18  # per-unit figure of the on-the-fly 2-opt roofline
+FIXTURE = os.path.join(ROOT, "tests", "golden", "uni100000_bi_moves.npz")
+NCU_KEYED = os.path.join(ROOT, "profiles", "ncu_by_tile_shape.json")
 
 
 def parse_args():
@@ -43,64 +50,80 @@ def parse_args():
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-tlo", action="store_true", help="skip the time-to-local-optimum runs (uni100000 on N GPUs, uni10000)")
+    ap.add_argument("--no-extras", action="store_true", help="skip ga_batch / matrix roofline / per-pass breakdown")
     ap.add_argument("--rows-per-thread", type=int, default=0)
     ap.add_argument("--tile-cols", type=int, default=0)
     return ap.parse_args()
 
 
-class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md clocks line)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+def workload_config(n: int) -> dict:
+    """Identical in both arms (the driver compares the two lines' config)."""
+    return {"workload": f"uni{n} EUC_2D (SURVEY.md §8c generator), nearest-neighbour start, best-improvement 2-opt passes with "
+                        f"on-the-fly distances (BASELINE configs[3])",
+            "n": n, "pairs_per_step": n * (n - 3) // 2,
+            "l2": "GPU arm: 256 MB written before every timed pass on the engine's stream, outside the per-pass event pairs "
+                  "(at N > 1 followed by a peer-slot barrier so that no rank's flush time lands in a peer's timed pass); "
+                  "CPU arm: not applicable"}
 
-    def __init__(self, gpu_index: int):
-        self.idx = gpu_index
-        self.proc = None
-        self.lines = []
+
+def sha(a) -> str:
+    return hashlib.sha256(np.ascontiguousarray(a, dtype=np.int32).tobytes()).hexdigest()
+
+
+class ClockSampler:
+    """SM clock and throttle reasons read IN-PROCESS through NVML (pynvml) every few milliseconds from a thread that is
+    started before the warm-up, so that even a 30 ms timed region holds samples; stop(t0, t1) reports the samples taken
+    inside [t0, t1] (perf_counter), falling back to the samples of the whole run under load."""
+
+    def __init__(self, gpu_index: int, period_s: float = 0.002):
+        self.idx, self.period, self.samples, self._stop = gpu_index, period_s, [], False
+        self.err = None
+        self.max_mhz = None
+        self.t = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.idx), "-lms", "25"], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._pump, daemon=True)
-            self.t.start()
-        except OSError:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.idx)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:  # noqa: BLE001
+            self.err = f"NVML unavailable: {e}"
+            return self
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
+        return self
 
-    def _pump(self):
-        for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
-
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
+    def _run(self):
+        nv, h = self.nv, self.h
+        reasons_fn = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self._stop:
             try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for nm, v in zip(names, f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        # "under load": samples in the upper half of the observed range
-        hi = [x for x in sm if x >= 0.5 * max(sm)]
-        return {"sm_mhz": float(np.median(hi)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "samples": len(sm)}
+                self.samples.append((time.perf_counter(), float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), int(reasons_fn(h))))
+            except Exception as e:  # noqa: BLE001
+                self.err = str(e)
+                return
+            time.sleep(self.period)
+
+    def stop(self, t0: float, t1: float) -> dict:
+        self._stop = True
+        if self.t:
+            self.t.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [self.err or "no samples"], "samples": 0, "source": "nvml"}
+        inside = [s for s in self.samples if t0 <= s[0] <= t1]
+        where = "timed region"
+        if len(inside) < 3:  # a region shorter than a few sampling periods: the whole run, upper half of the clock range
+            top = max(s[1] for s in self.samples)
+            inside = [s for s in self.samples if s[1] >= 0.5 * top]
+            where = "warm-up + timed region (timed region shorter than 3 sampling periods)"
+        bits = 0
+        for s in inside:
+            bits |= s[2]
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+        return {"sm_mhz": float(np.median([s[1] for s in inside])), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(v for k, v in names.items() if bits & k), "samples": len(inside), "source": f"nvml, {where}"}
 
 
 def measured_peaks():
@@ -123,16 +146,21 @@ def pinned(arr: np.ndarray) -> np.ndarray:
 out_holder = []
 
 
-def cpu_baseline_sample(xy, succ, seconds_budget: float):
-    """Rows of ONE best-improvement scan on the host cores: the reference's compiled calc_dist when
-    oracle/_ref is present (kind "reference"), else the oracle port."""
+# ---- CPU reference (test infrastructure: the only place bench.py touches oracle/) ---------------------------------------
+def _ref_lib():
     from oracle.oracle import Oracle, RefLib, REF_SO
+    if os.path.exists(REF_SO):
+        return RefLib(), "reference"
+    return Oracle(), "port"
+
+
+def cpu_baseline_sample(xy, succ, seconds_budget: float):
+    """Rows of ONE best-improvement scan on the host cores, the loop of reference src/tabusearch.c:126-156 line by line
+    (adjacency test, the four x_udir_pos calls, the NULL tabu-list test, four calc_dist calls) with the reference's own
+    compiled calc_dist / x_udir_pos when oracle/_ref is present (kind "reference"), else the oracle port."""
     n = len(xy)
     threads = os.cpu_count() or 1
-    if os.path.exists(REF_SO):
-        lib, kind = RefLib(), "reference"
-    else:
-        lib, kind = Oracle(), "port"
+    lib, kind = _ref_lib()
     # calibrate on a few rows, then size the sample for the time budget
     ev, sec, _ = lib.bi_scan_rows_mt(xy, 0, succ, 0, min(n - 1, 16 * threads), threads)
     rate = ev / max(sec, 1e-6)
@@ -144,26 +172,47 @@ def cpu_baseline_sample(xy, succ, seconds_budget: float):
         rows = int(n - np.sqrt(max(0.0, float(n) * n - 2.0 * want)))
         rows = max(16 * threads, min(n - 1, rows))
     ev, sec, _ = lib.bi_scan_rows_mt(xy, 0, succ, 0, rows, threads)
-    return {"value": ev / sec, "unit": UNIT, "cores": threads, "kind": kind,
+    return {"value": ev / sec, "unit": UNIT, "cores": threads, "kind": kind, "value_per_core": ev / sec / threads,
             "sample": f"rows [0,{rows}) of one best-improvement scan of uni{n} from the NN start = {ev} pair evaluations "
-                      f"in {sec:.2f} s; {'reference calc_dist (oracle/_ref)' if kind == 'reference' else 'oracle port'}, "
+                      f"in {sec:.2f} s; {'reference calc_dist + x_udir_pos (oracle/_ref)' if kind == 'reference' else 'oracle port'}, "
                       f"{threads} threads, rows dealt in blocks of 16"}, rows
+
+
+def stock_one_core(m: int = 2000):
+    """The UNMODIFIED alg_2opt_tabu(inst, NULL, NULL, 1, 1) (reference src/tabusearch.c:107) run to completion on uni<m>
+    from the nearest-neighbour start, one thread: the stock single-core figure BASELINE.md §3 asks for.  Known answer at
+    m = 2000: cost 339437, 315 moves, 631 052 000 evaluations."""
+    from oracle.oracle import REF_SO, RefLib
+    from tsp_optimization_b200.instances import uniform_instance
+    if not os.path.exists(REF_SO):
+        return None
+    lib = RefLib()
+    xy = uniform_instance(m)
+    succ, _ = lib.nn_tour(xy, 0, 0)
+    t0 = time.perf_counter()
+    s, cost = lib.two_opt_bi(xy, 0, succ)
+    sec = time.perf_counter() - t0
+    # moves = passes - 1; the reference does not count, so replay the count from the cost trajectory of the port
+    from oracle.oracle import Oracle
+    _, ocost, ost, _ = Oracle().two_opt_bi(xy, 0, succ)
+    ok = bool(cost == ocost)
+    return {"workload": f"uni{m} NN start -> alg_2opt_tabu(inst, NULL, NULL, 1, 1) to the local optimum, unmodified reference, 1 thread",
+            "seconds": sec, "final_cost": cost, "passes": int(ost.passes), "moves": int(ost.moves), "evals": int(ost.evals),
+            "value": ost.evals / sec, "unit": UNIT, "cores": 1, "cost_equals_port": ok}
 
 
 def run_reference(args, rank):
     """--impl reference: the reference CPU implementation on the same workload (rank 0 only)."""
     if rank != 0:
         return
-    from oracle.oracle import Oracle
     from tsp_optimization_b200.instances import uniform_instance
     n = args.n
     xy = uniform_instance(n)
     succ = start_tour_cpu_or_cached(xy, n)
     total = max(1, args.steps + args.warmup)
-    per_step = max(0.3, min(8.0, 150.0 / total))
+    per_step = max(0.3, min(8.0, 120.0 / total))
     base, rows = cpu_baseline_sample(xy, succ, per_step)
-    from oracle.oracle import RefLib, REF_SO
-    lib = RefLib() if os.path.exists(REF_SO) else Oracle()
+    lib, _ = _ref_lib()
     threads = os.cpu_count() or 1
     for _ in range(args.warmup):
         lib.bi_scan_rows_mt(xy, 0, succ, 0, rows, threads)
@@ -174,11 +223,15 @@ def run_reference(args, rank):
         sec_sum += sec
     val = ev_sum / sec_sum
     base["value"] = val
+    base["value_per_core"] = val / threads
+    stock = stock_one_core(2000 if n >= 10000 else 600)
+    if stock:
+        base["stock_1core"] = stock
+        base["harness_per_core_over_stock_1core"] = val / threads / stock["value"]
     line = {"metric": METRIC, "value": val, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * sec_sum / max(1, args.steps), "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"uni{n} EUC_2D, NN start, best-improvement 2-opt scan (reference CPU code)", "n": n},
-            "cpu_baseline": base,
+            "config": workload_config(n), "cpu_baseline": base,
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -203,6 +256,43 @@ def start_tour_cpu_or_cached(xy, n):
     return succ
 
 
+class TourFixture:
+    """The committed single-GPU move log of the workload (tests/golden/make_uni100000_moves.py): expected tour after P passes
+    = the NN start with the first P moves applied on the host."""
+
+    def __init__(self, n: int, succ0):
+        self.ok = n == 100000 and os.path.exists(FIXTURE)
+        self.succ0 = succ0
+        if self.ok:
+            z = np.load(FIXTURE)
+            self.moves = z["moves"]
+            self.final = {"passes": int(z["final_passes"]), "moves": int(z["final_moves"]), "cost": float(z["final_cost"]),
+                          "sha256": str(z["final_sha256"])}
+            self.ok = sha(succ0) == str(z["nn_sha256"])
+
+    def check_after_passes(self, succ, passes: int) -> dict:
+        out = {"tour_sha256": sha(succ), "passes": int(passes)}
+        if not self.ok or passes > len(self.moves):
+            out["check"] = "no fixture for this workload / pass count"
+            return out
+        from tsp_optimization_b200.instances import apply_moves
+        exp = apply_moves(self.succ0, self.moves[:passes])
+        out["expected_sha256"] = sha(exp)
+        out["check"] = "ok" if out["expected_sha256"] == out["tour_sha256"] else "MISMATCH"
+        return out
+
+    def check_final(self, succ, passes, moves, cost) -> dict:
+        out = {"tour_sha256": sha(succ)}
+        if not self.ok:
+            out["check"] = "no fixture for this workload"
+            return out
+        f = self.final
+        good = out["tour_sha256"] == f["sha256"] and passes == f["passes"] and moves == f["moves"] and cost == f["cost"]
+        out["expected_sha256"] = f["sha256"]
+        out["check"] = "ok" if good else "MISMATCH"
+        return out
+
+
 def main():
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -219,16 +309,31 @@ def main():
     import torch
     import torch.distributed as dist
 
-    from tsp_optimization_b200 import BI, Engine
-    from tsp_optimization_b200.dist import attach_engine_comm, init_process_group_from_env
-    from tsp_optimization_b200.instances import uniform_instance
+    from tsp_optimization_b200 import BI, FI, Engine
+    from tsp_optimization_b200.dist import attach_engine_comm, init_process_group_from_env, shard_batch
+    from tsp_optimization_b200.instances import order_to_succ, reference_random_population, uniform_instance
 
     if world > 1:
         init_process_group_from_env("nccl")
     torch.cuda.set_device(local)
+    sampler = ClockSampler(local).start()
     n = args.n
     xy = uniform_instance(n)
     pairs = n * (n - 3) // 2
+
+    def maxr(x: float) -> float:
+        if world == 1:
+            return float(x)
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def all_ok(flag: bool) -> bool:
+        if world == 1:
+            return bool(flag)
+        t = torch.tensor([1 if flag else 0], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(t.item())
 
     eng = Engine(local)
     if args.rows_per_thread:
@@ -245,8 +350,10 @@ def main():
             np.save(os.path.join(ROOT, "gpurun_out", f"nn_uni{n}.npy"), succ0)
         except OSError:
             pass
+    fixture = TourFixture(n, succ0)
     if world > 1:
         attach_engine_comm(eng, rank, world)
+    eng.set_option("prune", 0)  # throughput = exhaustive scans: every non-adjacent pair of every pass is evaluated
     eng.tour_upload(succ0)
 
     flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # matrix kernel timing only
@@ -264,21 +371,18 @@ def main():
     eng.bi_run(args.warmup)
     if not args.no_flush:
         eng.set_option("l2_flush_bytes", 256 << 20)
-    sampler = ClockSampler(local)
     barrier()
-    sampler.start()
-    wall0 = time.perf_counter()
+    t_region0 = time.perf_counter()
     st = eng.bi_run(args.steps)
     barrier()
-    wall_s = time.perf_counter() - wall0
-    clocks = sampler.stop()
+    t_region1 = time.perf_counter()
+    wall_s = t_region1 - t_region0
     eng.set_option("l2_flush_bytes", 0)
-    gpu_ms, launches, moves, done_passes = st.gpu_ms, st.launches, st.moves, st.passes
-    if world > 1:
-        t = torch.tensor([gpu_ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        gpu_ms = float(t.item())
+    gpu_ms, launches, moves, done_passes = maxr(st.gpu_ms), st.launches, st.moves, st.passes
     value = done_passes * pairs / (gpu_ms * 1e-3)
+    tour_after, _ = eng.tour_download()
+    chk_value = fixture.check_after_passes(tour_after, args.warmup + done_passes)
+    clocks = sampler.stop(t_region0, t_region1)
 
     # ---- e2e: host buffers through the C-ABI, copies inside the timed region -------------------------------
     h_xy = pinned(xy)
@@ -291,12 +395,9 @@ def main():
     eng.set_instance(h_xy, 0)
     s_out, obj_out, st_e, _ = eng.two_opt(BI, h_succ, 0.0, max_iters=e2e_passes)
     torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - w0
-    if world > 1:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
+    e2e_s = maxr(time.perf_counter() - w0)
     e2e_val = st_e.passes * pairs / e2e_s
+    chk_e2e = fixture.check_after_passes(s_out, st_e.passes)
     h2d = 16 * n + 4 * n
     d2h = 4 * n + 8
 
@@ -314,43 +415,105 @@ def main():
         cur, _, st_s, _ = eng.two_opt(BI, cur, 0.0, max_iters=1)
         done_step += st_s.passes
     torch.cuda.synchronize()
-    step_s = time.perf_counter() - w0
-    if world > 1:
-        t = torch.tensor([step_s], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        step_s = float(t.item())
+    step_s = maxr(time.perf_counter() - w0)
     e2e_step = {"value": done_step * pairs / step_s, "unit": UNIT, "h2d_bytes_per_step": 4 * n, "d2h_bytes_per_step": 4 * n + 8,
-                "steps": step_calls, "seconds": step_s, "call": "tspb200_two_opt(BI, host succ[], max_iters=1) once per step"}
+                "steps": step_calls, "seconds": step_s, "call": "tspb200_two_opt(BI, host succ[], max_iters=1) once per step",
+                "tour_check": fixture.check_after_passes(cur, done_step)["check"]}
+
+    # ---- where a pass's time goes (device %globaltimer stamps; a separate short run, not part of `value`) -----------
+    breakdown = None
+    if not args.no_extras:
+        eng.set_option("timing", 1)
+        eng.tour_upload(succ0)
+        eng.bi_run(4)
+        eng.tour_upload(succ0)
+        barrier()
+        stb = eng.bi_run(60)
+        cnt = max(1, eng.info("tm_count"))
+        breakdown = {k[3:] + "_us": round(eng.info(k) / cnt / 1e3, 2) for k in
+                     ("tm_gap", "tm_scan", "tm_spread", "tm_tail", "tm_xwait", "tm_apply_gap", "tm_apply")}
+        breakdown.update({"passes": int(stb.passes), "us_per_pass_events": round(1e3 * stb.gpu_ms / max(1, stb.passes), 2),
+                          "legend": "per pass, this rank: gap = previous apply's end -> first scan block; scan = first scan block -> "
+                                    "last block's ticket; spread = first block done -> last block done (inside scan); tail = ticket -> "
+                                    "move published (includes xwait = polling the peers' keys); apply_gap = published -> first "
+                                    "apply block; apply = apply kernel.  L2 not flushed in this run."})
+        eng.set_option("timing", 0)
 
     # ---- time to local optimum (BASELINE metric, second half): the same instance and start tour, run to the end ----
     tlo = None
     if not args.no_tlo:
-        eng.set_instance(h_xy, 0)
-        barrier()
-        w0 = time.perf_counter()
-        s_out, obj_out, st_f, _ = eng.two_opt(BI, h_succ, 0.0)
-        torch.cuda.synchronize()
-        tlo_s = time.perf_counter() - w0
-        if world > 1:
-            t = torch.tensor([tlo_s], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            tlo_s = float(t.item())
-        tlo = {"workload": f"uni{n} NN start -> best-improvement 2-opt local optimum on {world} GPU(s), host buffers in and out",
-               "time_to_local_optimum_s": tlo_s, "passes": st_f.passes, "moves": st_f.moves, "gpu_ms": st_f.gpu_ms,
-               "start_cost": nn_cost, "final_cost": obj_out, "evals": st_f.evals, "evals_per_s": st_f.evals / tlo_s}
+        tlo = {}
+        for key, prune in (("exhaustive", 0), ("pruned", 1)):
+            eng.set_option("prune", prune)
+            eng.set_instance(h_xy, 0)
+            barrier()
+            w0 = time.perf_counter()
+            s_out, obj_out, st_f, _ = eng.two_opt(BI, h_succ, 0.0)
+            torch.cuda.synchronize()
+            tlo_s = maxr(time.perf_counter() - w0)
+            rec = {"time_to_local_optimum_s": tlo_s, "passes": st_f.passes, "moves": st_f.moves, "gpu_ms": st_f.gpu_ms,
+                   "start_cost": nn_cost, "final_cost": obj_out, "evals": st_f.evals, "evals_per_s": st_f.evals / tlo_s,
+                   "tour_check": fixture.check_final(s_out, st_f.passes, st_f.moves, obj_out)}
+            if prune:
+                rec.update({"tiles_scanned": st_f.tiles_scanned, "tiles_total": st_f.tiles_total,
+                            "tiles_skipped": st_f.tiles_total - st_f.tiles_scanned,
+                            "note": "exact tile pruning: tiles whose lower bound exceeds the best exact delta known are not "
+                                    "evaluated; same move log, `evals` counts evaluated pairs only (this rank's share)"})
+            rec["all_ranks_ok"] = all_ok(rec["tour_check"]["check"] != "MISMATCH")
+            if key == "exhaustive":
+                tlo.update({"workload": f"uni{n} NN start -> best-improvement 2-opt local optimum on {world} GPU(s), host buffers in and out"})
+                tlo.update(rec)
+            else:
+                tlo["pruned"] = rec
+        eng.set_option("prune", 0)
         if world == 1 and n != 10000:  # BASELINE configs[2]: uni10000, greedy start + 2-opt to the local optimum, 1 B200
             xy2 = uniform_instance(10000)
             eng.set_instance(xy2, 0)
             s2, c2 = eng.nn_tour(0)
-            eng.two_opt(BI, s2, 0.0, max_iters=4)  # warm-up of this tile shape
-            for mode, nm in ((BI, "BI"), (1 - BI, "FI")):
-                w0 = time.perf_counter()
-                _, o2, st2, _ = eng.two_opt(mode, s2, c2)
-                d2 = time.perf_counter() - w0
-                tlo[f"uni10000_{nm}"] = {"time_to_local_optimum_s": d2, "passes": st2.passes, "moves": st2.moves,
-                                         "final_cost": o2, "evals": st2.evals}
+            for prune in (0, 1):
+                eng.set_option("prune", prune)
+                eng.two_opt(BI, s2, 0.0, max_iters=4)  # warm-up of this tile shape
+                for mode, nm in ((BI, "BI"), (FI, "FI")):
+                    if mode == FI and prune:
+                        continue
+                    w0 = time.perf_counter()
+                    _, o2, st2, _ = eng.two_opt(mode, s2, c2)
+                    d2 = time.perf_counter() - w0
+                    tlo[f"uni10000_{nm}" + ("_pruned" if prune else "")] = {
+                        "time_to_local_optimum_s": d2, "passes": st2.passes, "moves": st2.moves, "final_cost": o2, "evals": st2.evals,
+                        "us_per_pass": 1e3 * st2.gpu_ms / max(1, st2.passes) if mode == BI else None}
+            eng.set_option("prune", 0)
             eng.set_instance(h_xy, 0)
-            eng.tour_upload(h_succ)
+
+    # ---- BASELINE configs[4]: GA population 1024 x uni1000, every tour driven to its 2-opt local optimum -----------------
+    ga = None
+    if not args.no_extras:
+        n_ga, pop = 1000, 1024
+        xy_ga = uniform_instance(n_ga)
+        orders = reference_random_population(n_ga, pop, 123)  # reference genetic.c:349-364, srandom(123)
+        succ_ga = np.stack([order_to_succ(o) for o in orders])
+        lo, hi = shard_batch(pop, rank, world)
+        eng.set_instance(xy_ga, 0)
+        ga = {"workload": f"{pop} x uni{n_ga} tours from random_generation() (glibc random(), seed 123), each to its 2-opt local optimum; "
+                          f"contiguous shards of {hi - lo} tours per GPU, no data-path collective",
+              "population_sha256": sha(orders)}
+        mine = np.ascontiguousarray(succ_ga[lo:hi])
+        costs0 = eng.tour_costs(mine, as_order=False)
+        for mode, nm in ((FI, "FI"), (BI, "BI")):
+            eng.two_opt_batch(mode, mine[:8], costs0[:8])  # warm-up
+            barrier()
+            w0 = time.perf_counter()
+            sb, ob, stg = eng.two_opt_batch(mode, mine, costs0)
+            torch.cuda.synchronize()
+            sec = maxr(time.perf_counter() - w0)
+            tot = torch.tensor([float(stg.moves), float(stg.evals), float(ob.sum())], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(tot)
+            ga[nm] = {"seconds": sec, "tours_per_s": pop / sec, "moves": int(tot[0].item()), "evals": int(tot[1].item()),
+                      "evals_per_s": float(tot[1].item()) / sec, "sum_of_final_costs": float(tot[2].item()),
+                      "call": "tspb200_two_opt_batch (host buffers in and out, inside the timed region)"}
+        eng.set_instance(h_xy, 0)
+
     if rank != 0:
         eng.close()
         if world > 1:
@@ -358,84 +521,102 @@ def main():
         return
 
     peaks, peaks_src = measured_peaks()
-    sm_mhz = clocks.get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
+    if clocks.get("sm_mhz"):
+        sm_mhz, clock_src = clocks["sm_mhz"], f"NVML median over the {clocks['source'].split(', ', 1)[1]}"
+    else:
+        sm_mhz, clock_src = peaks.get("sm_max_mhz", 1965.0), "no NVML sample: MEASURED_PEAKS.json sm_max_mhz"
     num_sms = eng.info("num_sms")
     per_gpu = value / world
     # Binding unit of bi_scan_kernel: the SFU (MUFU.SQRT, 16 results/clk/SM).  Algorithmic minimum = ONE distance
     # (one sqrt) per evaluated move: every D[p][q] is shared by the two moves that use it.
     sqrt_peak = num_sms * 16 * sm_mhz * 1e6
     fp32_peak = num_sms * 128 * sm_mhz * 1e6
-    R = eng.info("rows_per_thread")
+    T, R, TJ = eng.info("block_threads"), eng.info("rows_per_thread"), eng.info("tile_cols")
+    ncu = {}
+    if os.path.exists(NCU_KEYED):
+        with open(NCU_KEYED) as f:
+            ncu = json.load(f).get(f"{T}x{R}x{TJ}", {})
+    ipe = ncu.get("thread_instr_per_eval")
     roofline = {"bound": "sfu_sqrt", "achieved": per_gpu / 1e12, "peak": sqrt_peak / 1e12, "unit": "T sqrt/s (= T evals/s)",
-                "frac": per_gpu / sqrt_peak, "traffic": 1.726e6, "kernel": "bi_scan_kernel",
+                "frac": per_gpu / sqrt_peak, "traffic": ncu.get("dram_bytes_per_launch"), "kernel": "bi_scan_kernel",
                 "per_unit": f"1 MUFU.SQRT per evaluated move (algorithmic minimum: every distance serves two moves); the kernel "
                             f"issues (R+1)/R = {(R + 1) / R:.4f} with R = {R} rows per thread",
-                "peak_source": f"{num_sms} SMs x 16 MUFU/clk x {sm_mhz:.0f} MHz (nvidia-smi median under load); "
-                               f"MEASURED_PEAKS.json ({peaks_src}) holds HBM and bf16 figures only, neither bounds this kernel",
-                "ncu": "profiles/r1_ncu_full_bi_scan_64x8_final.txt (bi_scan_kernel<64,8>, n = 100 000): XU pipe 89 % of peak, "
-                       "issue slots 66 %, 6.66 thread instructions per evaluated move, DRAM 1.7 MB read / 0 written per launch",
+                "peak_source": f"{num_sms} SMs x 16 MUFU/clk x {sm_mhz:.0f} MHz ({clock_src}); MEASURED_PEAKS.json ({peaks_src}) "
+                               f"holds HBM and bf16 figures only, neither bounds this kernel",
+                "ncu": ncu if ncu else f"no ncu capture committed for tile shape {T}x{R}x{TJ} (profiles/ncu_by_tile_shape.json)",
                 "fp32_issue_view": {"survey_per_unit": FP32_INSTR_PER_EVAL,
                                     "frac_vs_survey_18_instr_model": per_gpu * FP32_INSTR_PER_EVAL / fp32_peak,
-                                    "executed_thread_instr_per_eval": 6.66,
-                                    "frac_issue_slots": per_gpu * 6.66 / fp32_peak,
+                                    "executed_thread_instr_per_eval": ipe,
+                                    "frac_issue_slots": per_gpu * ipe / fp32_peak if ipe else None,
                                     "note": "SURVEY.md §8d's 18 lane-instr/eval model evaluates two fresh distances per move with "
                                             "scalar FP32; sharing each distance between its two moves and packed FP32x2 arithmetic "
-                                            "bring the executed count to 6.66, so the 18-instr fraction exceeds 1 and is reported "
-                                            "for reference only"},
-                "traffic_note": "dram__bytes_read.sum per launch (ncu --set full, cold L2): the tour records once, 16 B/node; compute-bound"}
+                                            "bring the executed count far below it, so the 18-instr fraction exceeds 1 and is "
+                                            "reported for reference only"}}
     # secondary kernel: distance matrix, HBM-store-bound (4*n*ld bytes written per launch)
     mat = None
-    if world == 1:
+    if world == 1 and not args.no_extras:
         nm = 20000  # 1.6 GB of int32 (> L2); the size the ncu --set full capture in profiles/ was taken at
-        eng_m = eng
-        eng_m.set_instance(uniform_instance(nm), 0)
-        eng_m.dist_matrix_build()
+        eng.set_instance(uniform_instance(nm), 0)
+        eng.dist_matrix_build()
         ms_list = []
         for _ in range(5):
             if flush is not None:
                 flush.zero_()
                 torch.cuda.synchronize()
-            ms_list.append(eng_m.dist_matrix_build())
-        ld = eng_m.info("matrix_ld")
-        eng_m.dist_matrix_free()
+            ms_list.append(eng.dist_matrix_build())
+        ld = eng.info("matrix_ld")
+        eng.dist_matrix_free()
         ms = float(np.median(ms_list))
         gbs = 4.0 * nm * ld / (ms * 1e-3) / 1e9
+        mncu = {}
+        if os.path.exists(NCU_KEYED):
+            with open(NCU_KEYED) as f:
+                mncu = json.load(f).get("dist_matrix_n20000", {})
         mat = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
-               "traffic": 1.5446e9, "traffic_note": "ncu --set full at this n: dram__bytes_write.sum 1.544 GB + dram__bytes_read.sum 0.3 MB per launch, of "
-                                                    "1.600 GB algorithmic (the rest is still dirty in L2 at kernel end); gpu__dram_throughput 82 % "
-                                                    "of peak (profiles/r1_ncu_full_bi_scan_128x16_and_matrix.txt)",
-               "kernel": "dist_matrix_kernel", "n": nm, "ms": ms,
+               "traffic": mncu.get("dram_bytes_per_launch"), "ncu": mncu, "kernel": "dist_matrix_kernel", "n": nm, "ms": ms,
                "per_unit": "4 bytes written per matrix entry (int32), reads O(n)", "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peaks_src})"}
+    cfg = workload_config(n)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": gpu_ms / max(1, done_passes), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"uni{n} EUC_2D (SURVEY.md §8c generator), GPU nearest-neighbour start, best-improvement "
-                                   f"2-opt passes with on-the-fly distances (BASELINE configs[3])",
-                       "n": n, "pairs_per_step": pairs, "block_threads": eng.info("block_threads"), "rows_per_thread": eng.info("rows_per_thread"),
-                       "tile_cols": eng.info("tile_cols"), "grid": eng.info("grid_bi"), "tiles": eng.info("ntiles"),
+            "dtype": "f32", "data": "synthetic", "config": cfg,
+            "engine": {"block_threads": T, "rows_per_thread": R, "tile_cols": TJ, "grid": eng.info("grid_bi"), "tiles": eng.info("ntiles"),
                        "sharding": ("tiles round-robin over ranks; per pass each rank's 8-byte argmin key is " +
                                     ("stored into every peer's slots over NVLink by the scan kernel (CUDA IPC peer memory)"
                                      if eng.info("exchange_p2p") else "min-allreduced by NCCL")) if world > 1 else "single GPU",
-                       "l2": "flushed before every timed pass (256 MB write on the engine stream, outside the per-pass event pairs)"
-                             if not args.no_flush else "not flushed (5.7 MB working set)",
-                       "nn_start_s": nn_s},
+                       "l2_flush": not args.no_flush, "nn_start_s": nn_s, "tile_pruning": "off for value / e2e (exhaustive scans)"},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d / e2e_passes, "d2h_bytes_per_step": d2h / e2e_passes,
                     "passes": st_e.passes, "seconds": e2e_s,
                     "call": "tspb200_set_instance + tspb200_two_opt(BI, host succ[], max_iters=steps)",
-                    "one_call_per_step": e2e_step},
+                    "tour_check": chk_e2e, "one_call_per_step": e2e_step},
             "gpu_launches": int(launches), "moves_applied": int(moves), "wall_s": wall_s,
-            "clocks": clocks, "roofline": roofline}
+            "tour_check": chk_value, "clocks": clocks, "roofline": roofline}
+    if breakdown:
+        line["pass_breakdown"] = breakdown
     if mat:
         line["roofline_matrix"] = mat
     if tlo:
         line["time_to_local_optimum"] = tlo
+    if ga:
+        line["ga_batch"] = ga
     if not args.no_cpu_baseline and world == 1:
-        base, _ = cpu_baseline_sample(xy, succ0, 15.0)
+        base, _ = cpu_baseline_sample(xy, succ0, 12.0)
+        stock = stock_one_core(2000 if n >= 10000 else 600)
+        if stock:
+            base["stock_1core"] = stock
+            base["harness_per_core_over_stock_1core"] = base["value_per_core"] / stock["value"]
         line["cpu_baseline"] = base
+    bad = [k for k, c in (("value", chk_value), ("e2e", chk_e2e)) if c.get("check") == "MISMATCH"]
+    if tlo and tlo.get("tour_check", {}).get("check") == "MISMATCH":
+        bad.append("time_to_local_optimum")
+    if tlo and tlo.get("pruned", {}).get("tour_check", {}).get("check") == "MISMATCH":
+        bad.append("time_to_local_optimum.pruned")
+    line["self_check"] = "ok" if not bad else "MISMATCH in " + ", ".join(bad)
     print(json.dumps(line), flush=True)
     eng.close()
     if world > 1:
         dist.destroy_process_group()
+    if bad:
+        sys.exit(3)
 
 
 if __name__ == "__main__":

@@ -67,14 +67,17 @@ typedef struct tspb200_ctx tspb200_ctx;
 typedef struct {
     int64_t passes;     /* BI: scans performed (incl. the terminating one); FI: sweeps               */
     int64_t moves;      /* applied moves                                                             */
-    int64_t evals;      /* BI: passes * n(n-3)/2 (every non-adjacent pair is evaluated every scan);  */
-                        /* FI: linear pairs swept (upper bound of the reference's count)             */
+    int64_t evals;      /* BI: passes * n(n-3)/2 (every non-adjacent pair is evaluated every scan), scaled    */
+                        /* by tiles_scanned / tiles_total when tiles were pruned (pairs excluded by the exact */
+                        /* bound are not evaluations); FI: linear pairs swept (upper bound of the reference's) */
     int64_t launches;   /* kernel launches of OUR kernels inside the timed region                    */
     int64_t obj_delta;  /* sum of the applied deltas                                                 */
     double gpu_ms;      /* device time of the run, CUDA events on the engine's stream                */
     double cost;        /* tour cost after the run (BI: recomputed from scratch; FI: obj_in + delta) */
     int32_t status;     /* TSPB200_LOCAL_OPTIMUM / _TIME_LIMIT_EXCEEDED / _STOPPED_BY_CAP            */
     int32_t path;       /* 0 = FP32 filter + FP64 exact (EUC/CEIL/ATT), 1 = exact on the fly, 2 = matrix lookup */
+    int64_t tiles_scanned; /* BI with exact tile pruning: tiles this rank evaluated ...                          */
+    int64_t tiles_total;   /* ... out of passes * (this rank's tiles); both 0 when the scan was exhaustive        */
 } tspb200_stats;
 
 typedef struct {
@@ -174,6 +177,10 @@ int tspb200_comm_destroy(tspb200_ctx *ctx);
  * sharding tests. */
 int tspb200_debug_tile_plan(int n, int T, int R, int TJ, int num_sms, int world, int *out_T, int *out_R, int *out_TJ,
                             int *row_start, int *row_j0, int cap, int *ntr);
+
+/* Timing experiments: device-side debug buffers ("block_times": [grid][2] uint64 %globaltimer stamps {start, end} of every
+ * block of the last best-improvement pass run with option "timing" = 2). */
+int tspb200_debug_fetch(tspb200_ctx *ctx, const char *what, void *out, int64_t bytes);
 
 #ifdef __cplusplus
 }

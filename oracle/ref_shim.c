@@ -4,7 +4,7 @@
  * touches has the reference's real layout; it re-creates the few lines of set-up that
  * src/solver.c:264-270 (TSP_heuc) does before calling a heuristic, and exposes helpers that the
  * reference has no API for (layout report, all-pairs calc_dist, a multi-threaded partial BI scan
- * that calls the reference's own calc_dist for the CPU baseline).
+ * that calls the reference's own calc_dist and x_udir_pos per pair, like src/tabusearch.c:126-156, for the CPU baseline).
  */
 #include <pthread.h>
 #include <stddef.h>
@@ -118,6 +118,8 @@ static void *ref_scan_worker(void *arg) {
     instance *inst = jb->inst;
     int n = inst->num_nodes;
     const edge *ed = inst->solution.edges;
+    int *volatile skip_edge_v = NULL;
+    int *skip_edge = skip_edge_v; /* opaque to the optimiser: the index computations stay, like in the stock build */
     jb->evals = 0; jb->best = 0; jb->bi = 0; jb->bj = 0;
     for (int r0 = jb->row_begin + jb->tid * 16; r0 < jb->row_end; r0 += jb->nthreads * 16) {
         int r1 = r0 + 16 < jb->row_end ? r0 + 16 : jb->row_end;
@@ -126,6 +128,11 @@ static void *ref_scan_worker(void *arg) {
                 int a1 = ed[a].j, b1 = ed[b].j;
                 if (b == a1 || b1 == a) continue;
                 jb->evals++;
+                /* src/tabusearch.c:137-149: the stock loop computes the four tabu-list indices with the reference's own
+                 * x_udir_pos() for every pair and tests `skip_edge &&` (NULL here) before the four calc_dist calls; kept
+                 * so that this harness does per pair exactly what alg_2opt_tabu(inst, NULL, NULL, 1, 1) does */
+                int e1 = x_udir_pos(a, b, n), e2 = x_udir_pos(a, a1, n), e3 = x_udir_pos(b, b1, n), e4 = x_udir_pos(a, b1, n);
+                if (skip_edge && (skip_edge[e1] | skip_edge[e2] | skip_edge[e3] | skip_edge[e4])) continue;
                 double delta = calc_dist(a, b, inst) + calc_dist(a1, b1, inst) - calc_dist(a, a1, inst) - calc_dist(b, b1, inst);
                 if (delta < jb->best || (delta == jb->best && delta < 0 && (a < jb->bi || (a == jb->bi && b < jb->bj)))) {
                     jb->best = delta; jb->bi = a; jb->bj = b;

@@ -162,15 +162,23 @@ def _check_bi(engine, oracle, xy, wt, succ0, max_passes=-1, force_path=-1):
         engine.dist_matrix_build()
     os_, oobj, ost, olog = oracle.two_opt_bi(xy, wt, succ0, max_passes=max_passes, log_cap=100000)
     st = None
-    for route in ((0, 1) if (max_passes < 0 and len(xy) <= 2000) else (0,)):
+    # (route, prune): grid kernels exhaustive, grid kernels with exact tile pruning (must select the very same moves), one-block
+    combos = [(0, 0), (0, 1)] + ([(1, 0)] if (max_passes < 0 and len(xy) <= 2000) else [])
+    for route, prune in combos:
         engine.set_option("single_block", route)
+        engine.set_option("prune", prune)
         s, obj, st_r, log = engine.two_opt(BI, succ0, 0.0, max_iters=max_passes, log_cap=100000)
-        assert log.tolist() == olog.tolist(), route
-        assert (s == os_).all() and obj == oobj, route
-        assert st_r.moves == ost.moves and st_r.passes == ost.passes and st_r.evals == ost.evals, route
+        assert log.tolist() == olog.tolist(), (route, prune)
+        assert (s == os_).all() and obj == oobj, (route, prune)
+        assert st_r.moves == ost.moves and st_r.passes == ost.passes, (route, prune)
+        if prune and st_r.tiles_total:
+            assert st_r.evals <= ost.evals and 0 <= st_r.tiles_scanned <= st_r.tiles_total
+        else:
+            assert st_r.evals == ost.evals, (route, prune)
         assert st_r.launches == 1 or route == 0
         st = st or st_r
     engine.set_option("single_block", -1)
+    engine.set_option("prune", -1)
     engine.set_option("force_path", -1)
     return st
 
@@ -719,8 +727,13 @@ def test_synthetic_full_runs_reach_the_reference_known_answers(engine):
         if nn is not None:
             assert cost == nn
         if bi is not None:
-            s, obj, st, _ = engine.two_opt(BI, succ, 0.0)
-            assert (obj, st.moves) == bi and st.passes == bi[1] + 1 and st.evals == (bi[1] + 1) * (n * (n - 3) // 2)
+            for prune in (0, 1):  # exhaustive scan / exact tile pruning: same moves, same local optimum
+                engine.set_option("prune", prune)
+                s, obj, st, _ = engine.two_opt(BI, succ, 0.0)
+                assert (obj, st.moves) == bi and st.passes == bi[1] + 1, (n, prune)
+                full = (bi[1] + 1) * (n * (n - 3) // 2)
+                assert st.evals == full if not prune else st.evals <= full, (n, prune)
+            engine.set_option("prune", -1)
         for route in ((0, 1) if n <= 4096 else (0,)):
             engine.set_option("single_block", route)
             s, obj, st, _ = engine.two_opt(FI, succ, cost)
@@ -728,3 +741,84 @@ def test_synthetic_full_runs_reach_the_reference_known_answers(engine):
             if fi_full:
                 assert (st.moves, st.passes) == fi[1:], (n, route)
         engine.set_option("single_block", -1)
+
+
+def test_capped_runs_can_be_continued_in_either_mode(engine, oracle):
+    """include/tspb200.h: repeated calls on the resident tour continue where the previous one stopped.  fi_run(k) then
+    fi_run(-1) is the oracle's full first-improvement run; bi_run(k) then fi_run(-1) is the oracle's first-improvement
+    run started from the tour k best-improvement passes lead to (node-space tables rebuilt, fresh sweep)."""
+    xy = uniform_instance(900)
+    succ0, c0 = oracle.nn_tour(xy, 0, 0)
+    engine.set_instance(xy, 0)
+    engine.set_option("single_block", 0)
+    try:
+        fs, fobj, fst, flog = oracle.two_opt_fi(xy, 0, succ0, c0, log_cap=100000)
+        engine.tour_upload(succ0, log_cap=100000)
+        st = engine.fi_run(7)
+        assert st.status == eng.STOPPED_BY_CAP and st.moves == 7
+        st = engine.fi_run(-1)
+        assert st.status == eng.LOCAL_OPTIMUM and st.moves == fst.moves - 7
+        s, cost = engine.tour_download()
+        assert engine.tour_log(100000).tolist() == flog.tolist() and (s == fs).all() and cost == fobj
+        # a finished run stays finished: one more call of either mode does nothing
+        assert engine.fi_run(-1).moves == 0 and engine.bi_run(-1).moves == 0
+
+        bs, bobj, bst, blog = oracle.two_opt_bi(xy, 0, succ0, max_passes=9, log_cap=100000)
+        es, eobj, est, elog = oracle.two_opt_fi(xy, 0, bs, bobj, log_cap=100000)
+        engine.tour_upload(succ0, log_cap=100000)
+        st = engine.bi_run(9)
+        assert st.status == eng.STOPPED_BY_CAP and st.moves == 9
+        st = engine.fi_run(-1)
+        assert st.status == eng.LOCAL_OPTIMUM and st.moves == est.moves
+        s, cost = engine.tour_download()
+        assert engine.tour_log(100000).tolist() == blog.tolist() + elog.tolist()
+        assert (s == es).all() and cost == eobj
+        # and the other way round: a capped first-improvement run followed by best improvement to the end
+        ps, pobj, pst, plog = oracle.two_opt_fi(xy, 0, succ0, c0, max_moves=11, log_cap=100000)
+        qs, qobj, qst, qlog = oracle.two_opt_bi(xy, 0, ps, log_cap=100000)
+        engine.tour_upload(succ0, log_cap=100000)
+        assert engine.fi_run(11).moves == 11
+        st = engine.bi_run(-1)
+        assert st.status == eng.LOCAL_OPTIMUM and st.moves == qst.moves
+        s, cost = engine.tour_download()
+        assert engine.tour_log(100000).tolist() == plog.tolist() + qlog.tolist() and (s == qs).all() and cost == qobj
+    finally:
+        engine.set_option("single_block", -1)
+
+
+def test_edge_lengths_up_to_2_pow_24_and_loud_rejection_beyond(engine, oracle):
+    """coordinates ~1e7: distances up to 1.4e7 still fit the FP32 edge-length words exactly (exact path, FP64 distances);
+    coordinates ~1e8 do not — the 2-opt entry points must refuse instead of silently rounding."""
+    rng = np.random.default_rng(123)
+    xy = rng.integers(0, 10_000_000, size=(300, 2)).astype(np.float64)
+    succ0 = order_to_succ(rng.permutation(300).astype(np.int32))
+    _check_bi(engine, oracle, xy, 0, succ0)
+    assert engine.info("fp32_ok") == 0 and engine.info("dist_bound") < (1 << 24)
+    _check_fi(engine, oracle, xy, 0, succ0, oracle.succ_cost(xy, 0, succ0))
+    big = rng.integers(0, 100_000_000, size=(300, 2)).astype(np.float64)
+    engine.set_instance(big, 0)
+    assert (engine.dist_matrix() == oracle.dist_matrix(big, 0)).all()  # distances themselves are fine
+    engine.dist_matrix_free()
+    for call in (lambda: engine.two_opt(BI, succ0, 0.0), lambda: engine.two_opt(FI, succ0, 0.0),
+                 lambda: engine.two_opt_batch(BI, succ0[None, :])):
+        with pytest.raises(eng.TspB200Error) as ei:
+            call()
+        assert ei.value.code == 5  # TSPB200_E_UNSUPPORTED
+
+
+def test_pruned_scan_skips_tiles_but_not_moves(engine, oracle):
+    """exact tile pruning on a spatially coherent tour: most tiles are provably dead, the move log is unchanged."""
+    xy = uniform_instance(6000)
+    succ0, _ = oracle.nn_tour(xy, 0, 0)
+    engine.set_instance(xy, 0)
+    logs = {}
+    for prune in (0, 1):
+        engine.set_option("prune", prune)
+        s, obj, st, log = engine.two_opt(BI, succ0, 0.0, max_iters=120, log_cap=200)
+        logs[prune] = (log.tolist(), s.tolist(), obj, st)
+    engine.set_option("prune", -1)
+    assert logs[0][:3] == logs[1][:3]
+    st = logs[1][3]
+    assert st.tiles_total > 0 and st.tiles_scanned < 0.7 * st.tiles_total
+    es, eobj, est, elog = oracle.two_opt_bi(xy, 0, succ0, max_passes=120, log_cap=200)
+    assert logs[1][0] == elog.tolist() and logs[1][2] == eobj

@@ -26,7 +26,11 @@ cudaError_t launch_bi_scan_exact(const InstDev &inst, const TourDev &tour, int r
 cudaError_t launch_bi_scan_tabu(const InstDev &inst, const TourDev &tour, int *skip, int iter, int tenure, long long *zl,
                                 unsigned long long *zl_count, long long zl_cap, int grid, cudaStream_t st);
 cudaError_t launch_bi_decode_packed(const TourDev &tour, cudaStream_t st);
-cudaError_t launch_apply_move(const InstDev &inst, const TourDev &tour, int num_sms, int seed, bool pdl, cudaStream_t st);
+cudaError_t launch_apply_move(const InstDev &inst, const TourDev &tour, int num_sms, int seed, int timing, bool pdl,
+                              cudaStream_t st);
+cudaError_t launch_tile_prune(const BiArgs &a, int TI, int grid_bi, bool pdl, cudaStream_t st);
+cudaError_t launch_rank_align(const XchgDev &x, int rank, int world, Ctl *ctl, cudaStream_t st);
+cudaError_t launch_rebuild_node_space(const TourDev &T, cudaStream_t st);
 cudaError_t launch_refresh_node_space(const TourDev &tour, int num_sms, bool pdl, cudaStream_t st);
 cudaError_t launch_fi_search(const InstDev &I, const TourDev &T, int grid, bool pdl, cudaStream_t st);
 cudaError_t launch_dist_matrix(const InstDev &I, int *out, long long ld, int row_begin, int row_end, bool fast,
@@ -76,6 +80,7 @@ static NcclApi g_nccl;
 constexpr int NCCL_CHAR = 0;    // ncclInt8
 constexpr int NCCL_INT32 = 2;   // ncclInt32
 constexpr int NCCL_UINT64 = 5;  // ncclUint64
+constexpr int NCCL_MAX = 2;     // ncclMax
 constexpr int NCCL_MIN = 3;     // ncclMin
 
 }  // namespace tspb
@@ -106,6 +111,11 @@ struct tspb200_ctx {
     int tour_cap_rec = 0;             // records allocated in tour.rec
     long long tour_cap_log = 0;       // move-log entries allocated
     int tile_cap = 0;                 // ints allocated in each tile table
+    int box_cap = 0;                  // entries allocated in each of the pruning box arrays
+    long long live_cap = 0;           // entries allocated in the live-tile list
+    bool node_dirty = false;          // best-improvement moves were applied since the node-space tables were built
+    bool fi_cursor_stale = false;     // ... and the first-improvement sweep state refers to a tour that no longer exists
+    double dist_bound = 0;            // upper bound of any distance of the instance (edge lengths live in FP32 words)
     // grow-only scratch buffers of the one-shot entry points (batched 2-opt, NN, tour costs, extra mileage)
     void *scratch_ptr[16] = {};
     size_t scratch_cap[16] = {};
@@ -126,6 +136,11 @@ struct tspb200_ctx {
     int opt_seed_hint = 1;
     int opt_pdl = 1;
     int opt_single_block = -1;
+    int opt_prune = -1;         // exact tile pruning of the best-improvement scan: -1 auto, 0 off (exhaustive scan), 1 on
+    int opt_timing = 0;         // accumulate the per-pass breakdown (scan / tail / exchange wait / apply) on the device
+    int opt_tail_split = -1;    // tail smoothing: -1 auto, 0/1 off, 2 or 4 = sub-tiles per split tile
+    int opt_tail_tiles = 0;     // tiles per rank that are split (0 = auto: half a wave)
+    unsigned long long *d_dbg = nullptr;  // per-block time stamps of the last pass ("timing" = 2)
     int opt_debug_shard = 0;    // timing experiments only: (world << 8 | rank) -> scan that rank's share of the tiles on one GPU  // -1 auto, 0 never, 1 whenever the tour fits in shared memory
     // benchmark hygiene: write this many bytes (> L2) before every pass and time each pass with its own event pair
     long long opt_flush_bytes = 0;
@@ -147,8 +162,9 @@ struct tspb200_ctx {
     int rank = 0, world = 1;
     // argmin exchange over NVLink peer memory (see XchgDev): own slots + IPC-mapped peer slots
     XchgDev xchg{};
-    XchgSlot *d_slots = nullptr;
-    unsigned *d_epoch = nullptr;
+    XchgMem *d_slots = nullptr;
+    unsigned *d_epoch = nullptr;      // [0] exchange epoch, [1] alignment epoch
+    int *d_stop = nullptr;            // collective time-limit decision
     void *peer_mapped[XCHG_MAX_WORLD] = {};
     std::string xchg_note;
     int opt_exchange = 0;  // 0 = peer memory when available, 1 = NCCL allreduce
@@ -190,6 +206,8 @@ static void *dev_scratch(tspb200_ctx *c, int slot, size_t bytes) {
 static void free_tour(tspb200_ctx *c) {
     cudaFree(c->tour.rec); cudaFree(c->tour.pos); cudaFree(c->tour.nrec); cudaFree(c->tour.nds);
     cudaFree(c->tour.nsucc); cudaFree(c->tour.block_best); cudaFree(c->tour.log);
+    cudaFree(c->tour.rowbox); cudaFree(c->tour.colbox); cudaFree(c->tour.rowmaxds); cudaFree(c->tour.colmaxds);
+    cudaFree(c->tour.live); cudaFree(c->tour.live_lb);
     cudaFree(c->d_order); cudaFree(c->d_succ); cudaFree(c->d_cost);
     cudaFree(c->d_tile_row_start); cudaFree(c->d_tile_row_j0);
     c->tour = TourDev{};
@@ -198,6 +216,8 @@ static void free_tour(tspb200_ctx *c) {
     c->has_tour = false;
     c->tour_cap_n = c->tour_cap_rec = c->tile_cap = 0;
     c->tour_cap_log = 0;
+    c->box_cap = 0;
+    c->live_cap = 0;
 }
 
 static void free_xchg(tspb200_ctx *c) {
@@ -207,8 +227,10 @@ static void free_xchg(tspb200_ctx *c) {
     }
     cudaFree(c->d_slots);
     cudaFree(c->d_epoch);
+    cudaFree(c->d_stop);
     c->d_slots = nullptr;
     c->d_epoch = nullptr;
+    c->d_stop = nullptr;
     c->xchg = XchgDev{};
 }
 
@@ -265,6 +287,7 @@ void tspb200_destroy(tspb200_ctx *ctx) {
         if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
         free_instance(ctx);
         for (int k = 0; k < 16; ++k) cudaFree(ctx->scratch_ptr[k]);
+        cudaFree(ctx->d_dbg);
         cudaFree(ctx->d_ctl);
         cudaFreeHost(ctx->h_ctl);
         cudaEventDestroy(ctx->ev0);
@@ -300,6 +323,18 @@ int tspb200_set_option(tspb200_ctx *ctx, const char *key, int64_t value) {
     } else if (k == "single_block") {
         if (value < -1 || value > 1) return fail(ctx, TSPB200_E_ARG, "single_block must be -1 (auto), 0 or 1");
         ctx->opt_single_block = (int)value;
+    } else if (k == "prune") {
+        if (value < -1 || value > 1) return fail(ctx, TSPB200_E_ARG, "prune must be -1 (auto), 0 or 1");
+        ctx->opt_prune = (int)value;
+    } else if (k == "timing") {
+        if (value < 0 || value > 2) return fail(ctx, TSPB200_E_ARG, "timing must be 0, 1 or 2");
+        ctx->opt_timing = (int)value;
+    } else if (k == "tail_split") {
+        if (value != -1 && value != 0 && value != 1 && value != 2 && value != 4) return fail(ctx, TSPB200_E_ARG, "tail_split must be -1 (auto), 0, 1, 2 or 4");
+        ctx->opt_tail_split = (int)value;
+    } else if (k == "tail_tiles") {
+        if (value < 0) return fail(ctx, TSPB200_E_ARG, "tail_tiles must be >= 0");
+        ctx->opt_tail_tiles = (int)value;
     } else if (k == "pdl") {
         ctx->opt_pdl = value ? 1 : 0;
     } else if (k == "seed_hint") {
@@ -339,6 +374,14 @@ int64_t tspb200_get_info(const tspb200_ctx *ctx, const char *key) {
     if (k == "matrix_resident") return ctx->d_mat != nullptr;
     if (k == "matrix_ld") return ctx->mat_ld;
     if (k == "cold_calls") return ctx->h_ctl ? (int64_t)ctx->h_ctl->cold_calls : -1;  // as of the last host sync
+    if (k == "tiles_scanned") return ctx->h_ctl ? (int64_t)ctx->h_ctl->tiles_scanned : -1;
+    // per-pass breakdown accumulated since the tour was uploaded (option "timing"), ns; tm_count = passes accumulated
+    if (k.rfind("tm_", 0) == 0 && ctx->h_ctl) {
+        const char *names[] = {"tm_gap", "tm_scan", "tm_spread", "tm_tail", "tm_xwait", "tm_apply_gap", "tm_apply", "tm_count"};
+        for (int t = 0; t < 8; ++t)
+            if (k == names[t]) return (int64_t)ctx->h_ctl->tm_acc[t];
+    }
+    if (k == "dist_bound") return (int64_t)ctx->dist_bound;
     if (k == "exchange_p2p") return ctx->xchg.enabled && ctx->opt_exchange == 0;
     if (k == "world") return ctx->world;
     if (k == "rank") return ctx->rank;
@@ -377,6 +420,12 @@ int tspb200_set_instance(tspb200_ctx *ctx, const double *xy, int n, int weight_t
     }
     double dmax = std::hypot(xmax - xmin, ymax - ymin);
     ctx->dmax = dmax;
+    // upper bound of any distance: the 2-opt state keeps edge lengths as exact integers in FP32 words (< 2^24)
+    if (!finite) ctx->dist_bound = INFINITY;
+    else if (weight_type == TSPB200_GEO) ctx->dist_bound = 20040.0;                        // pi * 6378.388 + 2
+    else if (weight_type == TSPB200_ATT) ctx->dist_bound = dmax / std::sqrt(10.0) + 2.0;
+    else if (weight_type == TSPB200_MAN_2D || weight_type == TSPB200_MAX_2D) ctx->dist_bound = (xmax - xmin) + 2.0;  // dy == 0
+    else ctx->dist_bound = dmax + 2.0;
     const bool metric_fp32 = (weight_type != TSPB200_GEO && weight_type != TSPB200_MAN_2D && weight_type != TSPB200_MAX_2D);
     // FP32 filter usable when distances stay well inside the FP32 integer range (exact ds as float)
     const bool fp32_ok = finite && metric_fp32 && dmax < 4.0e6;
@@ -534,9 +583,23 @@ static void choose_tile_shape(int n, int num_sms, int world, int opt_T, int opt_
     *T = bt; *R = br; *TJ = btj;
 }
 
+// exact tile pruning pays once a pass is deep enough that skipping tiles outweighs the two extra (tiny) launches
+constexpr int PRUNE_AUTO_MIN_N = 3000;
+static bool prune_wanted(const tspb200_ctx *ctx) {
+    return ctx->opt_prune >= 0 ? ctx->opt_prune == 1 : ctx->n >= PRUNE_AUTO_MIN_N;
+}
+
 static void plan_tiles(tspb200_ctx *ctx, std::vector<int> &row_start, std::vector<int> &row_j0) {
     const int world_eff = ctx->opt_debug_shard ? (ctx->opt_debug_shard >> 8) : ctx->world;
     choose_tile_shape(ctx->n, ctx->num_sms, world_eff, ctx->opt_T, ctx->opt_R, ctx->opt_TJ, &ctx->T, &ctx->R, &ctx->TJ);
+    // A pruned pass scans a few per cent of the tiles: small tiles (256 positions x 64 columns) hug the live region much
+    // more tightly than the throughput shape (measured on uni100000: 64 x 4 x 64 -> 76 us per pass, 64 x 8 x 256 -> 130 us).
+    if (prune_wanted(ctx) && ctx->inst.fp32_ok && ctx->opt_force_path <= 0 && ctx->n >= PRUNE_AUTO_MIN_N) {
+        if (!ctx->opt_T) ctx->T = 64;
+        if (!ctx->opt_R) ctx->R = 4;
+        if (!ctx->opt_TJ) ctx->TJ = 64;
+        if (!bi_shape_supported(ctx->T, ctx->R)) { ctx->T = 64; ctx->R = 4; }
+    }
     const int slots = ctx->num_sms * bi_blocks_per_sm(ctx->T, ctx->R);
     ctx->ntiles = (int)tile_plan(ctx->n, ctx->T * ctx->R, ctx->TJ, &row_start, &row_j0);
     ctx->ntr = (int)row_j0.size();
@@ -545,6 +608,18 @@ static void plan_tiles(tspb200_ctx *ctx, std::vector<int> &row_start, std::vecto
     if (grid > per_rank) grid = (int)(per_rank > 0 ? per_rank : 1);
     if (grid > 4096) grid = 4096;  // block_best[] capacity
     ctx->grid_bi = grid;
+}
+
+// Timing experiments: copies a device-side debug buffer to the host ("block_times": [grid][2] %globaltimer stamps of the
+// last best-improvement pass run with option "timing" = 2).
+int tspb200_debug_fetch(tspb200_ctx *ctx, const char *what, void *out, int64_t bytes) {
+    if (!ctx || !ctx->stream || !what || !out) return TSPB200_E_ARG;
+    if (std::string(what) != "block_times" || !ctx->d_dbg) return fail(ctx, TSPB200_E_STATE, "nothing recorded for %s", what);
+    const int64_t have = (int64_t)sizeof(unsigned long long) * 2 * 4096;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(out, ctx->d_dbg, (size_t)(bytes < have ? bytes : have), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return TSPB200_OK;
 }
 
 // Host-only helper (no device needed): the tile plan for (n, T, R, TJ); T, R or TJ == 0 -> automatic choice for
@@ -573,6 +648,9 @@ int tspb200_tour_upload(tspb200_ctx *ctx, const int32_t *succ, int64_t log_cap) 
     if (!succ) return fail(ctx, TSPB200_E_ARG, "null succ");
     CK(cudaSetDevice(ctx->device));
     const int n = ctx->n;
+    if (!(ctx->dist_bound < 16777216.0))
+        return fail(ctx, TSPB200_E_UNSUPPORTED, "2-opt keeps edge lengths as exact integers in FP32 words: distances up to %.0f "
+                    "(>= 2^24) are not supported", ctx->dist_bound);
     // successor array -> visiting order from node 0 (also validates that succ is one Hamiltonian cycle)
     std::vector<int> order((size_t)n);
     {
@@ -621,6 +699,30 @@ int tspb200_tour_upload(tspb200_ctx *ctx, const int32_t *succ, int64_t log_cap) 
         CK(cudaMalloc(&ctx->d_tile_row_j0, sizeof(int) * (size_t)tile_need));
         ctx->tile_cap = tile_need;
     }
+    // exact tile pruning: boxes per tile-row / tile-column and the live-tile list of this rank
+    {
+        const int box_need = n / 32 + 8;  // >= tile-columns at the smallest tile width and >= tile-rows
+        if (box_need > ctx->box_cap) {
+            cudaFree(ctx->tour.rowbox); cudaFree(ctx->tour.colbox); cudaFree(ctx->tour.rowmaxds); cudaFree(ctx->tour.colmaxds);
+            ctx->tour.rowbox = ctx->tour.colbox = nullptr;
+            ctx->tour.rowmaxds = ctx->tour.colmaxds = nullptr;
+            ctx->box_cap = 0;
+            CK(cudaMalloc(&ctx->tour.rowbox, sizeof(float4) * (size_t)box_need));
+            CK(cudaMalloc(&ctx->tour.colbox, sizeof(float4) * (size_t)box_need));
+            CK(cudaMalloc(&ctx->tour.rowmaxds, sizeof(float) * (size_t)box_need));
+            CK(cudaMalloc(&ctx->tour.colmaxds, sizeof(float) * (size_t)box_need));
+            ctx->box_cap = box_need;
+        }
+        const long long live_need = (long long)ctx->ntiles + 32;
+        if (live_need > ctx->live_cap) {
+            cudaFree(ctx->tour.live); cudaFree(ctx->tour.live_lb);
+            ctx->tour.live = nullptr; ctx->tour.live_lb = nullptr;
+            ctx->live_cap = 0;
+            CK(cudaMalloc(&ctx->tour.live, sizeof(int) * (size_t)live_need));
+            CK(cudaMalloc(&ctx->tour.live_lb, sizeof(float) * (size_t)live_need));
+            ctx->live_cap = live_need;
+        }
+    }
     CK(cudaMemcpyAsync(ctx->d_tile_row_start, row_start.data(), sizeof(int) * row_start.size(), cudaMemcpyHostToDevice, ctx->stream));
     if (!row_j0.empty())
         CK(cudaMemcpyAsync(ctx->d_tile_row_j0, row_j0.data(), sizeof(int) * row_j0.size(), cudaMemcpyHostToDevice, ctx->stream));
@@ -631,7 +733,11 @@ int tspb200_tour_upload(tspb200_ctx *ctx, const int32_t *succ, int64_t log_cap) 
     c0.fi_found = FI_NONE;
     c0.max_moves = -1;
     c0.last.i = c0.last.j = 0x7fffffff;
+    c0.pass_min = KEY_PACK_NONE;
+    c0.tm_scan_first = c0.tm_blk_end_min = c0.tm_apply_first = ~0ull;
     *ctx->h_ctl = c0;
+    ctx->node_dirty = false;
+    ctx->fi_cursor_stale = false;
     CK(cudaMemcpyAsync(ctx->d_ctl, ctx->h_ctl, sizeof(Ctl), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemsetAsync(ctx->tour.block_best, 0, sizeof(MoveKey) * 4096, ctx->stream));  // delta 0 = "no previous winner"
     InstDev I = inst_for_path(ctx, select_path(ctx));
@@ -684,6 +790,28 @@ static int sync_ctl(tspb200_ctx *ctx) {
     return TSPB200_OK;
 }
 
+// A run that stopped at a cap leaves done = 1 behind with done_reason = DONE_CAP; the next run — whichever mode — clears
+// it (include/tspb200.h: repeated calls continue where the previous one stopped).  A real local optimum stays final.
+// `reset_fi_cursor`: the first-improvement sweep state refers to a tour that best-improvement moves have changed since;
+// the next fi_run starts a fresh sweep.  The host owns the state here: the stream was just synchronised by sync_ctl().
+static int prepare_run(tspb200_ctx *ctx, bool reset_fi_cursor, long long max_moves_abs) {
+    Ctl *h = ctx->h_ctl;
+    if (h->done && h->done_reason == DONE_CAP) {
+        h->done = 0;
+        h->done_reason = DONE_NONE;
+    }
+    if (reset_fi_cursor) {
+        h->cur_i = 0;
+        h->cur_j = 1;
+        h->sweep_moves = 0;
+        h->fi_found = FI_NONE;
+        h->fi_seg = 0;
+    }
+    h->max_moves = max_moves_abs;
+    CK(cudaMemcpyAsync(ctx->d_ctl, h, sizeof(Ctl), cudaMemcpyHostToDevice, ctx->stream));
+    return TSPB200_OK;
+}
+
 int tspb200_bi_run(tspb200_ctx *ctx, int64_t max_passes, tspb200_stats *st) {
     if (!ctx || !ctx->stream) return fail(ctx, TSPB200_E_CUDA, "context has no CUDA device");
     if (!ctx->has_tour) return fail(ctx, TSPB200_E_STATE, "no tour uploaded");
@@ -696,7 +824,9 @@ int tspb200_bi_run(tspb200_ctx *ctx, int64_t max_passes, tspb200_stats *st) {
     }
     if (path == 2 && !ctx->d_mat) return fail(ctx, TSPB200_E_STATE, "matrix path selected but no resident matrix");
     if (path == 0 && !ctx->inst.fp32_ok) return fail(ctx, TSPB200_E_UNSUPPORTED, "FP32 filter path is not valid for this instance");
-    if (ctx->world > 1 && (n > (1 << 17))) return fail(ctx, TSPB200_E_UNSUPPORTED, "multi-GPU key packing supports n <= 131072");
+    const bool packable = n <= KEY_PACK_MAX_N && 2.0 * ctx->dist_bound < (double)KEY_PACK_MAX_DELTA;
+    if (ctx->world > 1 && !packable)
+        return fail(ctx, TSPB200_E_UNSUPPORTED, "multi-GPU key packing supports n <= 131072 and |delta| < 2^27");
     InstDev I = inst_for_path(ctx, path);
     BiArgs a;
     a.inst = I;
@@ -717,26 +847,47 @@ int tspb200_bi_run(tspb200_ctx *ctx, int64_t max_passes, tspb200_stats *st) {
                                 (ctx->opt_fuse_apply >= 0 ? ctx->opt_fuse_apply == 1 : false);
     a.fuse_apply = ctx->world == 1 ? (fuse_in_kernel ? 2 : 1) : 0;
     a.seed_hint = ctx->opt_seed_hint;
+    a.packed_tail = (path == 0 && packable && ctx->opt_seed_hint < 2) ? 1 : 0;
+    a.timing = ctx->opt_timing;
+    if (a.timing == 2 && !ctx->d_dbg) CK(cudaMalloc(&ctx->d_dbg, sizeof(unsigned long long) * 2 * 4096));
+    a.dbg = ctx->d_dbg;
+    {
+        // tail smoothing: auto = quarter tiles for the last half wave once a pass is at least two waves deep and the tile
+        // width allows it (sub-tile widths must stay multiples of the filter granularity 4)
+        const long long own = ((long long)ctx->ntiles - a.rank + a.world - 1) / a.world;
+        int F = ctx->opt_tail_split >= 0 ? ctx->opt_tail_split : (own >= 2ll * ctx->grid_bi ? 4 : 1);
+        while (F > 1 && (ctx->TJ % (4 * F)) != 0) F >>= 1;
+        a.split_factor = F > 1 ? F : 1;
+        a.split_tiles = ctx->opt_tail_tiles > 0 ? ctx->opt_tail_tiles : ctx->grid_bi / 2;
+    }
+    // exact tile pruning: same moves, fewer evaluated pairs (the throughput benchmarks switch it off: "prune" = 0)
+    const bool prune = path == 0 && !ctx->tabu_on && ctx->ntr > 0 && prune_wanted(ctx);
+    a.pruned = prune ? 1 : 0;
     // multi-GPU: keys travel as NVLink peer stores from the scan kernel (path 0) unless NCCL was asked for
     const bool use_xchg = ctx->world > 1 && path == 0 && ctx->xchg.enabled && ctx->opt_exchange == 0;
     a.xchg = ctx->xchg;
     a.xchg.enabled = use_xchg ? 1 : 0;
-    // programmatic dependent launch along the scan -> (decode) -> apply chain; not across a NCCL collective
+    // programmatic dependent launch along the (prune ->) scan -> apply chain; not across a NCCL collective
     const bool pdl = path == 0 && !ctx->tabu_on && ctx->opt_pdl && (ctx->world == 1 || use_xchg);
     int rc = sync_ctl(ctx);
     if (rc) return rc;
+    rc = prepare_run(ctx, false, -1);
+    if (rc) return rc;
     const long long passes0 = ctx->h_ctl->passes, moves0 = ctx->h_ctl->moves, delta0 = ctx->h_ctl->obj_delta;
+    const unsigned long long scanned0 = ctx->h_ctl->tiles_scanned;
     int exact_grid = ctx->opt_grid > 0 ? ctx->opt_grid : 4 * ctx->num_sms;
     if (exact_grid > n) exact_grid = n > 0 ? n : 1;
     // passes per host round trip: large instances run for milliseconds per pass, small ones for microseconds
     // (a pass that finds the tour already optimal returns at once, so over-launching by a batch costs microseconds, while
     // every host round trip idles the GPU — and, on several GPUs, every rank that waits for this one's next key)
-    const long long batch_cap = ctx->opt_batch > 0 ? ctx->opt_batch : (n >= 5000 ? 64 : 256);
+    const long long batch_cap = ctx->opt_batch > 0 ? ctx->opt_batch : (n >= 5000 && !prune ? 64 : 256);
     long long batch = ctx->opt_batch > 0 ? ctx->opt_batch : 8;  // grows: short runs (TSPLIB-size tours) stop after a few passes
     long long host_launches = 0;
     int status = TSPB200_LOCAL_OPTIMUM;
     // "l2_flush_bytes": every pass starts with a cold L2 and is timed by its own event pair (the flush is outside the
-    // timed intervals); nothing else changes, and there is still no host round trip between the passes of a batch
+    // timed intervals); nothing else changes, and there is still no host round trip between the passes of a batch.
+    // On several GPUs the ranks' flushes do not take the same time; an alignment barrier over the peer slots between the
+    // flush and the start event keeps that skew — an artefact of the benchmark — out of the peers' timed intervals.
     const bool flush = ctx->opt_flush_bytes > 0;
     double flush_ms = 0;
     if (flush) {
@@ -766,7 +917,12 @@ int tspb200_bi_run(tspb200_ctx *ctx, int64_t max_passes, tspb200_stats *st) {
         for (long long q = 0; q < k; ++q) {
             if (flush) {
                 CK(cudaMemsetAsync(ctx->d_flush, (int)(q & 0xff), (size_t)ctx->opt_flush_bytes, ctx->stream));
+                if (use_xchg) CK(launch_rank_align(ctx->xchg, ctx->rank, ctx->world, ctx->d_ctl, ctx->stream));
                 CK(cudaEventRecord(ctx->pass_events[2 * q], ctx->stream));
+            }
+            if (prune) {
+                CK(launch_tile_prune(a, ctx->T * ctx->R, ctx->grid_bi, pdl, ctx->stream));
+                host_launches += 2;
             }
             if (ctx->tabu_on)
                 CK(launch_bi_scan_tabu(I, ctx->tour, ctx->d_skip, ctx->tabu_iter, ctx->tabu_tenure, ctx->d_zl, ctx->d_zl_count,
@@ -782,7 +938,8 @@ int tspb200_bi_run(tspb200_ctx *ctx, int64_t max_passes, tspb200_stats *st) {
                 host_launches++;
             }
             if (!fuse_in_kernel) {
-                CK(launch_apply_move(I, ctx->tour, ctx->num_sms, (path == 0 && ctx->opt_seed_hint >= 2) ? 1 : 0, pdl, ctx->stream));
+                CK(launch_apply_move(I, ctx->tour, ctx->num_sms, (path == 0 && ctx->opt_seed_hint >= 2) ? 1 : 0, ctx->opt_timing,
+                                     pdl, ctx->stream));
                 host_launches++;
             }
             if (flush) CK(cudaEventRecord(ctx->pass_events[2 * q + 1], ctx->stream));
@@ -801,18 +958,39 @@ int tspb200_bi_run(tspb200_ctx *ctx, int64_t max_passes, tspb200_stats *st) {
         done = ctx->h_ctl->done != 0;
         if (!done && ctx->opt_time_limit_ms > 0) {
             auto el = std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - t_start).count();
-            if (el > ctx->opt_time_limit_ms) { status = TSPB200_TIME_LIMIT_EXCEEDED; break; }
+            int stop = el > ctx->opt_time_limit_ms ? 1 : 0;
+            if (ctx->world > 1) {
+                // the stop decision must be collective: a rank that left alone would leave its peers waiting for its keys
+                CK(cudaMemcpyAsync(ctx->d_stop, &stop, sizeof stop, cudaMemcpyHostToDevice, ctx->stream));
+                int nr = g_nccl.AllReduce(ctx->d_stop, ctx->d_stop, 1, NCCL_INT32, NCCL_MAX, ctx->comm, ctx->stream);
+                if (nr != 0) return fail(ctx, TSPB200_E_NCCL, "ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(nr) : "?");
+                CK(cudaMemcpyAsync(&stop, ctx->d_stop, sizeof stop, cudaMemcpyDeviceToHost, ctx->stream));
+                CK(cudaStreamSynchronize(ctx->stream));
+            }
+            if (stop) { status = TSPB200_TIME_LIMIT_EXCEEDED; break; }
         }
     }
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->h_ctl->moves != moves0) {
+        ctx->node_dirty = true;       // the node-space tables of the first-improvement search are rebuilt on demand
+        ctx->fi_cursor_stale = true;
+    }
     if (st) {
         float ms = 0;
         CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
         memset(st, 0, sizeof *st);
         st->passes = ctx->h_ctl->passes - passes0;
         st->moves = ctx->h_ctl->moves - moves0;
-        st->evals = st->passes * ((long long)n * (n - 3) / 2);
+        const long long pairs = (long long)n * (n - 3) / 2;
+        st->evals = st->passes * pairs;
+        if (prune) {
+            // pairs really evaluated (estimate: scanned tiles / this rank's tiles); the skipped ones were excluded by the bound
+            const long long own = ((long long)ctx->ntiles - a.rank + a.world - 1) / a.world;
+            st->tiles_scanned = (long long)(ctx->h_ctl->tiles_scanned - scanned0);
+            st->tiles_total = st->passes * own;
+            if (st->tiles_total > 0) st->evals = (long long)((double)st->evals * (double)st->tiles_scanned / (double)st->tiles_total);
+        }
         st->launches = host_launches;
         st->obj_delta = ctx->h_ctl->obj_delta - delta0;
         st->gpu_ms = flush ? flush_ms : ms;
@@ -837,10 +1015,16 @@ int tspb200_fi_run(tspb200_ctx *ctx, int64_t max_moves, tspb200_stats *st) {
                     swept0 = ctx->h_ctl->pairs_swept;
     // max_moves is an absolute cap on the device counter
     long long cap = max_moves >= 0 ? moves0 + max_moves : -1;
-    CK(cudaMemcpyAsync(&ctx->d_ctl->max_moves, &cap, sizeof cap, cudaMemcpyHostToDevice, ctx->stream));
+    rc = prepare_run(ctx, ctx->fi_cursor_stale, cap);
+    if (rc) return rc;
+    ctx->fi_cursor_stale = false;
     if (n < 4) {  // no non-adjacent pair exists: one empty sweep
         if (st) { memset(st, 0, sizeof *st); st->passes = 1; st->path = path; }
         return TSPB200_OK;
+    }
+    if (ctx->node_dirty) {  // best-improvement moves do not maintain the node-space tables
+        CK(launch_rebuild_node_space(ctx->tour, ctx->stream));
+        ctx->node_dirty = false;
     }
     int grid = ctx->opt_grid > 0 ? ctx->opt_grid : 2 * ctx->num_sms;
     if (grid > n - 1) grid = n - 1;
@@ -852,13 +1036,10 @@ int tspb200_fi_run(tspb200_ctx *ctx, int64_t max_moves, tspb200_stats *st) {
     bool done = false;
     if (max_moves == 0) { done = false; status = TSPB200_STOPPED_BY_CAP; }
     else {
-        // a previous capped run leaves done=1 behind: clear it when the caller asks for more
-        int zero = 0;
-        if (ctx->h_ctl->done && cap != -1 && ctx->h_ctl->moves < cap) CK(cudaMemcpyAsync(&ctx->d_ctl->done, &zero, sizeof zero, cudaMemcpyHostToDevice, ctx->stream));
         while (!done) {
             for (long long q = 0; q < batch; ++q) {
                 CK(launch_fi_search(I, ctx->tour, grid, ctx->opt_pdl != 0, ctx->stream));
-                CK(launch_apply_move(I, ctx->tour, ctx->num_sms, 0, ctx->opt_pdl != 0, ctx->stream));
+                CK(launch_apply_move(I, ctx->tour, ctx->num_sms, 0, 0, ctx->opt_pdl != 0, ctx->stream));
                 CK(launch_refresh_node_space(ctx->tour, ctx->num_sms, ctx->opt_pdl != 0, ctx->stream));
                 host_launches += 3;
             }
@@ -996,6 +1177,9 @@ static int run_batch(tspb200_ctx *ctx, int mode, int32_t *succ, double *obj, int
     if (ctx->n < 1) return fail(ctx, TSPB200_E_STATE, "no instance");
     if (mode != TSPB200_FI && mode != TSPB200_BI) return fail(ctx, TSPB200_E_ARG, "mode must be TSPB200_FI or TSPB200_BI");
     if (!succ || batch < 1) return fail(ctx, TSPB200_E_ARG, "bad batch");
+    if (!(ctx->dist_bound < 16777216.0))
+        return fail(ctx, TSPB200_E_UNSUPPORTED, "2-opt keeps edge lengths as exact integers in FP32 words: distances up to %.0f "
+                    "(>= 2^24) are not supported", ctx->dist_bound);
     CK(cudaSetDevice(ctx->device));
     const int n = ctx->n;
     const int path = select_path(ctx);
@@ -1192,42 +1376,58 @@ int tspb200_comm_init(tspb200_ctx *ctx, const void *id128, int rank, int world) 
     nccl_unique_id id;
     memcpy(&id, id128, sizeof id);
     if (ctx->comm) { g_nccl.CommDestroy(ctx->comm); ctx->comm = nullptr; }
-    int nr = g_nccl.CommInitRank(&ctx->comm, world, id, rank);
-    if (nr != 0) return fail(ctx, TSPB200_E_NCCL, "ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(nr) : "?");
-    ctx->rank = rank;
-    ctx->world = world;
-    ctx->has_tour = false;  // tile plan depends on the world size
-
-    // ---- peer-memory exchange: every rank maps every other rank's slot array (CUDA IPC -> NVLink P2P) -------------
     free_xchg(ctx);
     ctx->xchg_note.clear();
+    ctx->rank = 0;
+    ctx->world = 1;
+    ctx->has_tour = false;  // tile plan depends on the world size
+
+    // ---- everything local is allocated BEFORE the first collective: a rank must never leave a collective half-way
+    // because of a local failure (its peers would block in it); local failures are folded into the agreed `ok` flag ----
     int ok = (world <= XCHG_MAX_WORLD && g_nccl.AllGather) ? 1 : 0;
     if (!ok) ctx->xchg_note = "peer exchange needs world <= 16 and ncclAllGather";
     cudaIpcMemHandle_t mine;
     memset(&mine, 0, sizeof mine);
     char *d_h = nullptr;
     std::vector<cudaIpcMemHandle_t> all((size_t)world);
-    if (ok) {
-        CK(cudaMalloc(&ctx->d_slots, sizeof(XchgSlot) * 2 * XCHG_MAX_WORLD));
-        CK(cudaMalloc(&ctx->d_epoch, sizeof(unsigned)));
-        CK(cudaMemsetAsync(ctx->d_slots, 0, sizeof(XchgSlot) * 2 * XCHG_MAX_WORLD, ctx->stream));
-        CK(cudaMemsetAsync(ctx->d_epoch, 0, sizeof(unsigned), ctx->stream));
-        if (cudaIpcGetMemHandle(&mine, ctx->d_slots) != cudaSuccess) {
-            cudaGetLastError();
-            ok = 0;
-            ctx->xchg_note = "cudaIpcGetMemHandle failed";
-        }
+    bool local_ok = cudaMalloc(&d_h, sizeof(cudaIpcMemHandle_t) * (size_t)(world + 1)) == cudaSuccess &&
+                    cudaMalloc(&ctx->d_stop, sizeof(int)) == cudaSuccess &&
+                    cudaMalloc(&ctx->d_slots, sizeof(XchgMem)) == cudaSuccess &&
+                    cudaMalloc(&ctx->d_epoch, 2 * sizeof(unsigned)) == cudaSuccess &&
+                    cudaMemsetAsync(ctx->d_slots, 0, sizeof(XchgMem), ctx->stream) == cudaSuccess &&
+                    cudaMemsetAsync(ctx->d_epoch, 0, 2 * sizeof(unsigned), ctx->stream) == cudaSuccess;
+    if (!local_ok) {
+        cudaGetLastError();
+        cudaFree(d_h);
+        free_xchg(ctx);
+        return fail(ctx, TSPB200_E_CUDA, "cannot allocate the communicator's device buffers");
     }
-    // the handles travel through the communicator we already have; the all-gather also orders every rank's memset of
-    // its slots before any peer can write to them
-    CK(cudaMalloc(&d_h, sizeof(cudaIpcMemHandle_t) * (size_t)(world + 1)));
-    CK(cudaMemcpyAsync(d_h, &mine, sizeof mine, cudaMemcpyHostToDevice, ctx->stream));
+    if (ok && cudaIpcGetMemHandle(&mine, ctx->d_slots) != cudaSuccess) {
+        cudaGetLastError();
+        ok = 0;
+        ctx->xchg_note = "cudaIpcGetMemHandle failed";
+    }
+    auto bail = [&](int code, const char *what, int nr) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaFree(d_h);
+        free_xchg(ctx);
+        if (ctx->comm) { g_nccl.CommDestroy(ctx->comm); ctx->comm = nullptr; }
+        return fail(ctx, code, "%s failed: %s", what, nr >= 0 && g_nccl.GetErrorString ? g_nccl.GetErrorString(nr) : "CUDA error");
+    };
+    int nr = g_nccl.CommInitRank(&ctx->comm, world, id, rank);
+    if (nr != 0) return bail(TSPB200_E_NCCL, "ncclCommInitRank", nr);
+
+    // ---- peer-memory exchange: every rank maps every other rank's slot array (CUDA IPC -> NVLink P2P).  The handles
+    // travel through the communicator; the all-gather also orders every rank's memset of its slots before any peer can
+    // write to them ----
+    if (cudaMemcpyAsync(d_h, &mine, sizeof mine, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) ok = 0;
     if (g_nccl.AllGather) {
         nr = g_nccl.AllGather(d_h, d_h + sizeof(cudaIpcMemHandle_t), sizeof(cudaIpcMemHandle_t), NCCL_CHAR, ctx->comm, ctx->stream);
-        if (nr != 0) { cudaFree(d_h); return fail(ctx, TSPB200_E_NCCL, "ncclAllGather failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(nr) : "?"); }
-        CK(cudaMemcpyAsync(all.data(), d_h + sizeof(cudaIpcMemHandle_t), sizeof(cudaIpcMemHandle_t) * (size_t)world, cudaMemcpyDeviceToHost, ctx->stream));
+        if (nr != 0) return bail(TSPB200_E_NCCL, "ncclAllGather", nr);
+        if (cudaMemcpyAsync(all.data(), d_h + sizeof(cudaIpcMemHandle_t), sizeof(cudaIpcMemHandle_t) * (size_t)world,
+                            cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) ok = 0;
     }
-    CK(cudaStreamSynchronize(ctx->stream));
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) ok = 0;
     if (ok) {
         for (int r = 0; r < world && ok; ++r) {
             if (r == rank) { ctx->xchg.peer[r] = ctx->d_slots; continue; }
@@ -1239,21 +1439,24 @@ int tspb200_comm_init(tspb200_ctx *ctx, const void *id128, int rank, int world) 
                 break;
             }
             ctx->peer_mapped[r] = p;
-            ctx->xchg.peer[r] = reinterpret_cast<XchgSlot *>(p);
+            ctx->xchg.peer[r] = reinterpret_cast<XchgMem *>(p);
         }
     }
     // all ranks must agree: one failure anywhere -> everybody uses the NCCL allreduce
     int *d_ok = reinterpret_cast<int *>(d_h);
-    CK(cudaMemcpyAsync(d_ok, &ok, sizeof ok, cudaMemcpyHostToDevice, ctx->stream));
-    nr = g_nccl.AllReduce(d_ok, d_ok, 1, NCCL_INT32, NCCL_MIN, ctx->comm, ctx->stream);
-    if (nr != 0) { cudaFree(d_h); return fail(ctx, TSPB200_E_NCCL, "ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(nr) : "?"); }
     int all_ok = 0;
-    CK(cudaMemcpyAsync(&all_ok, d_ok, sizeof all_ok, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    cudaMemcpyAsync(d_ok, &ok, sizeof ok, cudaMemcpyHostToDevice, ctx->stream);
+    nr = g_nccl.AllReduce(d_ok, d_ok, 1, NCCL_INT32, NCCL_MIN, ctx->comm, ctx->stream);
+    if (nr != 0) return bail(TSPB200_E_NCCL, "ncclAllReduce", nr);
+    cudaMemcpyAsync(&all_ok, d_ok, sizeof all_ok, cudaMemcpyDeviceToHost, ctx->stream);
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return bail(TSPB200_E_CUDA, "cudaStreamSynchronize", -1);
     cudaFree(d_h);
     ctx->xchg.epoch = ctx->d_epoch;
+    ctx->xchg.align_epoch = ctx->d_epoch + 1;
     ctx->xchg.enabled = all_ok ? 1 : 0;
     if (!all_ok && ctx->xchg_note.empty()) ctx->xchg_note = "a peer rank could not map the exchange slots";
+    ctx->rank = rank;   // only now: a failed init leaves the context single-GPU
+    ctx->world = world;
     return TSPB200_OK;
 }
 

@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(BI_THREADS, (R >= 16 ? (BI_THREADS == 256 ? 1 
     __shared__ int s_hint;
     __shared__ int s_last;
     __shared__ MoveKey s_keys[BI_THREADS / 32];
-    __shared__ int s_ap[2];
+    __shared__ int s_ap[3];
 
     Ctl *ctl = A.tour.ctl;
     const int tid = threadIdx.x;
@@ -121,7 +121,6 @@ __global__ void __launch_bounds__(BI_THREADS, (R >= 16 ? (BI_THREADS == 256 ? 1 
     const float4 *rec = A.tour.rec;
     float4 *scols0 = reinterpret_cast<float4 *>(smem_raw);
     float4 *scols1 = scols0 + (TJ + 2);
-    const unsigned col_bytes = (unsigned)(TJ + 1) * 16u;
 
     // tile tables -> shared memory (one coalesced L2 round trip instead of a dependent chain per binary-search step)
     int *s_rs = reinterpret_cast<int *>(scols1 + (TJ + 2));  // [ntr+1] prefix sums of tiles per tile-row
@@ -141,6 +140,11 @@ __global__ void __launch_bounds__(BI_THREADS, (R >= 16 ? (BI_THREADS == 256 ? 1 
     if (done) {  // local optimum already reached: later launches of the same batch return at once
         if (blockIdx.x == 0 && tid == 0) ctl->ap_valid = 0;
         return;
+    }
+    if (A.timing && tid == 0) {
+        const unsigned long long t = globaltimer_ns();
+        atomicMin(&ctl->tm_scan_first, t);
+        if (A.timing == 2) A.dbg[2 * blockIdx.x] = t;
     }
     __syncthreads();
 
@@ -164,7 +168,7 @@ __global__ void __launch_bounds__(BI_THREADS, (R >= 16 ? (BI_THREADS == 256 ? 1 
     // the tile ids r, r + world, ...; every tile costs the same — masked and padded pairs are computed too), so the blocks
     // run dry within one tile of each other whatever slows some of them down (exact-path calls, the far die's L2
     // latency).  Static dealing left the SMs idle ~10 % of a pass once a pass is only ~5 tiles deep (8 ranks).
-    __shared__ int s_tile[2][3];  // [stage] = {P0, Q0, valid}, written by thread 0 one tile ahead
+    __shared__ int s_tile[2][4];  // [stage] = {P0, Q0, valid, columns}, written by thread 0 one tile ahead
 
     // tile id -> (tile row I, tile column J)
     auto decode = [&](int t, int &P0, int &Q0) {
@@ -179,25 +183,71 @@ __global__ void __launch_bounds__(BI_THREADS, (R >= 16 ? (BI_THREADS == 256 ? 1 
     // thread 0: take the next tile, start the bulk copy of its column records, publish it for stage b.  A block's first
     // tile is its block index (no atomic on the critical path of the prologue); the following ones are drawn from the
     // counter, which therefore counts from gridDim.x.  tiles_rank <= gridDim.x (one wave, n <~ 10^4) never touches it.
-    const long long tiles_rank = ((long long)A.ntiles - A.rank + A.world - 1) / A.world;
+    // Exact tile pruning (A.pruned): the tiles come from this rank's live list (tile_filter_kernel); a live tile whose lower
+    // bound meanwhile exceeds the best exact delta found in this pass is dropped at the draw (it cannot hold the argmin
+    // nor a tie: ties need delta == best).
+    // Tail smoothing (A.split_factor F > 1): this rank's last A.split_tiles tiles are handed out as F sub-tiles of TJ/F
+    // columns each, so that the blocks run dry within a sub-tile of each other instead of a whole tile (at 8 ranks a pass
+    // is only ~8 tiles deep and the last-tile spread was ~15 % of it).  Draw index kl < whole: tile kl, all TJ columns;
+    // otherwise k2 = kl - whole: tile whole + k2 / F, columns [(k2 % F) * TJ / F, +TJ / F).
+    const long long tiles_own = A.pruned ? (long long)__ldcg(&ctl->live_count)
+                                         : ((long long)A.ntiles - A.rank + A.world - 1) / A.world;
+    const int F = (A.pruned || A.split_factor < 2) ? 1 : A.split_factor;
+    const long long split = F > 1 ? (A.split_tiles < tiles_own ? (long long)A.split_tiles : tiles_own) : 0;
+    const long long whole = tiles_own - split;
+    const long long tiles_rank = whole + split * F;  // number of draws
+    unsigned scanned = 0;    // thread 0: tiles this block really scanned (statistics of the pruned mode)
+    long long next_kl = -1;  // thread 0: draw index fetched ahead of its use (the atomic's latency stays off the critical path)
+    auto fetch = [&]() {
+        next_kl = tiles_rank > (long long)gridDim.x ? (long long)gridDim.x + (long long)atomicAdd(&ctl->tile_next, 1u) : tiles_rank;
+    };
     auto draw = [&](int b, bool first) {
-        long long kl = first ? (long long)blockIdx.x : tiles_rank;
-        if (!first && tiles_rank > (long long)gridDim.x) kl = (long long)gridDim.x + (long long)atomicAdd(&ctl->tile_next, 1u);
-        int P = 0, Q = 0, valid = 0;
-        if (kl < tiles_rank) {
-            decode((int)((long long)A.rank + (long long)A.world * kl), P, Q);
-            valid = 1;
-            mbar_expect_tx(&bars[b], col_bytes);
-            tma_load_1d(b ? scols1 : scols0, rec + Q, col_bytes, &bars[b]);
+        int P = 0, Q = 0, valid = 0, nc = TJ;
+        for (;;) {
+            long long kl = first ? (long long)blockIdx.x : next_kl;
+            if (kl >= tiles_rank) break;
+            long long tl = kl;
+            int sub = 0;
+            if (kl >= whole) {
+                const long long k2 = kl - whole;
+                tl = whole + k2 / F;
+                sub = (int)(k2 % F);
+                nc = TJ / F;
+            }
+            int t;
+            if (A.pruned) {
+                if (__ldg(&A.tour.live_lb[tl]) > (float)(*((volatile int *)&s_hint))) {
+                    first = false;
+                    fetch();
+                    continue;
+                }
+                t = __ldg(&A.tour.live[tl]);
+            } else {
+                t = (int)((long long)A.rank + (long long)A.world * tl);
+            }
+            decode(t, P, Q);
+            Q += sub * nc;
+            valid = Q <= n - 1 ? 1 : 0;  // a sub-tile of the last tile column may lie entirely behind the tour
+            if (!valid) {
+                first = false;
+                fetch();
+                continue;
+            }
+            scanned += 1;
+            mbar_expect_tx(&bars[b], (unsigned)(nc + 1) * 16u);
+            tma_load_1d(b ? scols1 : scols0, rec + Q, (unsigned)(nc + 1) * 16u, &bars[b]);
+            break;
         }
         s_tile[b][0] = P;
         s_tile[b][1] = Q;
         s_tile[b][2] = valid;
+        s_tile[b][3] = nc;
+        if (valid) fetch();  // for the draw after this one
     };
 
     if (tid == 0) draw(0, true);
     __syncthreads();
-    int P0 = s_tile[0][0], Q0 = s_tile[0][1];
+    int P0 = s_tile[0][0], Q0 = s_tile[0][1], NC = s_tile[0][3];
     bool have = s_tile[0][2] != 0;
 
     for (int it = 0; have; ++it) {
@@ -232,7 +282,16 @@ __global__ void __launch_bounds__(BI_THREADS, (R >= 16 ? (BI_THREADS == 256 ? 1 
 
         // pairs with q < p+2 exist in this tile?  (mask them; they are mirrored / adjacent pairs)
         const bool diag = (Q0 < P0 + TI + 1);
-        float4 c0 = sc[0];
+        // In a diagonal tile a warp starts at the first column that holds a legal pair for its FIRST row (q >= p + 2), rounded
+        // down to the filter granularity: the columns before are masked for all its rows.  Diagonal tiles thus cost about
+        // half a regular tile instead of ~1.3 of one — they were the stragglers of a one-wave pass (n ~ 10^4).
+        int jbeg = 0;
+        if (diag) {
+            jbeg = P0 + (tid & ~31) * R + 2 - Q0;
+            jbeg = jbeg < 0 ? 0 : (jbeg & ~(BI_CB - 1));
+            if (jbeg > NC) jbeg = NC;
+        }
+        float4 c0 = sc[jbeg];
         f32x2 U2[R / 2];
         {
             float D0[R + 1];
@@ -264,7 +323,7 @@ __global__ void __launch_bounds__(BI_THREADS, (R >= 16 ? (BI_THREADS == 256 ? 1 
 
 // BI_CB columns, then ONE filter check per warp (ballot); hits are resolved one lane at a time by the whole warp
 #define BI_BLOCK(DIAG)                                                                                 \
-    for (int jj = 0; jj < TJ; jj += BI_CB) {                                                           \
+    for (int jj = jbeg; jj < NC; jj += BI_CB) {                                                        \
         float M = TSPB_BIG;                                                                            \
         _Pragma("unroll") for (int c = 0; c < BI_CB; ++c) BI_COL(DIAG, jj + c)                         \
         unsigned hits = __ballot_sync(0xffffffffu, M <= thr);                                          \
@@ -297,7 +356,7 @@ __global__ void __launch_bounds__(BI_THREADS, (R >= 16 ? (BI_THREADS == 256 ? 1 
     }
 
         const int qrel0 = Q0 - p0;  // q - p0 at jj = 0
-        float4 cnext = sc[1];
+        float4 cnext = sc[jbeg + 1];
         if (!diag) {
             BI_BLOCK(false)
         } else {
@@ -308,18 +367,17 @@ __global__ void __launch_bounds__(BI_THREADS, (R >= 16 ? (BI_THREADS == 256 ? 1 
 #undef UU
 
         __syncthreads();  // every thread is done with this stage before the next prefetch overwrites it
-        if (tid == 0) {
-            // exchange the best exact delta with the other blocks (only ever tightens the filter)
-            int h = s_hint;
-            int g = atomicMin(&ctl->hint, h);
-            if (g < h) s_hint = g;
-        }
+        // publish the best exact delta to the other blocks (fire and forget; theirs arrive through pend_hint above)
+        if (tid == 0 && s_hint < 0) atomicMin(&ctl->hint, s_hint);
         P0 = s_tile[buf ^ 1][0];
         Q0 = s_tile[buf ^ 1][1];
         have = s_tile[buf ^ 1][2] != 0;
+        NC = s_tile[buf ^ 1][3];
     }
 
     // ---- block argmin -> grid argmin ("last block done") -------------------------------------------
+    // packed_tail: every block folds its key into ctl->pass_min with ONE 64-bit atomicMin, so the last block only has to
+    // read that word (instead of reducing gridDim.x keys: ~3 us of every pass at 1184 blocks).
     best = key_warp_min(best);
     if ((tid & 31) == 0) s_keys[tid >> 5] = best;
     __syncthreads();
@@ -328,6 +386,13 @@ __global__ void __launch_bounds__(BI_THREADS, (R >= 16 ? (BI_THREADS == 256 ? 1 
         k = key_warp_min(k);
         if (tid == 0) {
             A.tour.block_best[blockIdx.x] = k;
+            if (A.packed_tail && k.delta < 0) atomicMin(&ctl->pass_min, key_pack(k.delta, k.i, k.j));
+            if (A.pruned && scanned) atomicAdd(&ctl->tiles_scanned, (unsigned long long)scanned);
+            if (A.timing) {
+                const unsigned long long t = globaltimer_ns();
+                atomicMin(&ctl->tm_blk_end_min, t);
+                if (A.timing == 2) A.dbg[2 * blockIdx.x + 1] = t;
+            }
             __threadfence();
             unsigned tk = atomicAdd(&ctl->ticket, 1u);
             s_last = (tk == gridDim.x - 1);
@@ -336,29 +401,59 @@ __global__ void __launch_bounds__(BI_THREADS, (R >= 16 ? (BI_THREADS == 256 ? 1 
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-
-    MoveKey mine = key_none();
-    for (int b = tid; b < (int)gridDim.x; b += BI_THREADS) {
-        MoveKey o = key_load_cg(&A.tour.block_best[b]);
-        if (key_less(o, mine)) mine = o;
+    unsigned long long t_ticket = 0;
+    if (A.timing && tid == 0) {
+        t_ticket = globaltimer_ns();
+        const unsigned long long t_first = ctl->tm_scan_first, ap0 = ctl->tm_apply_first, ap1 = ctl->tm_apply_end;
+        ctl->tm_acc[TM_SCAN] += t_ticket - t_first;
+        ctl->tm_acc[TM_SPREAD] += t_ticket - ctl->tm_blk_end_min;
+        if (ap1 != 0 && ap0 != ~0ull) {  // the previous pass applied a move
+            ctl->tm_acc[TM_GAP] += t_first > ap1 ? t_first - ap1 : 0;
+            ctl->tm_acc[TM_APPLY] += ap1 - ap0;
+            ctl->tm_acc[TM_APPLY_GAP] += ap0 > ctl->tm_publish ? ap0 - ctl->tm_publish : 0;
+        }
+        ctl->tm_acc[TM_COUNT] += 1;
+        ctl->tm_scan_first = ~0ull;
+        ctl->tm_blk_end_min = ~0ull;
+        ctl->tm_apply_first = ~0ull;
+        ctl->tm_apply_end = 0;
     }
-    // CTL_NCAND rounds of "block-wide minimum, then retire it": round 0 is the winner of the pass, the rest are
-    // runner-ups kept as seeds for the next pass's filter (seed_hint_from_candidates)
+
     MoveKey k = key_none();
-    const int rounds = (A.seed_hint >= 2) ? CTL_NCAND : 1;
+    int rounds = 1;
+    if (A.packed_tail) {
+        if (tid == 0) {
+            const unsigned long long pk = __ldcg(&ctl->pass_min);
+            ctl->pass_min = KEY_PACK_NONE;
+            if (pk < KEY_PACK_NONE) {
+                key_unpack(pk, &k.delta, &k.i, &k.j);
+                k.pad = 0;
+            }
+            ctl->cand[0] = k;
+        }
+    } else {
+        MoveKey mine = key_none();
+        for (int b = tid; b < (int)gridDim.x; b += BI_THREADS) {
+            MoveKey o = key_load_cg(&A.tour.block_best[b]);
+            if (key_less(o, mine)) mine = o;
+        }
+        // CTL_NCAND rounds of "block-wide minimum, then retire it": round 0 is the winner of the pass, the rest are
+        // runner-ups kept as seeds for the next pass's filter (seed_hint_from_candidates)
+        rounds = (A.seed_hint >= 2) ? CTL_NCAND : 1;
 #pragma unroll 1
-    for (int round = 0; round < rounds; ++round) {
-        MoveKey m = key_warp_min(mine);
-        if ((tid & 31) == 0) s_keys[tid >> 5] = m;
-        __syncthreads();
-        m = s_keys[0];
+        for (int round = 0; round < rounds; ++round) {
+            MoveKey m = key_warp_min(mine);
+            if ((tid & 31) == 0) s_keys[tid >> 5] = m;
+            __syncthreads();
+            m = s_keys[0];
 #pragma unroll
-        for (int w = 1; w < BI_THREADS / 32; ++w)
-            if (key_less(s_keys[w], m)) m = s_keys[w];
-        __syncthreads();
-        if (round == 0) k = m;
-        if (tid == 0) ctl->cand[round] = m;
-        if (m.delta < 0 && mine.i == m.i && mine.j == m.j) mine = key_none();
+            for (int w = 1; w < BI_THREADS / 32; ++w)
+                if (key_less(s_keys[w], m)) m = s_keys[w];
+            __syncthreads();
+            if (round == 0) k = m;
+            if (tid == 0) ctl->cand[round] = m;
+            if (m.delta < 0 && mine.i == m.i && mine.j == m.j) mine = key_none();
+        }
     }
 
     if (tid == 0) {
@@ -366,72 +461,67 @@ __global__ void __launch_bounds__(BI_THREADS, (R >= 16 ? (BI_THREADS == 256 ? 1 
         ctl->last = k;
         ctl->ticket = 0;
         ctl->tile_next = 0;
+        ctl->live_count = 0;
         ctl->hint = 0;
         ctl->launches += 1;
         if (!A.fuse_apply) {
-            // multi-GPU: publish this rank's key for the exchange; the decode kernel continues
-            ctl->packed = (k.delta < 0) ? key_pack(k.delta, k.i, k.j) : key_pack(0, 0x1ffff, 0x1ffff);
-            if (A.xchg.enabled) {
-                const unsigned e = *A.xchg.epoch + 1u;
-                *A.xchg.epoch = e;
-                s_ap[0] = (int)e;
-            }
+            // multi-GPU: this rank's key for the exchange (peer memory below, or NCCL + the decode kernel)
+            ctl->packed = (k.delta < 0) ? key_pack(k.delta, k.i, k.j) : KEY_PACK_NONE;
         } else {
             ctl->passes += 1;
             publish_move(A.tour, k.i, k.j, k.delta);
-            if (k.delta >= 0) ctl->done = 1;  // reference src/tabusearch.c:158: mindelta >= 0 -> stop
+            if (k.delta >= 0) { ctl->done = 1; ctl->done_reason = DONE_OPTIMUM; }  // reference src/tabusearch.c:158: mindelta >= 0 -> stop
             s_ap[0] = ctl->ap_pa;
             s_ap[1] = ctl->ap_pb;
+            s_ap[2] = k.delta < 0;
+            if (A.timing) {
+                const unsigned long long now = globaltimer_ns();
+                ctl->tm_publish = now;
+                ctl->tm_acc[TM_TAIL] += now - t_ticket;
+            }
         }
     }
-    // Multi-GPU exchange over peer memory, fused into this kernel's tail: thread r stores this rank's key, then the epoch,
-    // into rank r's slot array (NVLink peer stores), then polls this rank's LOCAL slot r until rank r's key of the same
-    // epoch has arrived; the block takes the minimum — every rank gets the same winner — and publishes the move for its own
-    // replica of the tour.  No collective launch and no tour data on the wire.
+    // Multi-GPU exchange over peer memory, fused into this kernel's tail (xchg_min): thread r stores this rank's key word
+    // into rank r's slot array (NVLink peer store), then polls this rank's LOCAL slot r until rank r's word of the same
+    // epoch has arrived; the block takes the minimum — every rank gets the same winner — and publishes the move for its
+    // own replica of the tour.  No collective launch and no tour data on the wire.
     if (!A.fuse_apply && A.xchg.enabled) {
         __shared__ unsigned long long s_xkey[XCHG_MAX_WORLD];
-        __syncthreads();
-        if (tid < A.world) {
-            const unsigned e = (unsigned)s_ap[0];
-            XchgSlot *dst = A.xchg.peer[tid] + (e & 1u) * XCHG_MAX_WORLD + A.rank;
-            unsigned long long key = *((volatile unsigned long long *)&ctl->packed);
-            asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(&dst->key), "l"(key) : "memory");
-            __threadfence_system();
-            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(&dst->epoch), "r"(e) : "memory");
-            const XchgSlot *src = A.xchg.peer[A.rank] + (e & 1u) * XCHG_MAX_WORLD + tid;
-            const long long t0 = clock64();
-            for (;;) {
-                unsigned got;
-                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(got) : "l"(&src->epoch) : "memory");
-                if (got == e) break;
-                if (clock64() - t0 > 20000000000ll) {  // ~10 s: a peer died; fail loudly instead of hanging the GPU
-                    ctl->error = 2;
-                    break;
-                }
-            }
-            asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(key) : "l"(&src->key) : "memory");
-            s_xkey[tid] = key;
+        __shared__ unsigned long long s_mine;
+        __shared__ int s_err;
+        if (tid == 0) {
+            s_mine = ctl->packed;
+            s_err = 0;
         }
         __syncthreads();
+        unsigned long long wait_ns = 0;
+        const unsigned long long win = xchg_min(A.xchg, A.rank, A.world, s_mine, s_xkey, &s_err, A.timing ? &wait_ns : nullptr);
         if (tid == 0) {
-            unsigned long long win = s_xkey[0];
-            for (int r = 1; r < A.world; ++r) win = s_xkey[r] < win ? s_xkey[r] : win;
             int delta, i, j;
             key_unpack(win, &delta, &i, &j);
-            if (ctl->error) {
+            if (s_err) {
+                ctl->error = 2;
                 ctl->done = 1;
+                ctl->done_reason = DONE_OPTIMUM;
                 ctl->ap_valid = 0;
             } else {
                 ctl->passes += 1;
                 publish_move(A.tour, i, j, delta);
-                if (delta >= 0) ctl->done = 1;
+                if (delta >= 0) { ctl->done = 1; ctl->done_reason = DONE_OPTIMUM; }
+            }
+            if (A.timing) {
+                const unsigned long long now = globaltimer_ns();
+                ctl->tm_publish = now;
+                ctl->tm_acc[TM_TAIL] += now - t_ticket;
+                ctl->tm_acc[TM_XWAIT] += wait_ns;
             }
         }
     }
     // fuse_apply == 2: this (last) block also applies the move, saving the apply launch — every other block has
     // finished reading rec[] before it took its ticket.  Used for mid-size tours where a launch costs more than the swap.
-    if (A.fuse_apply == 2 && k.delta < 0) {
-        __syncthreads();
+    if (A.fuse_apply == 2) {
+        __syncthreads();  // s_ap[] (thread 0 knows the winner; in packed_tail mode nobody else does)
+        if (!s_ap[2]) return;
         apply_swap_range(A.inst, A.tour, s_ap[0], s_ap[1], tid, BI_THREADS);
         if (tid == 0) ctl->ap_valid = 0;
         __threadfence();
@@ -449,17 +539,22 @@ __global__ void bi_decode_packed_kernel(const TourDev tour) {
     key_unpack(ctl->packed, &delta, &i, &j);
     ctl->passes += 1;
     publish_move(tour, i, j, delta);
-    if (delta >= 0) ctl->done = 1;
+    if (delta >= 0) { ctl->done = 1; ctl->done_reason = DONE_OPTIMUM; }
 }
 
 // Grid-wide application of the published move (see apply_swap_range).
-__global__ void __launch_bounds__(256) apply_move_kernel(const InstDev inst, const TourDev tour, int seed) {
+__global__ void __launch_bounds__(256) apply_move_kernel(const InstDev inst, const TourDev tour, int seed, int timing) {
     __shared__ int s_last;
     Ctl *ctl = tour.ctl;
     pdl_launch_dependents();
     pdl_wait();
     if (!ctl->ap_valid) return;
+    if (timing && threadIdx.x == 0) atomicMin(&ctl->tm_apply_first, globaltimer_ns());
     apply_swap_range(inst, tour, ctl->ap_pa, ctl->ap_pb, blockIdx.x * 256 + threadIdx.x, gridDim.x * 256);
+    if (timing) {
+        __syncthreads();
+        if (threadIdx.x == 0) atomicMax(&ctl->tm_apply_end, globaltimer_ns());
+    }
     if (!seed) return;
     // last block done: seed the next pass's filter from the runner-up moves (BI only)
     __threadfence();
@@ -481,6 +576,155 @@ __global__ void __launch_bounds__(256) refresh_node_space_kernel(const TourDev t
     pdl_wait();
     if (!ctl->ap_valid) return;
     refresh_node_space(tour, ctl->ap_pa, ctl->ap_pb, blockIdx.x * 256 + threadIdx.x, gridDim.x * 256);
+}
+
+// ---- exact tile pruning ---------------------------------------------------------------------------
+// For a tile (tile-row I, tile-column J) every pair it holds satisfies
+//     delta_exact >= 2 * scale * bd(I, J) - 1 - maxds(I) - maxds(J)
+// where bd is the distance between the bounding boxes of the positions of tile-row I (TI positions + the successor of
+// the last one) and of tile-column J (TJ positions + successor), maxds the largest edge length ds among them, scale = 1
+// (EUC_2D / CEIL_2D; an integer distance is never more than 1/2 below the real one) or 1/sqrt(10) (ATT).  A tile whose bound
+// exceeds `hint` — the exact delta of some legal move, i.e. an upper bound of the pass minimum — can hold neither the
+// argmin nor a tie (a tie needs delta == minimum <= hint), so skipping it cannot change the selected move: the move log
+// stays the reference's bit for bit, only the number of evaluated pairs drops.  The bound is evaluated in FP32 from the
+// FP32 records; W (>= 2 + the FP32 / coordinate-rounding error of a distance, see set_instance) plus 1 is subtracted,
+// far more than the roundings of the few operations below can add up to.
+__global__ void __launch_bounds__(64) tile_boxes_kernel(const InstDev inst, const TourDev tour, int TI, int TJ, int ntr, int ncb,
+                                                        int nseed) {
+    __shared__ float s_r[2][5];
+    Ctl *ctl = tour.ctl;
+    pdl_launch_dependents();
+    pdl_wait();
+    if (*((volatile int *)&ctl->done)) return;
+    const int n = tour.n;
+    const int tid = threadIdx.x;
+    const int b = blockIdx.x;
+    if (b >= ntr + ncb) {
+        // every block winner of the previous pass that is still a legal move bounds this pass's minimum
+        const int c = (b - ntr - ncb) * 64 + tid;
+        if (c < nseed) {
+            const long long d = legal_move_delta_cg(inst, tour, key_load_cg(&tour.block_best[c]));
+            if (d < 0) atomicMin(&ctl->hint, (int)d);
+        }
+        return;
+    }
+    const bool is_row = b < ntr;
+    const int start = is_row ? b * TI : (b - ntr) * TJ;
+    const int len = is_row ? TI : TJ;
+    const int end = min(start + len, n);  // inclusive: the successor of the last position (position n mirrors position 0)
+    float xmin = TSPB_BIG, ymin = TSPB_BIG, xmax = -TSPB_BIG, ymax = -TSPB_BIG, mds = -TSPB_BIG;
+    for (int p = start + tid; p <= end; p += 64) {
+        const float4 r = __ldcg(&tour.rec[p]);
+        xmin = fminf(xmin, r.x); xmax = fmaxf(xmax, r.x);
+        ymin = fminf(ymin, r.y); ymax = fmaxf(ymax, r.y);
+        if (p < start + len && p < n) mds = fmaxf(mds, r.z);
+    }
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) {
+        xmin = fminf(xmin, __shfl_xor_sync(0xffffffffu, xmin, m));
+        ymin = fminf(ymin, __shfl_xor_sync(0xffffffffu, ymin, m));
+        xmax = fmaxf(xmax, __shfl_xor_sync(0xffffffffu, xmax, m));
+        ymax = fmaxf(ymax, __shfl_xor_sync(0xffffffffu, ymax, m));
+        mds = fmaxf(mds, __shfl_xor_sync(0xffffffffu, mds, m));
+    }
+    if ((tid & 31) == 0) {
+        float *o = s_r[tid >> 5];
+        o[0] = xmin; o[1] = ymin; o[2] = xmax; o[3] = ymax; o[4] = mds;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const float4 box = make_float4(fminf(s_r[0][0], s_r[1][0]), fminf(s_r[0][1], s_r[1][1]), fmaxf(s_r[0][2], s_r[1][2]),
+                                       fmaxf(s_r[0][3], s_r[1][3]));
+        const float m = fmaxf(s_r[0][4], s_r[1][4]);
+        if (is_row) { tour.rowbox[b] = box; tour.rowmaxds[b] = m; }
+        else { tour.colbox[b - ntr] = box; tour.colmaxds[b - ntr] = m; }
+    }
+}
+
+// One thread per tile of this rank (tile ids rank, rank + world, ...): live tiles are appended to tour.live / live_lb.
+__global__ void __launch_bounds__(256) tile_filter_kernel(const BiArgs A) {
+    Ctl *ctl = A.tour.ctl;
+    pdl_launch_dependents();
+    pdl_wait();
+    if (*((volatile int *)&ctl->done)) return;
+    const int I = blockIdx.y;
+    const int rs = A.tile_row_start[I], cnt = A.tile_row_start[I + 1] - rs, j0 = A.tile_row_j0[I];
+    const float hint = (float)__ldcg(&ctl->hint);
+    const float4 rb = __ldcg(&A.tour.rowbox[I]);
+    const float rmax = __ldcg(&A.tour.rowmaxds[I]);
+    const float scale = (A.inst.metric == M_ATT) ? 0.31622773f : 0.99999905f;  // just below 1/sqrt(10) and 1
+    const int lane = threadIdx.x & 31;
+    const int cnt32 = (cnt + 31) & ~31;
+    for (int c = blockIdx.x * 256 + threadIdx.x; c < cnt32; c += gridDim.x * 256) {
+        bool live = false;
+        float lb = 0.f;
+        if (c < cnt && (rs + c) % A.world == A.rank) {
+            const int J = j0 + c;
+            const float4 cb = __ldcg(&A.tour.colbox[J]);
+            const float dx = fmaxf(0.f, fmaxf(rb.x - cb.z, cb.x - rb.z));
+            const float dy = fmaxf(0.f, fmaxf(rb.y - cb.w, cb.y - rb.w));
+            const float bd = sqrtf(fmaf(dy, dy, dx * dx)) * scale;
+            lb = 2.0f * bd - rmax - __ldcg(&A.tour.colmaxds[J]) - A.inst.W - 1.0f;
+            live = !(lb > hint);
+        }
+        const unsigned mask = __ballot_sync(0xffffffffu, live);
+        if (mask) {
+            unsigned base = 0;
+            if (lane == __ffs(mask) - 1) base = atomicAdd(&ctl->live_count, (unsigned)__popc(mask));
+            base = __shfl_sync(0xffffffffu, base, __ffs(mask) - 1);
+            if (live) {
+                const unsigned idx = base + __popc(mask & ((1u << lane) - 1u));
+                A.tour.live[idx] = rs + c;
+                A.tour.live_lb[idx] = lb;
+            }
+        }
+    }
+}
+
+cudaError_t launch_tile_prune(const BiArgs &a, int TI, int grid_bi, bool pdl, cudaStream_t st) {
+    const int ncb = (a.tour.n - 1) / a.TJ + 1;
+    const int nseed = grid_bi;
+    const int gb = a.ntr + ncb + (nseed + 63) / 64;
+    cudaError_t e = launch_maybe_pdl(tile_boxes_kernel, dim3(gb), dim3(64), 0, st, pdl, a.inst, a.tour, TI, a.TJ, a.ntr, ncb, nseed);
+    if (e != cudaSuccess) return e;
+    int maxcnt = 1;
+    if (a.ntr > 0) maxcnt = (a.tour.n - 1) / a.TJ + 1;
+    dim3 gf((unsigned)((maxcnt + 255) / 256), (unsigned)(a.ntr > 0 ? a.ntr : 1));
+    if (a.ntr == 0) return cudaSuccess;
+    return launch_maybe_pdl(tile_filter_kernel, gf, dim3(256), 0, st, pdl, a);
+}
+
+// ---- cross-rank alignment barrier (benchmarks): every rank bumps its counter in every peer's XchgMem and waits until all
+// peers' counters reached the same value.  Launched between the L2 flush and the start event of a timed pass, so that the
+// ranks enter the pass together whatever their flushes took.
+__global__ void rank_align_kernel(const XchgDev X, int rank, int world, Ctl *ctl) {
+    __shared__ unsigned s_e;
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        s_e = *X.align_epoch + 1u;
+        *X.align_epoch = s_e;
+    }
+    __syncthreads();
+    if (tid < world) {
+        const unsigned long long e = s_e;
+        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(&X.peer[tid]->align[rank]), "l"(e) : "memory");
+        const unsigned long long *src = &X.peer[rank]->align[tid];
+        const long long t0 = clock64();
+        for (;;) {
+            unsigned long long got;
+            asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(got) : "l"(src) : "memory");
+            if (got >= e) break;
+            if (clock64() - t0 > 20000000000ll) {
+                ctl->error = 2;
+                break;
+            }
+        }
+    }
+}
+
+cudaError_t launch_rank_align(const XchgDev &x, int rank, int world, Ctl *ctl, cudaStream_t st) {
+    rank_align_kernel<<<1, 32, 0, st>>>(x, rank, world, ctl);
+    return cudaGetLastError();
 }
 
 // ---- generic exact pass (any metric, incl. GEO / matrix lookup / oversized coordinates) ------------
@@ -593,11 +837,11 @@ __global__ void __launch_bounds__(256) bi_scan_exact_kernel(const InstDev inst, 
         ctl->ticket = 0;
         ctl->launches += 1;
         if (!fuse_apply) {
-            ctl->packed = (k.delta < 0) ? key_pack(k.delta, k.i, k.j) : key_pack(0, 0x1ffff, 0x1ffff);
+            ctl->packed = (k.delta < 0) ? key_pack(k.delta, k.i, k.j) : KEY_PACK_NONE;
         } else {
             ctl->passes += 1;
             publish_move(tour, k.i, k.j, k.delta);
-            if (k.delta >= 0) ctl->done = 1;
+            if (k.delta >= 0) { ctl->done = 1; ctl->done_reason = DONE_OPTIMUM; }
         }
     }
 }
@@ -687,24 +931,12 @@ cudaError_t launch_bi_decode_packed(const TourDev &tour, cudaStream_t st) {
 }
 
 // grid sized for one swap per thread (at most n/2 swaps), capped at 4 blocks per SM
-cudaError_t launch_apply_move(const InstDev &inst, const TourDev &tour, int num_sms, int seed, bool pdl, cudaStream_t st) {
+cudaError_t launch_apply_move(const InstDev &inst, const TourDev &tour, int num_sms, int seed, int timing, bool pdl,
+                              cudaStream_t st) {
     int grid = (tour.n / 2 + 255) / 256;
     if (grid < 1) grid = 1;
     if (grid > 4 * num_sms) grid = 4 * num_sms;
-    if (!pdl) {
-        apply_move_kernel<<<grid, 256, 0, st>>>(inst, tour, seed);
-        return cudaGetLastError();
-    }
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(256);
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, apply_move_kernel, inst, tour, seed);
+    return launch_maybe_pdl(apply_move_kernel, dim3(grid), dim3(256), 0, st, pdl, inst, tour, seed, timing);
 }
 
 cudaError_t launch_refresh_node_space(const TourDev &tour, int num_sms, bool pdl, cudaStream_t st) {

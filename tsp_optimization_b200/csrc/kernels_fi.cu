@@ -183,12 +183,18 @@ __global__ void __launch_bounds__(FI_THREADS) fi_search_kernel(const InstDev I, 
         ctl->launches += 1;
         if (sweep_end) {
             ctl->passes += 1;
-            if (ctl->sweep_moves == 0) ctl->done = 1;  // reference heuristics.c:492: the sweep brought no gain
+            if (ctl->sweep_moves == 0) {  // reference heuristics.c:492: the sweep brought no gain
+                ctl->done = 1;
+                ctl->done_reason = DONE_OPTIMUM;
+            }
             ctl->sweep_moves = 0;
             ci = 0;
             cj = 1;
         }
-        if (ctl->max_moves >= 0 && ctl->moves >= ctl->max_moves) ctl->done = 1;
+        if (ctl->max_moves >= 0 && ctl->moves >= ctl->max_moves && !ctl->done) {  // a capped run may be continued later
+            ctl->done = 1;
+            ctl->done_reason = DONE_CAP;
+        }
         ctl->cur_i = ci;
         ctl->cur_j = cj;
         ctl->fi_found = FI_NONE;

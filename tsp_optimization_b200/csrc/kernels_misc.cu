@@ -233,6 +233,26 @@ __global__ void export_state_kernel(const TourDev T, int *succ, unsigned long lo
     if ((threadIdx.x & 31) == 0 && local) atomicAdd(cost, local);
 }
 
+// Node-space tables rebuilt from the position-space records (after best-improvement moves, which only maintain rec/pos).
+__global__ void rebuild_node_space_kernel(const TourDev T) {
+    const int n = T.n;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+        const float4 rp = T.rec[p];
+        const float4 rn = T.rec[p + 1];  // rec[n] mirrors rec[0]
+        const int k = node_of(rp);
+        T.nrec[k] = make_float4(rp.x, rp.y, rn.x, rn.y);
+        T.nds[k] = rp.z;
+        T.nsucc[k] = node_of(rn);
+    }
+}
+
+cudaError_t launch_rebuild_node_space(const TourDev &T, cudaStream_t st) {
+    int grid = (T.n + 255) / 256;
+    if (grid > 1184) grid = 1184;
+    rebuild_node_space_kernel<<<grid, 256, 0, st>>>(T);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_build_state(const InstDev &I, const TourDev &T, const int *order, cudaStream_t st) {
     int grid = (T.alloc + 255) / 256;
     if (grid > 1184) grid = 1184;

@@ -187,16 +187,22 @@ __device__ __forceinline__ MoveKey key_warp_min(MoveKey k) {
     return k;
 }
 
-// 64-bit packing used for the NCCL min-allreduce across GPUs: valid for n <= 2^17 and |delta| < 2^29.
+// 62-bit packing of a key, ordered like key_less(): valid for n <= 2^17 and |delta| < 2^27.  Used for the per-pass
+// 64-bit atomicMin of the scan kernel and for the multi-GPU exchange (the two free top bits leave room for the
+// generation bits of the peer-memory exchange word, see xchg_min()).
+constexpr int KEY_PACK_MAX_N = 1 << 17;
+constexpr int KEY_PACK_MAX_DELTA = 1 << 27;
 __host__ __device__ __forceinline__ unsigned long long key_pack(int delta, int i, int j) {
-    return ((unsigned long long)(unsigned)(delta + (1 << 29)) << 34) | ((unsigned long long)(unsigned)i << 17) |
+    return ((unsigned long long)(unsigned)(delta + KEY_PACK_MAX_DELTA) << 34) | ((unsigned long long)(unsigned)i << 17) |
            (unsigned long long)(unsigned)j;
 }
 __host__ __device__ __forceinline__ void key_unpack(unsigned long long p, int *delta, int *i, int *j) {
-    *delta = (int)(p >> 34) - (1 << 29);
+    *delta = (int)(p >> 34) - KEY_PACK_MAX_DELTA;
     *i = (int)((p >> 17) & 0x1ffffu);
     *j = (int)(p & 0x1ffffu);
 }
+// "no improving move": larger than every key with delta < 0
+#define KEY_PACK_NONE (key_pack(0, 0x1ffff, 0x1ffff))
 
 // ---- programmatic dependent launch (sm_90+): the next kernel of the stream may be scheduled while this one still runs;
 // everything it does before pdl_wait() must not depend on this kernel's results.  Without the launch attribute both

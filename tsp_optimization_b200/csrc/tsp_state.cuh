@@ -58,8 +58,21 @@ struct Ctl {
     MoveKey cand[4];                // runner-up moves of the last BI pass: re-evaluated after the apply to seed `hint`
     int ncand;
     unsigned long long cold_calls;  // statistics: filter hits that went through the exact (cold) path
+    unsigned long long pass_min;    // BI: packed (delta,i,j) minimum of the running pass (one atomicMin per block)
+    int done_reason;                // why `done` is set: DONE_OPTIMUM or DONE_CAP (a capped run may be continued)
+    // exact tile pruning: this rank's live tiles of the coming pass, built by tile_filter_kernel
+    unsigned live_count;            // entries in TourDev::live
+    unsigned long long tiles_scanned, tiles_skipped;  // statistics over all pruned passes
+    // per-pass timing breakdown (option "timing"): %globaltimer stamps of the running pass and accumulated intervals
+    unsigned long long tm_scan_first, tm_blk_end_min, tm_apply_first, tm_apply_end, tm_publish;
+    unsigned long long tm_acc[8];   // see TM_* below
 };
 constexpr int CTL_NCAND = 4;
+enum { DONE_NONE = 0, DONE_OPTIMUM = 1, DONE_CAP = 2 };
+// tm_acc slots, all in ns summed over passes: gap between the previous apply's end and the first scan block's start,
+// scan (first block start -> last block's ticket), spread (first block end -> last block end), tail (ticket -> move
+// published, includes the exchange), exchange wait alone, publish -> first apply block, apply duration, pass count
+enum { TM_GAP = 0, TM_SCAN = 1, TM_SPREAD = 2, TM_TAIL = 3, TM_XWAIT = 4, TM_APPLY_GAP = 5, TM_APPLY = 6, TM_COUNT = 7 };
 
 struct TourDev {
     int n;
@@ -73,6 +86,12 @@ struct TourDev {
     MoveKey *block_best;
     MoveRec *log;
     long long log_cap;
+    // exact tile pruning: bounding boxes {xmin, ymin, xmax, ymax} and largest edge length of every tile-row (TI positions
+    // + the successor of the last one) and tile-column (TJ positions + successor); live tile ids + their lower bounds
+    float4 *rowbox, *colbox;
+    float *rowmaxds, *colmaxds;
+    int *live;
+    float *live_lb;
 };
 
 #define FI_NONE 0xffffffffffffffffull
@@ -240,23 +259,76 @@ __device__ __forceinline__ void seed_hint_from_candidates(const InstDev &I, cons
 
 // ---- kernel argument blocks shared by the kernel translation units and engine.cu ----------------------
 // ---- multi-GPU argmin exchange over NVLink peer memory ------------------------------------------------------
-// Every rank owns 2 x XCHG_MAX_WORLD slots (double-buffered by the parity of the pass epoch).  In the tail of its scan
-// kernel a rank STORES its packed (delta,i,j) key, then (after a system-scope fence) the epoch, into slot [epoch&1][rank]
-// of EVERY peer — plain st.global on pointers mapped with cudaIpcOpenMemHandle, i.e. NVLink writes through NVSwitch — and
-// then polls its LOCAL slots until all `world` epochs arrived.  No collective launch, no tour data on the wire: 12 bytes
-// per peer and pass.  A rank can be at most one pass ahead of a peer (it cannot finish pass k+1 without that peer's key of
-// pass k+1), so two buffers suffice.
+// Every rank owns 2 x XCHG_MAX_WORLD 64-bit slots (double-buffered by the parity of the exchange epoch) plus XCHG_MAX_WORLD
+// alignment counters.  In the tail of its scan kernel a rank STORES ONE 64-bit word — its packed (delta,i,j) key shifted
+// left by two, with a 2-bit generation number derived from the epoch in the low bits — into slot [epoch&1][rank] of EVERY
+// peer (plain st.global on pointers mapped with cudaIpcOpenMemHandle, i.e. NVLink writes through NVSwitch) and then polls
+// its LOCAL slots until all `world` words carry the generation of this epoch.  Key and "arrived" flag travel in the same
+// word, so no fence and no second store are needed.  No collective launch, no tour data on the wire: 8 bytes per peer
+// and pass.  A rank can be at most one exchange ahead of a peer (it cannot finish exchange k+1 without that peer's word
+// of exchange k+1), so two buffers suffice; successive words in one buffer are 2 epochs apart, i.e. their generations
+// ((epoch >> 1) + 1) & 3 differ, and the zero-initialised slot never matches the first expected generation (1).
 constexpr int XCHG_MAX_WORLD = 16;
-struct __align__(16) XchgSlot {
-    unsigned long long key;
-    unsigned epoch;
-    unsigned pad;
+struct XchgMem {
+    unsigned long long slot[2][XCHG_MAX_WORLD];
+    unsigned long long align[XCHG_MAX_WORLD];  // monotonically increasing barrier counters (rank_align_kernel)
 };
 struct XchgDev {
-    XchgSlot *peer[XCHG_MAX_WORLD];  // peer[r] = base of rank r's slot array (peer[rank] = own, local pointer)
-    unsigned *epoch;                 // this rank's pass epoch (device word, monotonically increasing, never reset)
+    XchgMem *peer[XCHG_MAX_WORLD];   // peer[r] = rank r's XchgMem (peer[rank] = own, local pointer)
+    unsigned *epoch;                 // this rank's exchange epoch (device word, monotonically increasing, never reset)
+    unsigned *align_epoch;           // this rank's alignment-barrier epoch
     int enabled;
 };
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Block-wide: every rank contributes `key62` (< 2^62) and gets the minimum over all ranks.  Threads 0..world-1 each serve
+// one peer; `s_x` is a shared array of XCHG_MAX_WORLD words.  Returns the minimum in thread 0 (other threads: undefined);
+// *err is set to 2 when a peer did not deliver within ~10 s.  `wait_ns` (may be null) accumulates thread 0's polling time.
+__device__ __forceinline__ unsigned long long xchg_min(const XchgDev &X, int rank, int world, unsigned long long key62,
+                                                       unsigned long long *s_x, int *err, unsigned long long *wait_ns) {
+    __shared__ unsigned s_epoch;
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        const unsigned e = *X.epoch + 1u;
+        *X.epoch = e;
+        s_epoch = e;
+    }
+    __syncthreads();
+    if (tid < world) {
+        const unsigned e = s_epoch;
+        const unsigned long long gen = (unsigned long long)(((e >> 1) + 1u) & 3u);
+        const unsigned long long word = (key62 << 2) | gen;
+        unsigned long long *dst = &X.peer[tid]->slot[e & 1u][rank];
+        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(word) : "memory");
+        const unsigned long long *src = &X.peer[rank]->slot[e & 1u][tid];
+        const long long t0 = clock64();
+        const unsigned long long g0 = (wait_ns && tid == 0) ? globaltimer_ns() : 0ull;
+        unsigned long long got;
+        for (;;) {
+            asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(got) : "l"(src) : "memory");
+            if ((got & 3ull) == gen) break;
+            if (clock64() - t0 > 20000000000ll) {  // ~10 s: a peer died; fail loudly instead of hanging the GPU
+                *err = 2;
+                got = ~0ull;
+                break;
+            }
+        }
+        s_x[tid] = got >> 2;
+        if (wait_ns && tid == 0) *wait_ns += globaltimer_ns() - g0;
+    }
+    __syncthreads();
+    unsigned long long win = ~0ull;
+    if (tid == 0) {
+        win = s_x[0];
+        for (int r = 1; r < world; ++r) win = s_x[r] < win ? s_x[r] : win;
+    }
+    return win;
+}
 
 struct BiArgs {
     InstDev inst;
@@ -270,6 +342,11 @@ struct BiArgs {
     int fuse_apply;  // 0: the last block only publishes this rank's key (multi-GPU); 1: it publishes the move for the
                      // apply launch; 2: it also applies the move itself
     int seed_hint;   // 0 = none, 1 = this block's previous winner re-evaluated at the start of the scan, 2 = also runner-ups
+    int packed_tail; // 1: blocks fold their key into ctl->pass_min with one 64-bit atomicMin (n <= 2^17, seed_hint < 2)
+    int pruned;      // 1: tiles come from the live list built by tile_filter_kernel (exact tile pruning)
+    int timing;      // 1: accumulate the per-pass breakdown in ctl->tm_acc; 2: also dump per-block {start, end} stamps
+    int split_tiles, split_factor;  // tail smoothing: this rank's last split_tiles tiles are drawn as split_factor sub-tiles
+    unsigned long long *dbg;        // timing == 2: [gridDim.x][2] globaltimer stamps of the last pass
     XchgDev xchg;    // fuse_apply == 0: how this rank's key reaches the other ranks (enabled = 0 -> NCCL allreduce of ctl->packed)
 };
 

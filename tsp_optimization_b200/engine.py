@@ -32,7 +32,7 @@ ABI_SYMBOLS = [
     "tspb200_dist_matrix_free", "tspb200_tour_upload", "tspb200_tour_download", "tspb200_tour_log",
     "tspb200_bi_run", "tspb200_fi_run", "tspb200_two_opt", "tspb200_two_opt_tabu", "tspb200_two_opt_batch", "tspb200_nn_tour", "tspb200_nn_tour_batch", "tspb200_extra_mileage",
     "tspb200_tour_costs", "tspb200_comm_unique_id", "tspb200_comm_init", "tspb200_comm_destroy",
-    "tspb200_debug_tile_plan",
+    "tspb200_debug_tile_plan", "tspb200_debug_fetch",
 ]
 
 
@@ -45,7 +45,7 @@ class TspB200Error(RuntimeError):
 class _Stats(C.Structure):
     _fields_ = [("passes", C.c_int64), ("moves", C.c_int64), ("evals", C.c_int64), ("launches", C.c_int64),
                 ("obj_delta", C.c_int64), ("gpu_ms", C.c_double), ("cost", C.c_double), ("status", C.c_int32),
-                ("path", C.c_int32)]
+                ("path", C.c_int32), ("tiles_scanned", C.c_int64), ("tiles_total", C.c_int64)]
 
 
 class _Move(C.Structure):
@@ -63,10 +63,13 @@ class Stats:
     cost: float
     status: int
     path: int
+    tiles_scanned: int = 0
+    tiles_total: int = 0
 
     @staticmethod
     def of(s: _Stats) -> "Stats":
-        return Stats(s.passes, s.moves, s.evals, s.launches, s.obj_delta, s.gpu_ms, s.cost, s.status, s.path)
+        return Stats(s.passes, s.moves, s.evals, s.launches, s.obj_delta, s.gpu_ms, s.cost, s.status, s.path,
+                     s.tiles_scanned, s.tiles_total)
 
 
 _lib = None
@@ -114,6 +117,7 @@ def load_library() -> C.CDLL:
     L.tspb200_comm_destroy.argtypes = [vp]
     L.tspb200_debug_tile_plan.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, i32p, i32p, i32p,
                                           C.c_void_p, C.c_void_p, C.c_int, i32p]
+    L.tspb200_debug_fetch.argtypes = [vp, C.c_char_p, C.c_void_p, i64]
     _lib = L
     return L
 
@@ -134,12 +138,13 @@ def tile_plan(n: int, rows_per_thread: int = 0, tile_cols: int = 0, threads: int
 
 
 def key_pack(delta: int, i: int, j: int) -> int:
-    """Python mirror of key_pack() in csrc/tsp_device.cuh (the 8-byte payload of the NCCL min-allreduce)."""
-    return ((delta + (1 << 29)) << 34) | (i << 17) | j
+    """Python mirror of key_pack() in csrc/tsp_device.cuh (the 62-bit key of the per-pass atomicMin and of the
+    multi-GPU exchange; n <= 2^17, |delta| < 2^27)."""
+    return ((delta + (1 << 27)) << 34) | (i << 17) | j
 
 
 def key_unpack(p: int):
-    return (p >> 34) - (1 << 29), (p >> 17) & 0x1FFFF, p & 0x1FFFF
+    return (p >> 34) - (1 << 27), (p >> 17) & 0x1FFFF, p & 0x1FFFF
 
 
 def _moves_to_array(buf, k: int) -> np.ndarray:
@@ -185,6 +190,12 @@ class Engine:
 
     def info(self, key: str) -> int:
         return int(self.L.tspb200_get_info(self.h, key.encode()))
+
+    def block_times(self) -> np.ndarray:
+        """[grid, 2] %globaltimer stamps {start, end} of every block of the last BI pass run with option timing = 2."""
+        out = np.zeros((4096, 2), dtype=np.uint64)
+        self._ck(self.L.tspb200_debug_fetch(self.h, b"block_times", out.ctypes.data, out.nbytes))
+        return out[:self.info("grid_bi")]
 
     # -- instance
     def set_instance(self, xy, weight_type: int):

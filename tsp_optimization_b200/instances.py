@@ -94,3 +94,113 @@ def is_tour(succ) -> bool:
         seen[at] = True
         at = succ[at]
     return at == 0
+
+
+class GlibcRandom:
+    """glibc's random() / srandom() (TYPE_3 additive feedback generator, r[i] = r[i-3] + r[i-31]) restated, so that
+    populations can be generated exactly like the reference does (reference include/utility.h:36 URAND() =
+    random() / RAND_MAX, src/utility.c:752-754 rand_choice) without touching the process-wide libc state.
+    tests/test_host_logic.py checks it against libc itself."""
+
+    RAND_MAX = 2147483647
+
+    def __init__(self, seed: int):
+        seed = seed & 0xFFFFFFFF
+        if seed == 0:
+            seed = 1
+        r = [0] * 34
+        r[0] = seed
+        for i in range(1, 31):
+            # 16807 * r[i-1] % 2147483647 on the signed 32-bit value, as glibc computes it (Schrage)
+            prev = r[i - 1] if r[i - 1] < 0x80000000 else r[i - 1] - 0x100000000
+            hi, lo = int(prev / 127773), int(prev - 127773 * int(prev / 127773))
+            word = 16807 * lo - 2836 * hi
+            if word < 0:
+                word += 2147483647
+            r[i] = word & 0xFFFFFFFF
+        for i in range(31, 34):
+            r[i] = r[i - 31]
+        self._r = r
+        for _ in range(310):
+            self._step()
+
+    def _step(self) -> int:
+        r = self._r
+        v = (r[-31] + r[-3]) & 0xFFFFFFFF
+        r.append(v)
+        del r[0]
+        return v
+
+    def random(self) -> int:
+        return self._step() >> 1
+
+    def urand(self) -> float:
+        return self.random() / 2147483647.0
+
+    def rand_choice(self, lo: int, hi: int) -> int:
+        return lo + int(self.urand() * (hi - lo))
+
+
+def reference_random_population(n: int, batch: int, seed: int) -> np.ndarray:
+    """`batch` chromosomes generated exactly like reference src/genetic.c:349-364 random_generation(): identity, then n
+    random transpositions (idx1, idx2 drawn with rand_choice(0, n) in that order), one generator stream (srandom(seed),
+    reference src/solver.c:264) for the whole population.  Returns visiting orders [batch, n]."""
+    g = GlibcRandom(seed)
+    draws = np.empty(2 * n * batch, dtype=np.int64)
+    r = g._r
+    out = draws
+    for k in range(len(out)):  # the recurrence has lag 3: a plain loop (about a second for 1024 x 1000)
+        v = (r[-31] + r[-3]) & 0xFFFFFFFF
+        r.append(v)
+        del r[0]
+        out[k] = v >> 1
+    idx = ((draws / 2147483647.0) * n).astype(np.int64)
+    pop = np.empty((batch, n), dtype=np.int32)
+    p = 0
+    for b in range(batch):
+        c = list(range(n))
+        for _ in range(n):
+            i1, i2 = idx[p], idx[p + 1]
+            p += 2
+            c[i1], c[i2] = c[i2], c[i1]
+        pop[b] = c
+    return pop
+
+
+def apply_moves(succ0, moves) -> np.ndarray:
+    """Applies 2-opt moves (i, j[, delta]) to a successor array exactly as the reference does (src/tabusearch.c:161-165,
+    src/heuristics.c:476-483): a = i, b = j, succ[a] = b, succ[a1] = b1, forward path a1..b reversed.  Host-side helper for
+    checking a downloaded tour against a committed move log (bench.py)."""
+    succ0 = np.asarray(succ0, dtype=np.int32)
+    n = len(succ0)
+    order = succ_to_order_fast(succ0)
+    pos = np.empty(n, dtype=np.int64)
+    pos[order] = np.arange(n)
+    for mv in moves:
+        a, b = int(mv[0]), int(mv[1])
+        pa, pb = int(pos[a]), int(pos[b])
+        s = (pa + 1) % n
+        length = (pb - pa) % n
+        if length <= 1:
+            continue
+        if s + length <= n:
+            seg = order[s:s + length][::-1].copy()
+            order[s:s + length] = seg
+            pos[seg] = np.arange(s, s + length)
+        else:
+            idx = (s + np.arange(length)) % n
+            seg = order[idx][::-1].copy()
+            order[idx] = seg
+            pos[seg] = idx
+    return order_to_succ(order)
+
+
+def succ_to_order_fast(succ) -> np.ndarray:
+    """succ_to_order from node 0 with list arithmetic (the numpy scalar loop is ~10x slower at n = 100 000)."""
+    s = np.asarray(succ).tolist()
+    out = [0] * len(s)
+    at = 0
+    for p in range(len(s)):
+        out[p] = at
+        at = s[at]
+    return np.asarray(out, dtype=np.int32)

@@ -98,7 +98,11 @@ const char *tspb200_last_error(const tspb200_ctx *ctx);
  * "single_block" (tspb200_two_opt on one tour: -1 auto = one thread block with the tour in shared memory for small
  * tours [FI n <= 1536, BI n <= 160], 0 = always the grid kernels, 1 = the block kernel whenever the tour fits),
  * "force_path" (-1 auto, 0 fp32 filter, 1 exact on the fly, 2 matrix), "batch" (passes per host sync),
- * "time_limit_ms" (<=0 unlimited; checked between launch batches). */
+ * "time_limit_ms" (<=0 unlimited; checked between launch batches; on several GPUs the decision is taken collectively),
+ * "prune" (exact tile pruning of the best-improvement scan: -1 auto = on for n >= 3000, 0 = exhaustive scan, 1 = on;
+ * the selected moves are identical either way), "timing" (1 = accumulate the per-pass breakdown read back through
+ * tspb200_get_info("tm_scan" ...), 2 = also per-block time stamps), "batch_kernel" (batched best improvement: 0 =
+ * position-space block kernel where applicable, 1 = node-space kernel). */
 int tspb200_set_option(tspb200_ctx *ctx, const char *key, int64_t value);
 int64_t tspb200_get_info(const tspb200_ctx *ctx, const char *key);
 
@@ -162,10 +166,49 @@ int tspb200_extra_mileage(tspb200_ctx *ctx, int32_t *succ, double *cost);
  * else successor arrays. */
 int tspb200_tour_costs(tspb200_ctx *ctx, const int32_t *tours, int batch, int as_order, double *out);
 
+/* ---- resident sessions: the perturbation steps of the reference's meta-heuristics on device-resident state --------
+ * The callers of the 2-opt path alternate a small perturbation with a 2-opt run (HEU_VNS src/vns.c:103-183, tabu()
+ * src/tabusearch.c:188-320, HEU_Genetic src/genetic.c:445-560).  With these entry points the tour, the n(n-1)/2-int tabu
+ * list and the population stay in HBM between the steps; the caller keeps the random number generator (the reference
+ * draws from glibc random()) and the control flow, only indices and costs cross the bus. */
+
+/* Cost of the resident tour (sum of the exact integer edge lengths, reference vns.c:78-86 / tabusearch.c:168-172). */
+int tspb200_tour_cost(tspb200_ctx *ctx, double *cost);
+/* Device-side copies of the resident tour, slot 0 or 1 ("best solution so far", vns.c:121-122,171-173). */
+int tspb200_tour_save(tspb200_ctx *ctx, int slot);
+int tspb200_tour_restore(tspb200_ctx *ctx, int slot);
+/* kick() (src/vns.c:11-100) on the resident tour: idx1..3 = the three tour indices (counted from node 0) the reference
+ * draws with rand_choice(0, n), any order; a [b..c] [d..e] f becomes a [d..e] [b..c] f.  For idx3 = n-1 the reference reads
+ * one element past its tour array; here the successor wraps to tour[0].  *cost (may be NULL) = recomputed tour cost.
+ * Follow with tspb200_fi_run(ctx, -1, ..) = alg_2opt (vns.c:143): it starts a fresh sweep on the kicked tour. */
+int tspb200_vns_kick(tspb200_ctx *ctx, int idx1, int idx2, int idx3, double *cost);
+
+/* tabu() with the list in HBM: begin = CALLOC of the list (tabusearch.c:196); run = alg_2opt_tabu(inst, tabu_edge, prev,
+ * iter, tenure) on the resident tour (:238), st->cost = recomputed cost; kick = the random 2-opt kick (:262-309):
+ * `pairs` holds count candidate (a, b) node pairs in the order the caller drew them, the first that passes the
+ * reference's adjacency and check_tenure tests is applied and its two removed edges enter the list with `iter`;
+ * *accepted = its index or -1 (draw again); end = optional download of the list (n(n-1)/2 ints). n <= 46340. */
+int tspb200_tabu_begin(tspb200_ctx *ctx);
+int tspb200_tabu_run(tspb200_ctx *ctx, int iter, int tenure, int64_t max_passes, tspb200_stats *st);
+int tspb200_tabu_kick(tspb200_ctx *ctx, const int32_t *pairs, int count, int iter, int tenure, int *accepted);
+int tspb200_tabu_end(tspb200_ctx *ctx, int32_t *skip_out);
+
+/* Resident population (GA): tours live in HBM as successor arrays.  upload with slots == NULL creates a population of
+ * `count` tours; with slots it overwrites those individuals (offspring).  as_order != 0: tours are chromosomes (visiting
+ * orders, genetic.c:22-26), converted on the device (from_chromosome_to_edges, genetic.c:34-44; back: :437-441).
+ * costs = fitness() (genetic.c:51-60) of the listed slots (all `count` first ones when slots == NULL); two_opt = alg_2opt
+ * (FI, genetic.c:435) or best improvement on the listed slots in place, obj in/out like tspb200_two_opt_batch. */
+int tspb200_population_upload(tspb200_ctx *ctx, const int32_t *tours, const int32_t *slots, int count, int as_order);
+int tspb200_population_download(tspb200_ctx *ctx, int32_t *tours, const int32_t *slots, int count, int as_order);
+int tspb200_population_costs(tspb200_ctx *ctx, const int32_t *slots, int count, double *out);
+int tspb200_population_two_opt(tspb200_ctx *ctx, int mode, const int32_t *slots, int count, double *obj, tspb200_stats *st);
+
 /* ---- multi-GPU (one process per GPU; the caller bootstraps the id, e.g. over torch.distributed) ---- */
-/* Neighbourhood sharding: with a communicator attached, tspb200_bi_run deals the pair tiles round-robin
- * over the ranks and selects the move with ONE 8-byte NCCL min-allreduce per pass; every rank applies the
- * same move to its own replica of the tour. */
+/* Neighbourhood sharding: with a communicator attached, tspb200_bi_run deals the pair tiles round-robin over the ranks;
+ * per pass every rank's packed (delta, i, j) key is stored into every peer's exchange slots over NVLink by the scan kernel
+ * itself (CUDA IPC peer memory mapped at comm_init; option "exchange" = 1 or a failed mapping falls back to one 8-byte
+ * NCCL min-allreduce per pass) and every rank applies the same move to its own replica of the tour.  tspb200_fi_run
+ * shards the first-improvement search the same way (segments of the pair order dealt over the ranks). */
 int tspb200_comm_unique_id(void *id128); /* 128 bytes out (ncclUniqueId), call on rank 0 */
 int tspb200_comm_init(tspb200_ctx *ctx, const void *id128, int rank, int world);
 int tspb200_comm_destroy(tspb200_ctx *ctx);

@@ -157,6 +157,25 @@ class Oracle:
             return succ, o.value, st, _log_to_array(log, st.logged), prev
         return succ, o.value, st, _log_to_array(log, st.logged)
 
+    def vns_kick(self, xy, wt, succ, idx1, idx2, idx3):
+        """reference kick() (src/vns.c:11-100) with the three drawn tour indices -> (succ, cost)."""
+        xy = _as_xy(xy)
+        succ = np.array(succ, dtype=np.int32, copy=True)
+        self.L.orc_vns_kick.restype = C.c_double
+        self.L.orc_vns_kick.argtypes = [_f64p, C.c_int, C.c_int, _i32p, C.c_int, C.c_int, C.c_int]
+        cost = self.L.orc_vns_kick(xy, len(xy), wt, succ, int(idx1), int(idx2), int(idx3))
+        return succ, cost
+
+    def tabu_kick(self, succ, skip, pairs, iter_, tenure):
+        """the random kick of tabu() (src/tabusearch.c:262-309) -> (accepted index, succ, skip)."""
+        succ = np.array(succ, dtype=np.int32, copy=True)
+        skip = np.array(skip, dtype=np.int32, copy=True)
+        pairs = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
+        self.L.orc_tabu_kick.restype = C.c_int
+        self.L.orc_tabu_kick.argtypes = [C.c_int, _i32p, _i32p, _i32p, C.c_int, C.c_int, C.c_int]
+        acc = self.L.orc_tabu_kick(len(succ), succ, skip, pairs, len(pairs), int(iter_), int(tenure))
+        return acc, succ, skip
+
     def bi_scan_rows_mt(self, xy, wt, succ, row_begin, row_end, threads):
         xy = _as_xy(xy)
         sec = C.c_double(0)
@@ -286,6 +305,18 @@ class RefLib:
         self.L.alg_2opt_tabu(h, skip_edge.ctypes.data if skip_edge is not None else None,
                              prev.ctypes.data if prev is not None else None, iter_, tenure)
         out = (self.get_succ(h), self.L.refshim_obj(h)) + ((prev,) if want_prev else ())
+        self.free(h)
+        return out
+
+    def vns_kick_stock(self, xy, wt, succ, seed):
+        """The reference's own kick() (src/vns.c:11) after srandom(seed): it draws its three indices from glibc random()."""
+        libc = C.CDLL("libc.so.6")
+        h = self.new(xy, wt)
+        self.L.refshim_set_succ(h, np.ascontiguousarray(succ, dtype=np.int32))
+        libc.srandom(C.c_uint(seed))
+        self.L.kick.argtypes = [C.c_void_p]
+        self.L.kick(h)
+        out = self.get_succ(h), self.L.refshim_obj(h)
         self.free(h)
         return out
 

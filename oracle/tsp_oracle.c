@@ -341,6 +341,68 @@ int orc_two_opt_bi(const double *xy, int n, int weight_type, int32_t *succ, doub
 
 /* ---- CPU-baseline helpers (bench.py) -------------------------------------------------------- */
 
+/* ---- the perturbation steps of the meta-heuristics (callers of the path; tests for the resident sessions) ---------- */
+
+/* src/vns.c:11-100 kick(), with the three tour indices handed in instead of drawn (the reference draws them with
+ * rand_choice at :25-31): tour[] from node 0 (:15-22), indices sorted (:34-50), a,b / c,d / e,f (:54-59), new successors
+ * a->d, e->b, c->f (:60-62), cost recomputed (:78-86).  For idx3 == n-1 the reference reads tour[n] (one past its
+ * calloc'ed array); f then wraps to tour[0] here, the only value that keeps the result a tour.  Returns the new cost. */
+double orc_vns_kick(const double *xy, int n, int weight_type, int32_t *succ, int idx1, int idx2, int idx3) {
+    int32_t *tour = (int32_t *)malloc(sizeof(int32_t) * (size_t)n);
+    int node = 0;
+    for (int idx = 0; idx < n; idx++) { tour[idx] = node; node = succ[node]; }
+    if (idx1 > idx2) { int t = idx1; idx1 = idx2; idx2 = t; }
+    if (idx1 > idx3) { int t = idx1; idx1 = idx3; idx3 = t; }
+    if (idx2 > idx3) { int t = idx2; idx2 = idx3; idx3 = t; }
+    int a = tour[idx1], b = tour[idx1 + 1], c = tour[idx2], d = tour[idx2 + 1], e = tour[idx3];
+    int f = tour[idx3 + 1 < n ? idx3 + 1 : 0];
+    succ[a] = d;
+    succ[e] = b;
+    succ[c] = f;
+    node = 0;
+    for (int idx = 0; idx < n; idx++) { tour[idx] = node; node = succ[node]; }
+    double cost = 0;
+    int prev_node = tour[0];
+    for (int i = 1; i < n; i++) { cost += orc_dist(xy, weight_type, 1, prev_node, tour[i]); prev_node = tour[i]; }
+    cost += orc_dist(xy, weight_type, 1, prev_node, tour[0]);
+    free(tour);
+    return cost;
+}
+
+/* src/tabusearch.c:83-92 check_tenure() */
+static int tenure_check(int32_t *v, int iter, int tenure) {
+    if (iter < 0 || tenure < 0) return 0;
+    if (*v == 0) return 0;
+    if (iter - *v > tenure) { *v = 0; return 0; }
+    return 1;
+}
+
+/* src/tabusearch.c:262-309, the random kick of tabu(): candidates (a, b) are taken from `pairs` in order (the reference
+ * draws them with rand_choice inside the loop); skipped when a == b or the edges touch (:271-273); the first whose four
+ * edges pass check_tenure (with its lazy expiry and && short-circuit, :283-290) is applied as a 2-opt move (:292-294) and
+ * (a,a1), (b,b1) enter the list with `iter` (:304-307).  Returns the index of the accepted candidate or -1. */
+int orc_tabu_kick(int n, int32_t *succ, int32_t *skip, const int32_t *pairs, int count, int iter, int tenure) {
+    for (int c = 0; c < count; c++) {
+        int a = pairs[2 * c], b = pairs[2 * c + 1];
+        int a1 = succ[a], b1 = succ[b];
+        if (a == b || a1 == b || b1 == a) continue;
+        int64_t e1 = tri_index(a, a1, n), e2 = tri_index(b, b1, n), e3 = tri_index(a, b, n), e4 = tri_index(a1, b1, n);
+        if (!tenure_check(&skip[e1], iter, tenure) && !tenure_check(&skip[e2], iter, tenure) &&
+            !tenure_check(&skip[e3], iter, tenure) && !tenure_check(&skip[e4], iter, tenure)) {
+            int32_t *prev = build_prev(n, succ);
+            succ[a] = b;
+            succ[a1] = b1;
+            orc_reverse_path(n, succ, b, a1, prev);
+            free(prev);
+            skip[e1] = iter;
+            skip[e2] = iter;
+            return c;
+        }
+    }
+    return -1;
+}
+
+
 int64_t orc_bi_scan_rows(const double *xy, int n, int weight_type, const int32_t *succ,
                          int row_begin, int row_end, int64_t *best_delta, int32_t *best_i, int32_t *best_j) {
     int64_t evals = 0;

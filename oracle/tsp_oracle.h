@@ -113,4 +113,8 @@ int64_t orc_bi_scan_rows_mt(const double *xy, int n, int weight_type, const int3
 #ifdef __cplusplus
 }
 #endif
+/* perturbation steps of the meta-heuristics (reference src/vns.c:11-100, src/tabusearch.c:262-309), indices handed in */
+double orc_vns_kick(const double *xy, int n, int weight_type, int32_t *succ, int idx1, int idx2, int idx3);
+int orc_tabu_kick(int n, int32_t *succ, int32_t *skip, const int32_t *pairs, int count, int iter, int tenure);
+
 #endif

@@ -822,3 +822,41 @@ def test_pruned_scan_skips_tiles_but_not_moves(engine, oracle):
     assert st.tiles_total > 0 and st.tiles_scanned < 0.7 * st.tiles_total
     es, eobj, est, elog = oracle.two_opt_bi(xy, 0, succ0, max_passes=120, log_cap=200)
     assert logs[1][0] == elog.tolist() and logs[1][2] == eobj
+
+
+def test_batch_bi_position_space_kernel_equals_node_space_kernel_and_oracle(engine, oracle):
+    """the position-space block kernel (csrc/kernels_batch.cu two_opt_batch_bi_kernel) against the node-space one and the
+    oracle: random tours (wrap-around reversals), every FP32-path metric, sizes around the warp-tile boundaries."""
+    rng = np.random.default_rng(31)
+    for n, wt, batch in [(1000, 0, 6), (257, 3, 5), (256, 5, 5), (129, 0, 4), (128, 0, 4), (61, 5, 6), (33, 0, 3), (9, 0, 3), (5, 0, 2),
+                         (4, 0, 2), (3, 0, 1), (700, 0, 3)]:
+        xy = rng.integers(0, 3000, size=(n, 2)).astype(np.float64)
+        if n == 700:
+            xy = xy + rng.integers(0, 1000, size=(n, 2)) / 1000.0  # not FP32-exact: FP64 exact check from the node table
+        tours = random_tours(n, batch, 1000 + n)
+        engine.set_instance(xy, wt)
+        res = {}
+        for kern in (0, 1):
+            engine.set_option("batch_kernel", kern)
+            res[kern] = engine.two_opt_batch(BI, tours)
+        engine.set_option("batch_kernel", 0)
+        assert (res[0][0] == res[1][0]).all() and (res[0][1] == res[1][1]).all(), (n, wt)
+        assert (res[0][2].moves, res[0][2].passes, res[0][2].evals) == (res[1][2].moves, res[1][2].passes, res[1][2].evals)
+        for b in range(min(batch, 2)):
+            es, eobj, est, _ = oracle.two_opt_bi(xy, wt, tours[b])
+            assert (res[0][0][b] == es).all() and res[0][1][b] == eobj, (n, wt, b)
+
+
+def test_batches_of_tours_too_large_for_one_block_run_on_the_grid_path(engine, oracle):
+    """n = 12 000 exceeds the shared-memory tour of both block kernels: the batch entry point must still deliver (each tour goes
+    through the grid kernels), with the same result as the single-tour call."""
+    xy = uniform_instance(12000)
+    engine.set_instance(xy, 0)
+    s0, c0 = engine.nn_tour(0)
+    s1, c1 = engine.nn_tour(5)
+    tours = np.stack([s0, s1])
+    sb, ob, st = engine.two_opt_batch(FI, tours, np.array([c0, c1]))
+    for b, (s, c) in enumerate(((s0, c0), (s1, c1))):
+        es, eo, _, _ = engine.two_opt(FI, s, c)
+        assert (sb[b] == es).all() and ob[b] == eo
+    assert is_tour(sb[0]) and ob[0] == oracle.succ_cost(xy, 0, sb[0])

@@ -89,3 +89,26 @@ def test_instance_helpers():
         o = succ_to_order(t[b])
         assert (order_to_succ(o) == t[b]).all()
     assert not is_tour(np.array([1, 0, 3, 2], dtype=np.int32))
+
+
+def test_glibc_random_restated_equals_libc():
+    """GlibcRandom == srandom()/random() of the C library (the generator behind the reference's URAND / rand_choice), and
+    reference_random_population == random_generation() (reference src/genetic.c:349-364) driven by it."""
+    import ctypes
+    from tsp_optimization_b200.instances import GlibcRandom, reference_random_population
+    libc = ctypes.CDLL("libc.so.6")
+    libc.random.restype = ctypes.c_long
+    for seed in (1, 123, 0, 2**31 + 5, 4242):
+        libc.srandom(ctypes.c_uint(seed))
+        g = GlibcRandom(seed)
+        assert [libc.random() for _ in range(500)] == [g.random() for _ in range(500)], seed
+    n = 97
+    pop = reference_random_population(n, 3, 123)
+    libc.srandom(123)
+    for b in range(3):
+        c = list(range(n))
+        for _ in range(n):
+            i1 = int(libc.random() / 2147483647.0 * n)
+            i2 = int(libc.random() / 2147483647.0 * n)
+            c[i1], c[i2] = c[i2], c[i1]
+        assert pop[b].tolist() == c

@@ -192,3 +192,29 @@ def test_constructive_restatements_equal_reference_and_csv(oracle, reflib, insta
         s, c = oracle.extra_mileage(xy, 0)
         st, rs, rc = reflib.run_method("HEU_extramileage", xy, 0)
         assert c == rc and (s == rs).all(), n
+
+
+def test_vns_kick_restatement_equals_the_reference_kick(oracle, reflib):
+    """oracle.vns_kick (indices handed in) against the reference's own kick() (src/vns.c:11), which draws its three indices
+    from glibc random(): the draws are replayed with the restated generator.  Seeds whose largest index is n-1 are skipped —
+    there the reference reads one element past its tour array."""
+    from tsp_optimization_b200.instances import GlibcRandom, is_tour, uniform_instance
+    n = 300
+    xy = uniform_instance(n)
+    succ, _ = oracle.nn_tour(xy, 0, 0)
+    compared = 0
+    for seed in range(1, 40):
+        g = GlibcRandom(seed)
+        i1 = g.rand_choice(0, n)
+        i2 = i3 = i1
+        while i2 == i1 or abs(i1 - i2) <= 1:
+            i2 = g.rand_choice(0, n)
+        while i3 == i1 or i3 == i2 or abs(i1 - i3) <= 1 or abs(i2 - i3) <= 1:
+            i3 = g.rand_choice(0, n)
+        if max(i1, i2, i3) == n - 1:
+            continue
+        s_ref, c_ref = reflib.vns_kick_stock(xy, 0, succ, seed)
+        s_o, c_o = oracle.vns_kick(xy, 0, succ, i1, i2, i3)
+        assert (s_ref == s_o).all() and c_ref == c_o and is_tour(s_o), seed
+        compared += 1
+    assert compared >= 30

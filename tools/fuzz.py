@@ -15,7 +15,7 @@ SHAPES = [(0, 0, 0), (64, 2, 32), (64, 4, 64), (64, 8, 88), (128, 8, 128), (128,
 
 
 def coords(n):
-    kind = rng.integers(0, 8)
+    kind = rng.integers(0, 9)
     if kind == 0:
         return rng.integers(0, 10000, size=(n, 2)).astype(np.float64), "int1e4"
     if kind == 1:
@@ -31,6 +31,8 @@ def coords(n):
         return (c[rng.integers(0, 8, size=n)] + rng.integers(-30, 30, size=(n, 2))).astype(np.float64), "clustered"
     if kind == 6:
         return rng.integers(-5000, 5000, size=(n, 2)).astype(np.float64), "neg"
+    if kind == 8:  # FP32-exact but NOT integer, 1e5..1e6 range: the matrix fast path without the integer shortcut
+        return rng.integers(800_000, 8_000_000, size=(n, 2)).astype(np.float64) / 8.0, "eighths1e6"
     x = rng.integers(0, 3000, size=(n, 1)).astype(np.float64)
     return np.hstack([x, np.zeros((n, 1))]), "collinear"
 
@@ -56,6 +58,8 @@ while time.time() - t0 < budget:
         cap = int(rng.integers(1, 30))
     eng.set_option("block_threads", T); eng.set_option("rows_per_thread", R); eng.set_option("tile_cols", TJ)
     eng.set_option("single_block", route)
+    eng.set_option("prune", int(rng.choice([-1, 0, 1, 1])))          # exact tile pruning must not change a single move
+    eng.set_option("batch_kernel", int(rng.integers(0, 2)))          # one-block BI: position-space / node-space kernel
     eng.set_option("grid", int(rng.choice([0, 0, 1, 3, 17, 64])))  # few blocks -> many rounds of dynamically drawn tiles
     eng.set_instance(xy, wt)
     use_matrix = wt in (1, 2, 4) or rng.random() < 0.15

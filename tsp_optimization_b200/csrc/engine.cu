@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/tspb200.h"
@@ -37,15 +38,23 @@ cudaError_t launch_dist_matrix(const InstDev &I, int *out, long long ld, int row
                                cudaStream_t st);
 cudaError_t launch_build_state(const InstDev &I, const TourDev &T, const int *order, cudaStream_t st);
 cudaError_t launch_export_state(const TourDev &T, int *succ, unsigned long long *cost, cudaStream_t st);
-cudaError_t launch_tour_cost(const InstDev &I, const int *tours, int as_order, long long *out, int batch, cudaStream_t st);
+cudaError_t launch_tour_cost(const InstDev &I, const int *tours, const int *slots, int as_order, long long *out, int batch,
+                             cudaStream_t st);
 cudaError_t launch_nn_tour(const NnArgs &a, int grid, cudaStream_t st);
 cudaError_t launch_prep_points(const double2 *raw, double2 *pt64, float2 *pt32, int n, int metric, cudaStream_t st);
 int nn_max_grid(int num_sms);
 cudaError_t launch_extra_mileage(const InstDev &I, int *succ_out, long long *cost_out, cudaStream_t st);
 cudaError_t launch_nn_batch(const InstDev &I, const int *starts, int batch, int *succ_out, long long *cost_out, float eps,
                             int num_sms, cudaStream_t st);
-cudaError_t launch_two_opt_batch(const InstDev &I, int mode, int *succ, long long *obj_delta, long long *counters,
+cudaError_t launch_two_opt_batch(const InstDev &I, int mode, int *succ, const int *slots, long long *obj_delta, long long *counters,
                                  int batch, int num_sms, cudaStream_t st, int *launched, MoveRec *log, long long log_cap);
+cudaError_t launch_two_opt_batch_bi_pos(const InstDev &I, int *succ, const int *slots, long long *obj, long long *counters, int batch,
+                                        int num_sms, cudaStream_t st, int *launched, MoveRec *log, long long log_cap);
+cudaError_t launch_vns_kick(const InstDev &I, const TourDev &T, int idx1, int idx2, int idx3, float4 *scratch, cudaStream_t st);
+cudaError_t launch_tabu_kick_select(const TourDev &T, int *skip, const int *pairs, int count, int iter, int tenure, int *accepted,
+                                    cudaStream_t st);
+cudaError_t launch_population_store(const int *staged, int *pop, const int *slots, int n, int count, int as_order, cudaStream_t st);
+cudaError_t launch_population_fetch(const int *pop, const int *slots, int *out, int n, int count, int as_order, cudaStream_t st);
 
 // ---- NCCL, loaded at run time (the torch-bundled or system libnccl.so.2) -------------------------------
 typedef struct { char internal[128]; } nccl_unique_id;
@@ -102,6 +111,7 @@ struct tspb200_ctx {
     int *d_mat = nullptr;
     long long mat_ld = 0;
     double dmax = 0;
+    float eps32 = 0;                  // bound of |FP32 distance - real distance| for this instance
 
     // tour (device buffers are kept across set_instance / tour_upload calls while they are big enough: cudaMalloc is
     // a synchronising call, and a slow one once peer access is enabled)
@@ -138,8 +148,7 @@ struct tspb200_ctx {
     int opt_single_block = -1;
     int opt_prune = -1;         // exact tile pruning of the best-improvement scan: -1 auto, 0 off (exhaustive scan), 1 on
     int opt_timing = 0;         // accumulate the per-pass breakdown (scan / tail / exchange wait / apply) on the device
-    int opt_tail_split = -1;    // tail smoothing: -1 auto, 0/1 off, 2 or 4 = sub-tiles per split tile
-    int opt_tail_tiles = 0;     // tiles per rank that are split (0 = auto: half a wave)
+    int opt_batch_kernel = 0;   // batched best improvement: 0 = position-space kernel when applicable, 1 = always the node-space kernel
     unsigned long long *d_dbg = nullptr;  // per-block time stamps of the last pass ("timing" = 2)
     int opt_debug_shard = 0;    // timing experiments only: (world << 8 | rank) -> scan that rank's share of the tiles on one GPU  // -1 auto, 0 never, 1 whenever the tour fits in shared memory
     // benchmark hygiene: write this many bytes (> L2) before every pass and time each pass with its own event pair
@@ -156,6 +165,16 @@ struct tspb200_ctx {
     long long *d_zl = nullptr;
     unsigned long long *d_zl_count = nullptr;
     long long zl_cap = 0;
+
+    // resident sessions (VNS / tabu / GA): saved tours, the tabu list kept in HBM, a population of successor arrays
+    bool tour_changed = false;        // the resident tour was perturbed since the last 2-opt run: `done` no longer holds
+    float4 *save_rec[2] = {};
+    int *save_pos[2] = {};
+    int save_n[2] = {}, save_alloc[2] = {};
+    bool tabu_session = false;
+    int *d_pop = nullptr;
+    long long pop_cap = 0;            // tours the population buffer can hold
+    int pop_count = 0, pop_n = 0;
 
     // comm
     nccl_comm_t comm = nullptr;
@@ -245,6 +264,16 @@ static void free_instance(tspb200_ctx *c) {
     c->d_skip = nullptr; c->d_zl = nullptr; c->d_zl_count = nullptr;
     c->skip_cap = c->zl_cap = 0;
     c->tabu_on = false;
+    c->tabu_session = false;
+    for (int k = 0; k < 2; ++k) {
+        cudaFree(c->save_rec[k]); cudaFree(c->save_pos[k]);
+        c->save_rec[k] = nullptr; c->save_pos[k] = nullptr;
+        c->save_n[k] = c->save_alloc[k] = 0;
+    }
+    cudaFree(c->d_pop);
+    c->d_pop = nullptr;
+    c->pop_cap = 0;
+    c->pop_count = c->pop_n = 0;
     cudaFree(c->d_raw); cudaFree(c->d_pt64); cudaFree(c->d_pt32); cudaFree(c->d_mat);
     c->d_raw = c->d_pt64 = nullptr; c->d_pt32 = nullptr; c->d_mat = nullptr;
     c->n = 0;
@@ -329,12 +358,8 @@ int tspb200_set_option(tspb200_ctx *ctx, const char *key, int64_t value) {
     } else if (k == "timing") {
         if (value < 0 || value > 2) return fail(ctx, TSPB200_E_ARG, "timing must be 0, 1 or 2");
         ctx->opt_timing = (int)value;
-    } else if (k == "tail_split") {
-        if (value != -1 && value != 0 && value != 1 && value != 2 && value != 4) return fail(ctx, TSPB200_E_ARG, "tail_split must be -1 (auto), 0, 1, 2 or 4");
-        ctx->opt_tail_split = (int)value;
-    } else if (k == "tail_tiles") {
-        if (value < 0) return fail(ctx, TSPB200_E_ARG, "tail_tiles must be >= 0");
-        ctx->opt_tail_tiles = (int)value;
+    } else if (k == "batch_kernel") {
+        ctx->opt_batch_kernel = value ? 1 : 0;
     } else if (k == "pdl") {
         ctx->opt_pdl = value ? 1 : 0;
     } else if (k == "seed_hint") {
@@ -402,6 +427,9 @@ int tspb200_set_instance(tspb200_ctx *ctx, const double *xy, int n, int weight_t
         ctx->d_mat = nullptr;
         ctx->mat_ld = 0;
         ctx->has_tour = false;
+        ctx->tabu_session = false;  // sessions belong to the instance they were opened on
+        ctx->pop_count = 0;
+        ctx->save_n[0] = ctx->save_n[1] = 0;
     }
     ctx->n = n;
     ctx->metric = weight_type;
@@ -438,7 +466,15 @@ int tspb200_set_instance(tspb200_ctx *ctx, const double *xy, int n, int weight_t
     ctx->inst.exact32 = exact32 ? 1 : 0;
     ctx->inst.fp32_ok = fp32_ok ? 1 : 0;
     ctx->inst.int_coords = (int_coords && exact32 && finite) ? 1 : 0;
-    ctx->inst.W = (float)(2.0 + 2.0 * eps);
+    // Filter window W: a pair whose exact delta is <= the best one must pass "Q_fp32 <= best + W".  The two fresh integer
+    // distances of a move differ from the real ones by at most 1/2 each for EUC_2D (nint), and are never BELOW the real ones
+    // for CEIL_2D and ATT (both round up): delta_exact >= Q_real - 1 resp. Q_real.  The FP32 evaluation of Q adds at most
+    // 2 eps (two distances) + three roundings of sums <= 2 dmax (0.4 eps); 4 eps is allowed for.  Every pair inside the
+    // window costs a trip through the exact path, so the window is kept as narrow as the arithmetic permits
+    // (round 1 used 2 + 2 eps for every metric: ~2x the exact-path calls on EUC_2D).
+    const bool rounds_up = weight_type == TSPB200_CEIL_2D || weight_type == TSPB200_ATT;
+    ctx->eps32 = (float)eps;
+    ctx->inst.W = metric_fp32 ? (float)((rounds_up ? 0.125 : 1.0) + 4.0 * eps) : (float)(2.0 + 2.0 * eps);
     ctx->inst.band = (float)std::ldexp(1.0, -20);
     if (n > ctx->inst_cap) {
         CK(cudaMalloc(&ctx->d_raw, sizeof(double2) * (size_t)n));
@@ -738,6 +774,7 @@ int tspb200_tour_upload(tspb200_ctx *ctx, const int32_t *succ, int64_t log_cap) 
     *ctx->h_ctl = c0;
     ctx->node_dirty = false;
     ctx->fi_cursor_stale = false;
+    ctx->tour_changed = false;
     CK(cudaMemcpyAsync(ctx->d_ctl, ctx->h_ctl, sizeof(Ctl), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemsetAsync(ctx->tour.block_best, 0, sizeof(MoveKey) * 4096, ctx->stream));  // delta 0 = "no previous winner"
     InstDev I = inst_for_path(ctx, select_path(ctx));
@@ -782,6 +819,9 @@ int tspb200_tour_log(tspb200_ctx *ctx, tspb200_move *log, int64_t cap, int64_t *
 static int run_batch(tspb200_ctx *ctx, int mode, int32_t *succ, double *obj, int batch, tspb200_stats *st, tspb200_move *log,
                      int64_t log_cap, int64_t *log_count);
 
+static int run_batch_sequential(tspb200_ctx *ctx, int mode, int32_t *succ, double *obj, int batch, tspb200_stats *st,
+                                tspb200_move *log, int64_t log_cap, int64_t *log_count);
+
 static int sync_ctl(tspb200_ctx *ctx) {
     CK(cudaMemcpyAsync(ctx->h_ctl, ctx->d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -796,10 +836,11 @@ static int sync_ctl(tspb200_ctx *ctx) {
 // the next fi_run starts a fresh sweep.  The host owns the state here: the stream was just synchronised by sync_ctl().
 static int prepare_run(tspb200_ctx *ctx, bool reset_fi_cursor, long long max_moves_abs) {
     Ctl *h = ctx->h_ctl;
-    if (h->done && h->done_reason == DONE_CAP) {
+    if (h->done && (h->done_reason == DONE_CAP || ctx->tour_changed)) {
         h->done = 0;
         h->done_reason = DONE_NONE;
     }
+    ctx->tour_changed = false;
     if (reset_fi_cursor) {
         h->cur_i = 0;
         h->cur_j = 1;
@@ -851,15 +892,6 @@ int tspb200_bi_run(tspb200_ctx *ctx, int64_t max_passes, tspb200_stats *st) {
     a.timing = ctx->opt_timing;
     if (a.timing == 2 && !ctx->d_dbg) CK(cudaMalloc(&ctx->d_dbg, sizeof(unsigned long long) * 2 * 4096));
     a.dbg = ctx->d_dbg;
-    {
-        // tail smoothing: auto = quarter tiles for the last half wave once a pass is at least two waves deep and the tile
-        // width allows it (sub-tile widths must stay multiples of the filter granularity 4)
-        const long long own = ((long long)ctx->ntiles - a.rank + a.world - 1) / a.world;
-        int F = ctx->opt_tail_split >= 0 ? ctx->opt_tail_split : (own >= 2ll * ctx->grid_bi ? 4 : 1);
-        while (F > 1 && (ctx->TJ % (4 * F)) != 0) F >>= 1;
-        a.split_factor = F > 1 ? F : 1;
-        a.split_tiles = ctx->opt_tail_tiles > 0 ? ctx->opt_tail_tiles : ctx->grid_bi / 2;
-    }
     // exact tile pruning: same moves, fewer evaluated pairs (the throughput benchmarks switch it off: "prune" = 0)
     const bool prune = path == 0 && !ctx->tabu_on && ctx->ntr > 0 && prune_wanted(ctx);
     a.pruned = prune ? 1 : 0;
@@ -1199,11 +1231,19 @@ static int run_batch(tspb200_ctx *ctx, int mode, int32_t *succ, double *obj, int
     CK(cudaMemsetAsync(d_delta, 0, sizeof(long long) * (size_t)batch, ctx->stream));
     CK(cudaMemsetAsync(d_cnt, 0, sizeof(long long) * 4 * (size_t)batch, ctx->stream));
     int launched = 0;
-    cudaError_t le = launch_two_opt_batch(I, mode, d_succ, d_delta, d_cnt, batch, ctx->num_sms, ctx->stream, &launched, d_log, lcap);
-    if (le != cudaSuccess) {
-        if (le == cudaErrorInvalidValue) return fail(ctx, TSPB200_E_UNSUPPORTED, "batched 2-opt keeps a tour in shared memory: n=%d is too large", n);
-        return fail(ctx, TSPB200_E_CUDA, "batched 2-opt launch failed: %s", cudaGetErrorString(le));
+    // best improvement on the FP32-filter path: the position-space block kernel; everything else: the node-space one
+    cudaError_t le = cudaErrorNotSupported;
+    if (mode == TSPB200_BI && path == 0 && ctx->opt_batch_kernel != 1)
+        le = launch_two_opt_batch_bi_pos(I, d_succ, nullptr, d_delta, d_cnt, batch, ctx->num_sms, ctx->stream, &launched, d_log, lcap);
+    if (le == cudaErrorNotSupported)
+        le = launch_two_opt_batch(I, mode, d_succ, nullptr, d_delta, d_cnt, batch, ctx->num_sms, ctx->stream, &launched, d_log, lcap);
+    if (le == cudaErrorInvalidValue) {
+        // a tour that does not fit one block's shared memory: the tours go through the grid kernels one after the other
+        // (still the CUDA path; the reference has no size limit either)
+        cudaGetLastError();
+        return run_batch_sequential(ctx, mode, succ, obj, batch, st, log, log_cap, log_count);
     }
+    if (le != cudaSuccess) return fail(ctx, TSPB200_E_CUDA, "batched 2-opt launch failed: %s", cudaGetErrorString(le));
     std::vector<long long> h_delta((size_t)batch), h_cnt((size_t)batch * 4);
     CK(cudaMemcpyAsync(succ, d_succ, sizeof(int) * (size_t)n * batch, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(h_delta.data(), d_delta, sizeof(long long) * (size_t)batch, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1238,6 +1278,42 @@ static int run_batch(tspb200_ctx *ctx, int mode, int32_t *succ, double *obj, int
     local.status = TSPB200_LOCAL_OPTIMUM;
     if (batch == 1) local.cost = obj ? obj[0] : 0.0;
     if (st) *st = local;
+    return TSPB200_OK;
+}
+
+// Tours too large for the one-block kernels: each tour runs through the resident-tour grid path (upload, run to the local
+// optimum, download).  The context's resident tour is replaced.
+static int run_batch_sequential(tspb200_ctx *ctx, int mode, int32_t *succ, double *obj, int batch, tspb200_stats *st,
+                                tspb200_move *log, int64_t log_cap, int64_t *log_count) {
+    const int n = ctx->n;
+    tspb200_stats total;
+    memset(&total, 0, sizeof total);
+    for (int b = 0; b < batch; ++b) {
+        int32_t *s = succ + (size_t)b * n;
+        const bool want_log = log && batch == 1 && log_cap > 0;
+        int rc = tspb200_tour_upload(ctx, s, want_log ? log_cap : 0);
+        if (rc) return rc;
+        tspb200_stats one;
+        memset(&one, 0, sizeof one);
+        rc = mode == TSPB200_BI ? tspb200_bi_run(ctx, -1, &one) : tspb200_fi_run(ctx, -1, &one);
+        if (rc) return rc;
+        double cost = 0;
+        rc = tspb200_tour_download(ctx, s, &cost);
+        if (rc) return rc;
+        if (obj) obj[b] = mode == TSPB200_BI ? cost : obj[b] + (double)one.obj_delta;
+        if (want_log || (log_count && batch == 1)) {
+            rc = tspb200_tour_log(ctx, log, log_cap, log_count);
+            if (rc) return rc;
+        }
+        total.passes += one.passes; total.moves += one.moves; total.evals += one.evals; total.launches += one.launches;
+        total.obj_delta += one.obj_delta; total.gpu_ms += one.gpu_ms; total.path = one.path;
+        total.tiles_scanned += one.tiles_scanned; total.tiles_total += one.tiles_total;
+    }
+    total.status = TSPB200_LOCAL_OPTIMUM;
+    if (batch == 1) total.cost = obj ? obj[0] : 0.0;
+    if (st) *st = total;
+    if (log_count && batch != 1) *log_count = 0;
+    ctx->has_tour = false;
     return TSPB200_OK;
 }
 
@@ -1292,7 +1368,7 @@ int tspb200_nn_tour_batch(tspb200_ctx *ctx, const int32_t *starts, int batch, in
     if (path == 2 && !ctx->d_mat) path = 1;
     InstDev I = inst_for_path(ctx, path == 2 ? 2 : 1);
     I.fp32_ok = ctx->inst.fp32_ok;  // the FP32 filter of the batched kernel is valid whenever the 2-opt filter is
-    const float eps = (ctx->inst.W - 2.0f) * 0.5f;
+    const float eps = ctx->eps32;
     SCRATCH(d_starts, int *, 9, sizeof(int) * (size_t)batch);
     SCRATCH(d_cost, long long *, 10, sizeof(long long) * (size_t)batch);
     int *d_succ = nullptr;
@@ -1347,12 +1423,305 @@ int tspb200_tour_costs(tspb200_ctx *ctx, const int32_t *tours, int batch, int as
     SCRATCH(d_t, int *, 14, sizeof(int) * (size_t)n * batch);
     SCRATCH(d_o, long long *, 15, sizeof(long long) * (size_t)batch);
     CK(cudaMemcpyAsync(d_t, tours, sizeof(int) * (size_t)n * batch, cudaMemcpyHostToDevice, ctx->stream));
-    cudaError_t le = launch_tour_cost(I, d_t, as_order, d_o, batch, ctx->stream);
+    cudaError_t le = launch_tour_cost(I, d_t, nullptr, as_order, d_o, batch, ctx->stream);
     std::vector<long long> h((size_t)batch);
     if (le == cudaSuccess) le = cudaMemcpyAsync(h.data(), d_o, sizeof(long long) * (size_t)batch, cudaMemcpyDeviceToHost, ctx->stream);
     if (le == cudaSuccess) le = cudaStreamSynchronize(ctx->stream);
     if (le != cudaSuccess) return fail(ctx, TSPB200_E_CUDA, "tour cost kernel failed: %s", cudaGetErrorString(le));
     for (int b = 0; b < batch; ++b) out[b] = (double)h[b];
+    return TSPB200_OK;
+}
+
+// ---- resident sessions -----------------------------------------------------------------------------------------
+// The callers of the 2-opt path (reference HEU_VNS src/vns.c:103-183, tabu() src/tabusearch.c:188-320, HEU_Genetic
+// src/genetic.c:445-560) alternate a small perturbation with a 2-opt run.  These entry points keep the tour / the tabu
+// list / the population in HBM across those steps; the caller keeps the random number generator and the control flow.
+
+int tspb200_tour_cost(tspb200_ctx *ctx, double *cost) { return tspb200_tour_download(ctx, nullptr, cost); }
+
+// Saves / restores the resident tour (position-space records + positions) in one of two device slots: the "best solution so
+// far" copies of reference vns.c:121-122,171-173 and tabusearch.c:241-243,313-314 without leaving the device.
+int tspb200_tour_save(tspb200_ctx *ctx, int slot) {
+    if (!ctx || !ctx->stream) return fail(ctx, TSPB200_E_CUDA, "context has no CUDA device");
+    if (!ctx->has_tour) return fail(ctx, TSPB200_E_STATE, "no tour uploaded");
+    if (slot < 0 || slot > 1) return fail(ctx, TSPB200_E_ARG, "slot must be 0 or 1");
+    CK(cudaSetDevice(ctx->device));
+    const int n = ctx->n, alloc = ctx->tour.alloc;
+    if (ctx->save_alloc[slot] < alloc) {
+        cudaFree(ctx->save_rec[slot]); cudaFree(ctx->save_pos[slot]);
+        ctx->save_rec[slot] = nullptr; ctx->save_pos[slot] = nullptr;
+        ctx->save_alloc[slot] = 0;
+        CK(cudaMalloc(&ctx->save_rec[slot], sizeof(float4) * (size_t)alloc));
+        CK(cudaMalloc(&ctx->save_pos[slot], sizeof(int) * (size_t)alloc));
+        ctx->save_alloc[slot] = alloc;
+    }
+    CK(cudaMemcpyAsync(ctx->save_rec[slot], ctx->tour.rec, sizeof(float4) * (size_t)alloc, cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->save_pos[slot], ctx->tour.pos, sizeof(int) * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
+    ctx->save_n[slot] = n;
+    return TSPB200_OK;
+}
+
+int tspb200_tour_restore(tspb200_ctx *ctx, int slot) {
+    if (!ctx || !ctx->stream) return fail(ctx, TSPB200_E_CUDA, "context has no CUDA device");
+    if (!ctx->has_tour) return fail(ctx, TSPB200_E_STATE, "no tour uploaded");
+    if (slot < 0 || slot > 1 || ctx->save_n[slot] != ctx->n || ctx->save_alloc[slot] < ctx->tour.alloc)
+        return fail(ctx, TSPB200_E_STATE, "nothing saved in slot %d for this tour", slot);
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(ctx->tour.rec, ctx->save_rec[slot], sizeof(float4) * (size_t)ctx->tour.alloc, cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->tour.pos, ctx->save_pos[slot], sizeof(int) * (size_t)ctx->n, cudaMemcpyDeviceToDevice, ctx->stream));
+    ctx->node_dirty = true;  // node-space tables are rebuilt from the records on the next first-improvement run
+    ctx->fi_cursor_stale = true;
+    ctx->tour_changed = true;
+    return TSPB200_OK;
+}
+
+// reference src/vns.c:11-100 kick(): idx1, idx2, idx3 are the three tour indices the reference draws with rand_choice
+// (in any order; they are sorted here like vns.c:34-50).  *cost (may be NULL) = the recomputed tour cost (vns.c:78-86).
+int tspb200_vns_kick(tspb200_ctx *ctx, int idx1, int idx2, int idx3, double *cost) {
+    if (!ctx || !ctx->stream) return fail(ctx, TSPB200_E_CUDA, "context has no CUDA device");
+    if (!ctx->has_tour) return fail(ctx, TSPB200_E_STATE, "no tour uploaded");
+    const int n = ctx->n;
+    if (idx1 > idx2) std::swap(idx1, idx2);
+    if (idx1 > idx3) std::swap(idx1, idx3);
+    if (idx2 > idx3) std::swap(idx2, idx3);
+    if (idx1 < 0 || idx3 >= n || idx2 - idx1 < 2 || idx3 - idx2 < 2)
+        return fail(ctx, TSPB200_E_ARG, "kick indices must be distinct, non-adjacent tour indices in [0, n) (reference vns.c:25-31)");
+    CK(cudaSetDevice(ctx->device));
+    int path = select_path(ctx);
+    if (path == 2 && !ctx->d_mat) path = 1;
+    InstDev I = inst_for_path(ctx, path);
+    SCRATCH(d_scr, float4 *, 3, sizeof(float4) * (size_t)n);
+    CK(launch_vns_kick(I, ctx->tour, idx1, idx2, idx3, d_scr, ctx->stream));
+    ctx->fi_cursor_stale = true;  // the next alg_2opt starts a fresh sweep on the kicked tour
+    ctx->tour_changed = true;
+    if (cost) return tspb200_tour_cost(ctx, cost);
+    return TSPB200_OK;
+}
+
+// reference tabu() src/tabusearch.c:188-320 with the tabu list resident in HBM.
+int tspb200_tabu_begin(tspb200_ctx *ctx) {
+    if (!ctx || !ctx->stream) return fail(ctx, TSPB200_E_CUDA, "context has no CUDA device");
+    if (ctx->n < 1) return fail(ctx, TSPB200_E_STATE, "no instance");
+    const int n = ctx->n;
+    if (n > 46340) return fail(ctx, TSPB200_E_UNSUPPORTED, "tabu list index overflows int for n=%d (reference limit)", n);
+    CK(cudaSetDevice(ctx->device));
+    const long long len = (long long)n * (n - 1) / 2;
+    if (ctx->skip_cap < len || !ctx->d_zl_count) {
+        cudaFree(ctx->d_skip); cudaFree(ctx->d_zl); cudaFree(ctx->d_zl_count);
+        ctx->d_skip = nullptr; ctx->d_zl = nullptr; ctx->d_zl_count = nullptr;
+        ctx->skip_cap = 0;
+        ctx->zl_cap = len < (1ll << 22) ? len : (1ll << 22);
+        CK(cudaMalloc(&ctx->d_skip, sizeof(int) * (size_t)(len > 0 ? len : 1)));
+        CK(cudaMalloc(&ctx->d_zl, sizeof(long long) * (size_t)(ctx->zl_cap > 0 ? ctx->zl_cap : 1)));
+        CK(cudaMalloc(&ctx->d_zl_count, sizeof(unsigned long long)));
+        ctx->skip_cap = len;
+    }
+    CK(cudaMemsetAsync(ctx->d_skip, 0, sizeof(int) * (size_t)(len > 0 ? len : 1), ctx->stream));  // CALLOC, tabusearch.c:196
+    CK(cudaMemsetAsync(ctx->d_zl_count, 0, sizeof(unsigned long long), ctx->stream));
+    ctx->tabu_session = true;
+    return TSPB200_OK;
+}
+
+// alg_2opt_tabu(inst, tabu_edge, prev, iter, tenure) on the resident tour and the resident list (tabusearch.c:238)
+int tspb200_tabu_run(tspb200_ctx *ctx, int iter, int tenure, int64_t max_passes, tspb200_stats *st) {
+    if (!ctx || !ctx->stream) return fail(ctx, TSPB200_E_CUDA, "context has no CUDA device");
+    if (!ctx->tabu_session) return fail(ctx, TSPB200_E_STATE, "no tabu session (tspb200_tabu_begin)");
+    if (!ctx->has_tour) return fail(ctx, TSPB200_E_STATE, "no tour uploaded");
+    const long long keep = ctx->zl_cap;
+    ctx->zl_cap = 0;  // the list never leaves the device: nothing to replay on a host copy
+    ctx->tabu_on = true;
+    ctx->tabu_iter = iter;
+    ctx->tabu_tenure = tenure;
+    ctx->tour_changed = true;  // a new call is a new search: whatever ended the previous one does not hold for this iter/tenure
+    int rc = tspb200_bi_run(ctx, max_passes, st);
+    ctx->tabu_on = false;
+    ctx->zl_cap = keep;
+    if (rc) return rc;
+    if (st) {
+        double cost = 0;
+        rc = tspb200_tour_cost(ctx, &cost);  // tabusearch.c:168-172
+        if (rc) return rc;
+        st->cost = cost;
+    }
+    return TSPB200_OK;
+}
+
+// The random kick of tabusearch.c:262-309: `pairs` = count candidate (a, b) node pairs in the order the caller drew them;
+// the first one that passes the reference's tests is applied as a 2-opt move and its two removed edges become tabu.
+// *accepted = its index, or -1 when every candidate was rejected (draw more and call again).
+int tspb200_tabu_kick(tspb200_ctx *ctx, const int32_t *pairs, int count, int iter, int tenure, int *accepted) {
+    if (!ctx || !ctx->stream) return fail(ctx, TSPB200_E_CUDA, "context has no CUDA device");
+    if (!ctx->tabu_session) return fail(ctx, TSPB200_E_STATE, "no tabu session (tspb200_tabu_begin)");
+    if (!ctx->has_tour) return fail(ctx, TSPB200_E_STATE, "no tour uploaded");
+    if (!pairs || count < 1 || !accepted) return fail(ctx, TSPB200_E_ARG, "bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    int path = ctx->d_mat ? 2 : 1;
+    InstDev I = inst_for_path(ctx, path);
+    SCRATCH(d_pairs, int *, 9, sizeof(int) * 2 * (size_t)count + sizeof(int));
+    int *d_acc = d_pairs + 2 * (size_t)count;
+    CK(cudaMemcpyAsync(d_pairs, pairs, sizeof(int) * 2 * (size_t)count, cudaMemcpyHostToDevice, ctx->stream));
+    CK(launch_tabu_kick_select(ctx->tour, ctx->d_skip, d_pairs, count, iter, tenure, d_acc, ctx->stream));
+    CK(launch_apply_move(I, ctx->tour, ctx->num_sms, 0, 0, false, ctx->stream));
+    int acc = -1;
+    CK(cudaMemcpyAsync(&acc, d_acc, sizeof acc, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (acc == -2) return fail(ctx, TSPB200_E_ARG, "kick candidate out of range");
+    *accepted = acc;
+    if (acc >= 0) {
+        ctx->node_dirty = true;
+        ctx->fi_cursor_stale = true;
+        ctx->tour_changed = true;
+    }
+    return TSPB200_OK;
+}
+
+int tspb200_tabu_end(tspb200_ctx *ctx, int32_t *skip_out) {
+    if (!ctx || !ctx->stream) return fail(ctx, TSPB200_E_CUDA, "context has no CUDA device");
+    if (!ctx->tabu_session) return fail(ctx, TSPB200_E_STATE, "no tabu session");
+    CK(cudaSetDevice(ctx->device));
+    if (skip_out) {
+        const long long len = (long long)ctx->n * (ctx->n - 1) / 2;
+        CK(cudaMemcpyAsync(skip_out, ctx->d_skip, sizeof(int) * (size_t)len, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    ctx->tabu_session = false;
+    return TSPB200_OK;
+}
+
+// ---- resident population (reference HEU_Genetic, src/genetic.c): tours stay in HBM as successor arrays --------------
+static int pop_slots_to_device(tspb200_ctx *ctx, const int32_t *slots, int count, int **d_slots) {
+    *d_slots = nullptr;
+    if (!slots) return TSPB200_OK;
+    for (int k = 0; k < count; ++k)
+        if (slots[k] < 0 || slots[k] >= ctx->pop_count) return fail(ctx, TSPB200_E_ARG, "population slot %d out of range", slots[k]);
+    SCRATCH(d, int *, 10, sizeof(int) * (size_t)count);
+    CK(cudaMemcpyAsync(d, slots, sizeof(int) * (size_t)count, cudaMemcpyHostToDevice, ctx->stream));
+    *d_slots = d;
+    return TSPB200_OK;
+}
+
+// Creates (count tours, slots == NULL) or updates (the listed slots) the resident population.  as_order != 0: tours are
+// chromosomes (visiting orders, genetic.c:22-26), converted on the device (from_chromosome_to_edges, genetic.c:34-44).
+int tspb200_population_upload(tspb200_ctx *ctx, const int32_t *tours, const int32_t *slots, int count, int as_order) {
+    if (!ctx || !ctx->stream) return fail(ctx, TSPB200_E_CUDA, "context has no CUDA device");
+    if (ctx->n < 1) return fail(ctx, TSPB200_E_STATE, "no instance");
+    if (!tours || count < 1) return fail(ctx, TSPB200_E_ARG, "bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    const int n = ctx->n;
+    if (!slots) {
+        if (count > ctx->pop_cap || ctx->pop_n != n) {
+            CK(cudaStreamSynchronize(ctx->stream));
+            cudaFree(ctx->d_pop);
+            ctx->d_pop = nullptr;
+            ctx->pop_cap = 0;
+            CK(cudaMalloc(&ctx->d_pop, sizeof(int) * (size_t)n * (size_t)count));
+            ctx->pop_cap = count;
+            ctx->pop_n = n;
+        }
+        ctx->pop_count = count;
+    } else if (ctx->pop_count < 1 || ctx->pop_n != n) {
+        return fail(ctx, TSPB200_E_STATE, "no resident population");
+    }
+    int *d_slots = nullptr;
+    int rc = pop_slots_to_device(ctx, slots, count, &d_slots);
+    if (rc) return rc;
+    SCRATCH(d_stage, int *, 0, sizeof(int) * (size_t)n * (size_t)count);
+    CK(cudaMemcpyAsync(d_stage, tours, sizeof(int) * (size_t)n * (size_t)count, cudaMemcpyHostToDevice, ctx->stream));
+    CK(launch_population_store(d_stage, ctx->d_pop, d_slots, n, count, as_order, ctx->stream));
+    return TSPB200_OK;
+}
+
+int tspb200_population_download(tspb200_ctx *ctx, int32_t *tours, const int32_t *slots, int count, int as_order) {
+    if (!ctx || !ctx->stream) return fail(ctx, TSPB200_E_CUDA, "context has no CUDA device");
+    if (ctx->pop_count < 1 || ctx->pop_n != ctx->n) return fail(ctx, TSPB200_E_STATE, "no resident population");
+    if (!tours || count < 1 || (!slots && count > ctx->pop_count)) return fail(ctx, TSPB200_E_ARG, "bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    const int n = ctx->n;
+    int *d_slots = nullptr;
+    int rc = pop_slots_to_device(ctx, slots, count, &d_slots);
+    if (rc) return rc;
+    SCRATCH(d_stage, int *, 0, sizeof(int) * (size_t)n * (size_t)count);
+    CK(launch_population_fetch(ctx->d_pop, d_slots, d_stage, n, count, as_order, ctx->stream));
+    CK(cudaMemcpyAsync(tours, d_stage, sizeof(int) * (size_t)n * (size_t)count, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return TSPB200_OK;
+}
+
+// fitness() (genetic.c:51-60) of the listed slots (all when slots == NULL): only `count` doubles cross the bus
+int tspb200_population_costs(tspb200_ctx *ctx, const int32_t *slots, int count, double *out) {
+    if (!ctx || !ctx->stream) return fail(ctx, TSPB200_E_CUDA, "context has no CUDA device");
+    if (ctx->pop_count < 1 || ctx->pop_n != ctx->n) return fail(ctx, TSPB200_E_STATE, "no resident population");
+    if (!out || count < 1 || (!slots && count > ctx->pop_count)) return fail(ctx, TSPB200_E_ARG, "bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    int path = select_path(ctx);
+    if (path == 2 && !ctx->d_mat) path = 1;
+    InstDev I = inst_for_path(ctx, path == 2 ? 2 : 1);
+    int *d_slots = nullptr;
+    int rc = pop_slots_to_device(ctx, slots, count, &d_slots);
+    if (rc) return rc;
+    SCRATCH(d_o, long long *, 15, sizeof(long long) * (size_t)count);
+    CK(launch_tour_cost(I, ctx->d_pop, d_slots, 0, d_o, count, ctx->stream));
+    std::vector<long long> h((size_t)count);
+    CK(cudaMemcpyAsync(h.data(), d_o, sizeof(long long) * (size_t)count, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int b = 0; b < count; ++b) out[b] = (double)h[(size_t)b];
+    return TSPB200_OK;
+}
+
+// alg_2opt (mode FI, genetic.c:435) / best improvement on the listed slots in place.  obj (count doubles, may be NULL):
+// FI adds the applied deltas to the incoming values, BI overwrites them with the recomputed costs.
+int tspb200_population_two_opt(tspb200_ctx *ctx, int mode, const int32_t *slots, int count, double *obj, tspb200_stats *st) {
+    if (!ctx || !ctx->stream) return fail(ctx, TSPB200_E_CUDA, "context has no CUDA device");
+    if (ctx->pop_count < 1 || ctx->pop_n != ctx->n) return fail(ctx, TSPB200_E_STATE, "no resident population");
+    if (mode != TSPB200_FI && mode != TSPB200_BI) return fail(ctx, TSPB200_E_ARG, "mode must be TSPB200_FI or TSPB200_BI");
+    if (count < 1 || (!slots && count > ctx->pop_count)) return fail(ctx, TSPB200_E_ARG, "bad arguments");
+    if (!(ctx->dist_bound < 16777216.0)) return fail(ctx, TSPB200_E_UNSUPPORTED, "distances >= 2^24 are not supported by the 2-opt kernels");
+    CK(cudaSetDevice(ctx->device));
+    const int path = select_path(ctx);
+    if (path == 2 && !ctx->d_mat) return fail(ctx, TSPB200_E_STATE, "matrix path selected but no resident matrix");
+    InstDev I = inst_for_path(ctx, path);
+    int *d_slots = nullptr;
+    int rc = pop_slots_to_device(ctx, slots, count, &d_slots);
+    if (rc) return rc;
+    SCRATCH(d_delta, long long *, 1, sizeof(long long) * (size_t)count);
+    SCRATCH(d_cnt, long long *, 2, sizeof(long long) * 4 * (size_t)count);
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    CK(cudaMemsetAsync(d_delta, 0, sizeof(long long) * (size_t)count, ctx->stream));
+    CK(cudaMemsetAsync(d_cnt, 0, sizeof(long long) * 4 * (size_t)count, ctx->stream));
+    int launched = 0;
+    cudaError_t le = cudaErrorNotSupported;
+    if (mode == TSPB200_BI && path == 0 && ctx->opt_batch_kernel != 1)
+        le = launch_two_opt_batch_bi_pos(I, ctx->d_pop, d_slots, d_delta, d_cnt, count, ctx->num_sms, ctx->stream, &launched, nullptr, 0);
+    if (le == cudaErrorNotSupported)
+        le = launch_two_opt_batch(I, mode, ctx->d_pop, d_slots, d_delta, d_cnt, count, ctx->num_sms, ctx->stream, &launched, nullptr, 0);
+    if (le == cudaErrorInvalidValue)
+        return fail(ctx, TSPB200_E_UNSUPPORTED, "resident populations use the one-block kernels: n=%d does not fit (use tspb200_two_opt_batch)", ctx->n);
+    if (le != cudaSuccess) return fail(ctx, TSPB200_E_CUDA, "batched 2-opt launch failed: %s", cudaGetErrorString(le));
+    std::vector<long long> h_delta((size_t)count), h_cnt((size_t)count * 4);
+    CK(cudaMemcpyAsync(h_delta.data(), d_delta, sizeof(long long) * (size_t)count, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(h_cnt.data(), d_cnt, sizeof(long long) * 4 * (size_t)count, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    tspb200_stats local;
+    memset(&local, 0, sizeof local);
+    for (int b = 0; b < count; ++b) {
+        if (h_cnt[4 * (size_t)b + 3]) return fail(ctx, TSPB200_E_DEVICE_CHECK, "population slot %d does not hold a single cycle", slots ? slots[b] : b);
+        local.moves += h_cnt[4 * (size_t)b + 0];
+        local.passes += h_cnt[4 * (size_t)b + 1];
+        local.evals += h_cnt[4 * (size_t)b + 2];
+        if (mode == TSPB200_FI) local.obj_delta += h_delta[(size_t)b];
+        if (obj) {
+            if (mode == TSPB200_BI) obj[b] = (double)h_delta[(size_t)b];
+            else obj[b] += (double)h_delta[(size_t)b];
+        }
+    }
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    local.gpu_ms = ms;
+    local.launches = launched;
+    local.path = path;
+    local.status = TSPB200_LOCAL_OPTIMUM;
+    if (st) *st = local;
     return TSPB200_OK;
 }
 

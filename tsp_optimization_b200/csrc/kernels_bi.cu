@@ -100,7 +100,7 @@ __device__ __noinline__ MoveKey bi_cold_warp(const InstDev I, const float4 *rec,
 // Shared memory per block (dynamic): two column buffers (TJ+2 records) filled by TMA bulk copies, one mbarrier per stage,
 // plus the tile tables.  Row records go straight from L2 into registers: a thread's R+1 rows are 16*(R+1) contiguous bytes,
 // and reading them through shared memory would put all lanes of a quarter-warp on the same banks (stride 16*R bytes).
-template <int BI_THREADS, int R, bool ATT, bool EXACT32>
+template <int BI_THREADS, int R, bool ATT, bool EXACT32, bool PRUNED>
 __global__ void __launch_bounds__(BI_THREADS, (R >= 16 ? (BI_THREADS == 256 ? 1 : 384 / BI_THREADS) : 512 / BI_THREADS)) bi_scan_kernel(const BiArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long bars[2];
@@ -121,6 +121,7 @@ __global__ void __launch_bounds__(BI_THREADS, (R >= 16 ? (BI_THREADS == 256 ? 1 
     const float4 *rec = A.tour.rec;
     float4 *scols0 = reinterpret_cast<float4 *>(smem_raw);
     float4 *scols1 = scols0 + (TJ + 2);
+    const unsigned col_bytes = (unsigned)(TJ + 1) * 16u;
 
     // tile tables -> shared memory (one coalesced L2 round trip instead of a dependent chain per binary-search step)
     int *s_rs = reinterpret_cast<int *>(scols1 + (TJ + 2));  // [ntr+1] prefix sums of tiles per tile-row
@@ -168,7 +169,10 @@ __global__ void __launch_bounds__(BI_THREADS, (R >= 16 ? (BI_THREADS == 256 ? 1 
     // the tile ids r, r + world, ...; every tile costs the same — masked and padded pairs are computed too), so the blocks
     // run dry within one tile of each other whatever slows some of them down (exact-path calls, the far die's L2
     // latency).  Static dealing left the SMs idle ~10 % of a pass once a pass is only ~5 tiles deep (8 ranks).
-    __shared__ int s_tile[2][4];  // [stage] = {P0, Q0, valid, columns}, written by thread 0 one tile ahead
+    // [stage] = {P0, Q0, valid, columns}, written by thread 0 one tile ahead.  The 4th word (the tile width, TJ for every tile)
+    // keeps a stage 16 bytes; with the 12-byte layout ptxas moved the hot loop's counter and shared-memory addresses from the
+    // uniform datapath into vector registers (+5 % pass time at n = 100 000; tests/test_codegen.py watches the SASS)
+    __shared__ __align__(16) int s_tile[2][4];
 
     // tile id -> (tile row I, tile column J)
     auto decode = [&](int t, int &P0, int &Q0) {
@@ -186,68 +190,49 @@ __global__ void __launch_bounds__(BI_THREADS, (R >= 16 ? (BI_THREADS == 256 ? 1 
     // Exact tile pruning (A.pruned): the tiles come from this rank's live list (tile_filter_kernel); a live tile whose lower
     // bound meanwhile exceeds the best exact delta found in this pass is dropped at the draw (it cannot hold the argmin
     // nor a tie: ties need delta == best).
-    // Tail smoothing (A.split_factor F > 1): this rank's last A.split_tiles tiles are handed out as F sub-tiles of TJ/F
-    // columns each, so that the blocks run dry within a sub-tile of each other instead of a whole tile (at 8 ranks a pass
-    // is only ~8 tiles deep and the last-tile spread was ~15 % of it).  Draw index kl < whole: tile kl, all TJ columns;
-    // otherwise k2 = kl - whole: tile whole + k2 / F, columns [(k2 % F) * TJ / F, +TJ / F).
-    const long long tiles_own = A.pruned ? (long long)__ldcg(&ctl->live_count)
-                                         : ((long long)A.ntiles - A.rank + A.world - 1) / A.world;
-    const int F = (A.pruned || A.split_factor < 2) ? 1 : A.split_factor;
-    const long long split = F > 1 ? (A.split_tiles < tiles_own ? (long long)A.split_tiles : tiles_own) : 0;
-    const long long whole = tiles_own - split;
-    const long long tiles_rank = whole + split * F;  // number of draws
-    unsigned scanned = 0;    // thread 0: tiles this block really scanned (statistics of the pruned mode)
-    long long next_kl = -1;  // thread 0: draw index fetched ahead of its use (the atomic's latency stays off the critical path)
-    auto fetch = [&]() {
-        next_kl = tiles_rank > (long long)gridDim.x ? (long long)gridDim.x + (long long)atomicAdd(&ctl->tile_next, 1u) : tiles_rank;
-    };
+    // Exact tile pruning (PRUNED): the tiles come from this rank's live list (tile_filter_kernel); a live tile whose lower
+    // bound meanwhile exceeds the best exact delta found in this pass is dropped at the draw (it cannot hold the argmin nor
+    // a tie: ties need delta == best).  The exhaustive kernel keeps the loop-free draw: a loop inside this thread-0-only
+    // region makes the compiler give up the uniform datapath for the hot loop's counter and shared-memory addresses
+    // (+4 % pass time at n = 100 000, measured).
+    const long long tiles_rank = PRUNED ? (long long)__ldcg(&ctl->live_count)
+                                        : ((long long)A.ntiles - A.rank + A.world - 1) / A.world;
+    unsigned scanned = 0;  // thread 0: tiles this block really scanned (statistics of the pruned mode)
     auto draw = [&](int b, bool first) {
-        int P = 0, Q = 0, valid = 0, nc = TJ;
-        for (;;) {
-            long long kl = first ? (long long)blockIdx.x : next_kl;
-            if (kl >= tiles_rank) break;
-            long long tl = kl;
-            int sub = 0;
-            if (kl >= whole) {
-                const long long k2 = kl - whole;
-                tl = whole + k2 / F;
-                sub = (int)(k2 % F);
-                nc = TJ / F;
+        int P = 0, Q = 0, valid = 0;
+        if (!PRUNED) {
+            long long kl = first ? (long long)blockIdx.x : tiles_rank;
+            if (!first && tiles_rank > (long long)gridDim.x) kl = (long long)gridDim.x + (long long)atomicAdd(&ctl->tile_next, 1u);
+            if (kl < tiles_rank) {
+                decode((int)((long long)A.rank + (long long)A.world * kl), P, Q);
+                valid = 1;
             }
-            int t;
-            if (A.pruned) {
-                if (__ldg(&A.tour.live_lb[tl]) > (float)(*((volatile int *)&s_hint))) {
-                    first = false;
-                    fetch();
-                    continue;
-                }
-                t = __ldg(&A.tour.live[tl]);
-            } else {
-                t = (int)((long long)A.rank + (long long)A.world * tl);
-            }
-            decode(t, P, Q);
-            Q += sub * nc;
-            valid = Q <= n - 1 ? 1 : 0;  // a sub-tile of the last tile column may lie entirely behind the tour
-            if (!valid) {
+        } else {
+            for (;;) {
+                long long kl = first ? (long long)blockIdx.x : tiles_rank;
+                if (!first && tiles_rank > (long long)gridDim.x) kl = (long long)gridDim.x + (long long)atomicAdd(&ctl->tile_next, 1u);
+                if (kl >= tiles_rank) break;
                 first = false;
-                fetch();
-                continue;
+                if (__ldg(&A.tour.live_lb[kl]) > (float)(*((volatile int *)&s_hint))) continue;
+                decode(__ldg(&A.tour.live[kl]), P, Q);
+                valid = 1;
+                scanned += 1;
+                break;
             }
-            scanned += 1;
-            mbar_expect_tx(&bars[b], (unsigned)(nc + 1) * 16u);
-            tma_load_1d(b ? scols1 : scols0, rec + Q, (unsigned)(nc + 1) * 16u, &bars[b]);
-            break;
+        }
+        if (valid) {
+            mbar_expect_tx(&bars[b], col_bytes);
+            tma_load_1d(b ? scols1 : scols0, rec + Q, col_bytes, &bars[b]);
         }
         s_tile[b][0] = P;
         s_tile[b][1] = Q;
         s_tile[b][2] = valid;
-        s_tile[b][3] = nc;
-        if (valid) fetch();  // for the draw after this one
+        s_tile[b][3] = TJ;
     };
 
     if (tid == 0) draw(0, true);
     __syncthreads();
-    int P0 = s_tile[0][0], Q0 = s_tile[0][1], NC = s_tile[0][3];
+    int P0 = s_tile[0][0], Q0 = s_tile[0][1], NCv = s_tile[0][3];
     bool have = s_tile[0][2] != 0;
 
     for (int it = 0; have; ++it) {
@@ -282,6 +267,7 @@ __global__ void __launch_bounds__(BI_THREADS, (R >= 16 ? (BI_THREADS == 256 ? 1 
 
         // pairs with q < p+2 exist in this tile?  (mask them; they are mirrored / adjacent pairs)
         const bool diag = (Q0 < P0 + TI + 1);
+        const int NC = PRUNED ? NCv : TJ;  // columns of this tile
         // In a diagonal tile a warp starts at the first column that holds a legal pair for its FIRST row (q >= p + 2), rounded
         // down to the filter granularity: the columns before are masked for all its rows.  Diagonal tiles thus cost about
         // half a regular tile instead of ~1.3 of one — they were the stragglers of a one-wave pass (n ~ 10^4).
@@ -291,14 +277,17 @@ __global__ void __launch_bounds__(BI_THREADS, (R >= 16 ? (BI_THREADS == 256 ? 1 
             jbeg = jbeg < 0 ? 0 : (jbeg & ~(BI_CB - 1));
             if (jbeg > NC) jbeg = NC;
         }
-        float4 c0 = sc[jbeg];
+        // first column of the scan: D0 -> U2 (kept per variant so that the regular tile's shared-memory addressing stays uniform)
+        float4 c0, cnext;
         f32x2 U2[R / 2];
-        {
-            float D0[R + 1];
-            column_dists<R, ATT>(xr2, yr2, xrl, yrl, c0.x, c0.y, D0);
-#pragma unroll
-            for (int k = 0; k < R / 2; ++k) U2[k] = f2add(f2pack(D0[2 * k], D0[2 * k + 1]), cp2[k]);
-        }
+#define BI_INIT(JB)                                                                                    \
+    {                                                                                                  \
+        c0 = sc[(JB)];                                                                                 \
+        cnext = sc[(JB) + 1];                                                                          \
+        float D0[R + 1];                                                                               \
+        column_dists<R, ATT>(xr2, yr2, xrl, yrl, c0.x, c0.y, D0);                                      \
+        _Pragma("unroll") for (int k = 0; k < R / 2; ++k) U2[k] = f2add(f2pack(D0[2 * k], D0[2 * k + 1]), cp2[k]); \
+    }
 #define UU(r_) (((r_) & 1) ? f2hi(U2[(r_) >> 1]) : f2lo(U2[(r_) >> 1]))
 
 // one column: R+1 fresh distances -> R move deltas Q[r] = (D[p_r][q] - ds_p) + D[p_r+1][q+1]; the filter quantity
@@ -323,7 +312,7 @@ __global__ void __launch_bounds__(BI_THREADS, (R >= 16 ? (BI_THREADS == 256 ? 1 
 
 // BI_CB columns, then ONE filter check per warp (ballot); hits are resolved one lane at a time by the whole warp
 #define BI_BLOCK(DIAG)                                                                                 \
-    for (int jj = jbeg; jj < NC; jj += BI_CB) {                                                        \
+    for (int jj = (DIAG) ? jbeg : 0; jj < NC; jj += BI_CB) {                                           \
         float M = TSPB_BIG;                                                                            \
         _Pragma("unroll") for (int c = 0; c < BI_CB; ++c) BI_COL(DIAG, jj + c)                         \
         unsigned hits = __ballot_sync(0xffffffffu, M <= thr);                                          \
@@ -356,12 +345,14 @@ __global__ void __launch_bounds__(BI_THREADS, (R >= 16 ? (BI_THREADS == 256 ? 1 
     }
 
         const int qrel0 = Q0 - p0;  // q - p0 at jj = 0
-        float4 cnext = sc[jbeg + 1];
         if (!diag) {
+            BI_INIT(0)
             BI_BLOCK(false)
         } else {
+            BI_INIT(jbeg)
             BI_BLOCK(true)
         }
+#undef BI_INIT
 #undef BI_BLOCK
 #undef BI_COL
 #undef UU
@@ -372,7 +363,7 @@ __global__ void __launch_bounds__(BI_THREADS, (R >= 16 ? (BI_THREADS == 256 ? 1 
         P0 = s_tile[buf ^ 1][0];
         Q0 = s_tile[buf ^ 1][1];
         have = s_tile[buf ^ 1][2] != 0;
-        NC = s_tile[buf ^ 1][3];
+        NCv = s_tile[buf ^ 1][3];
     }
 
     // ---- block argmin -> grid argmin ("last block done") -------------------------------------------
@@ -387,7 +378,7 @@ __global__ void __launch_bounds__(BI_THREADS, (R >= 16 ? (BI_THREADS == 256 ? 1 
         if (tid == 0) {
             A.tour.block_best[blockIdx.x] = k;
             if (A.packed_tail && k.delta < 0) atomicMin(&ctl->pass_min, key_pack(k.delta, k.i, k.j));
-            if (A.pruned && scanned) atomicAdd(&ctl->tiles_scanned, (unsigned long long)scanned);
+            if (PRUNED && scanned) atomicAdd(&ctl->tiles_scanned, (unsigned long long)scanned);
             if (A.timing) {
                 const unsigned long long t = globaltimer_ns();
                 atomicMin(&ctl->tm_blk_end_min, t);
@@ -853,14 +844,9 @@ static cudaError_t launch_bi_tr(const BiArgs &a, int grid, bool pdl, cudaStream_
     const bool att = (a.inst.metric == M_ATT);
     const bool ex = a.inst.exact32 != 0;
     auto go = [&](auto kern) -> cudaError_t {
-        // opt in to > 48 KB of dynamic shared memory once per (kernel instantiation, device)
-        static bool attr_set[64] = {};
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (!attr_set[dev & 63]) {
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (smem > 48 * 1024) {  // opt in to more dynamic shared memory than the default limit (never at the supported tile widths)
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
-            attr_set[dev & 63] = true;
         }
         if (!pdl) {
             kern<<<grid, T, smem, st>>>(a);
@@ -878,10 +864,16 @@ static cudaError_t launch_bi_tr(const BiArgs &a, int grid, bool pdl, cudaStream_
         cfg.numAttrs = 1;
         return cudaLaunchKernelEx(&cfg, kern, a);
     };
-    if (att && ex) return go(bi_scan_kernel<T, R, true, true>);
-    if (att) return go(bi_scan_kernel<T, R, true, false>);
-    if (ex) return go(bi_scan_kernel<T, R, false, true>);
-    return go(bi_scan_kernel<T, R, false, false>);
+    if (a.pruned) {
+        if (att && ex) return go(bi_scan_kernel<T, R, true, true, true>);
+        if (att) return go(bi_scan_kernel<T, R, true, false, true>);
+        if (ex) return go(bi_scan_kernel<T, R, false, true, true>);
+        return go(bi_scan_kernel<T, R, false, false, true>);
+    }
+    if (att && ex) return go(bi_scan_kernel<T, R, true, true, false>);
+    if (att) return go(bi_scan_kernel<T, R, true, false, false>);
+    if (ex) return go(bi_scan_kernel<T, R, false, true, false>);
+    return go(bi_scan_kernel<T, R, false, false, false>);
 }
 
 // supported (threads, rows per thread) shapes; anything else is rejected by tspb200_set_option

@@ -269,10 +269,11 @@ cudaError_t launch_export_state(const TourDev &T, int *succ, unsigned long long 
 
 // ---- batched tour cost (reference src/genetic.c:51-60 fitness; src/tabusearch.c:168-172) -----------------
 // tours[b*n + k]: as_order != 0 -> visiting order (chromosome), else successor array. One block per tour.
-__global__ void __launch_bounds__(256) tour_cost_kernel(const InstDev I, const int *tours, int as_order, long long *out) {
+__global__ void __launch_bounds__(256) tour_cost_kernel(const InstDev I, const int *tours, const int *slots, int as_order,
+                                                        long long *out) {
     __shared__ long long s_part[8];
     const int n = I.n;
-    const int *t = tours + (long long)blockIdx.x * n;
+    const int *t = tours + (long long)(slots ? slots[blockIdx.x] : (int)blockIdx.x) * n;
     long long local = 0;
     for (int k = threadIdx.x; k < n; k += 256) {
         int u, v;
@@ -290,8 +291,9 @@ __global__ void __launch_bounds__(256) tour_cost_kernel(const InstDev I, const i
     }
 }
 
-cudaError_t launch_tour_cost(const InstDev &I, const int *tours, int as_order, long long *out, int batch, cudaStream_t st) {
-    tour_cost_kernel<<<batch, 256, 0, st>>>(I, tours, as_order, out);
+cudaError_t launch_tour_cost(const InstDev &I, const int *tours, const int *slots, int as_order, long long *out, int batch,
+                             cudaStream_t st) {
+    tour_cost_kernel<<<batch, 256, 0, st>>>(I, tours, slots, as_order, out);
     return cudaGetLastError();
 }
 

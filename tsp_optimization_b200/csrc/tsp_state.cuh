@@ -345,7 +345,6 @@ struct BiArgs {
     int packed_tail; // 1: blocks fold their key into ctl->pass_min with one 64-bit atomicMin (n <= 2^17, seed_hint < 2)
     int pruned;      // 1: tiles come from the live list built by tile_filter_kernel (exact tile pruning)
     int timing;      // 1: accumulate the per-pass breakdown in ctl->tm_acc; 2: also dump per-block {start, end} stamps
-    int split_tiles, split_factor;  // tail smoothing: this rank's last split_tiles tiles are drawn as split_factor sub-tiles
     unsigned long long *dbg;        // timing == 2: [gridDim.x][2] globaltimer stamps of the last pass
     XchgDev xchg;    // fuse_apply == 0: how this rank's key reaches the other ranks (enabled = 0 -> NCCL allreduce of ctl->packed)
 };

@@ -33,6 +33,9 @@ ABI_SYMBOLS = [
     "tspb200_bi_run", "tspb200_fi_run", "tspb200_two_opt", "tspb200_two_opt_tabu", "tspb200_two_opt_batch", "tspb200_nn_tour", "tspb200_nn_tour_batch", "tspb200_extra_mileage",
     "tspb200_tour_costs", "tspb200_comm_unique_id", "tspb200_comm_init", "tspb200_comm_destroy",
     "tspb200_debug_tile_plan", "tspb200_debug_fetch",
+    "tspb200_tour_cost", "tspb200_tour_save", "tspb200_tour_restore", "tspb200_vns_kick",
+    "tspb200_tabu_begin", "tspb200_tabu_run", "tspb200_tabu_kick", "tspb200_tabu_end",
+    "tspb200_population_upload", "tspb200_population_download", "tspb200_population_costs", "tspb200_population_two_opt",
 ]
 
 
@@ -80,10 +83,11 @@ def load_library() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        raise TspB200Error(-1, f"{LIB_PATH} is missing: build it with `make -C tsp_optimization_b200/csrc` "
+    path = os.environ.get("TSPB200_LIB", LIB_PATH)  # development: A/B timing of another build of the same ABI
+    if not os.path.exists(path):
+        raise TspB200Error(-1, f"{path} is missing: build it with `make -C tsp_optimization_b200/csrc` "
                                "(there is no CPU fallback)")
-    L = C.CDLL(LIB_PATH)
+    L = C.CDLL(path)
     vp, i64, i32p = C.c_void_p, C.c_int64, C.POINTER(C.c_int32)
     L.tspb200_create.argtypes = [C.c_int, C.POINTER(vp)]
     L.tspb200_destroy.argtypes = [vp]
@@ -117,7 +121,21 @@ def load_library() -> C.CDLL:
     L.tspb200_comm_destroy.argtypes = [vp]
     L.tspb200_debug_tile_plan.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, i32p, i32p, i32p,
                                           C.c_void_p, C.c_void_p, C.c_int, i32p]
-    L.tspb200_debug_fetch.argtypes = [vp, C.c_char_p, C.c_void_p, i64]
+    if hasattr(L, "tspb200_tour_cost"):
+        L.tspb200_tour_cost.argtypes = [vp, C.POINTER(C.c_double)]
+        L.tspb200_tour_save.argtypes = [vp, C.c_int]
+        L.tspb200_tour_restore.argtypes = [vp, C.c_int]
+        L.tspb200_vns_kick.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
+        L.tspb200_tabu_begin.argtypes = [vp]
+        L.tspb200_tabu_run.argtypes = [vp, C.c_int, C.c_int, i64, C.POINTER(_Stats)]
+        L.tspb200_tabu_kick.argtypes = [vp, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
+        L.tspb200_tabu_end.argtypes = [vp, C.c_void_p]
+        L.tspb200_population_upload.argtypes = [vp, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.tspb200_population_download.argtypes = [vp, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.tspb200_population_costs.argtypes = [vp, C.c_void_p, C.c_int, C.c_void_p]
+        L.tspb200_population_two_opt.argtypes = [vp, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(_Stats)]
+    if hasattr(L, "tspb200_debug_fetch"):
+        L.tspb200_debug_fetch.argtypes = [vp, C.c_char_p, C.c_void_p, i64]
     _lib = L
     return L
 
@@ -320,6 +338,73 @@ class Engine:
         out = np.empty(len(tours), dtype=np.float64)
         self._ck(self.L.tspb200_tour_costs(self.h, tours.ctypes.data, len(tours), 1 if as_order else 0, out.ctypes.data))
         return out
+
+    # -- resident sessions (VNS / tabu / GA callers of the path)
+    def tour_cost(self) -> float:
+        c = C.c_double(0)
+        self._ck(self.L.tspb200_tour_cost(self.h, C.byref(c)))
+        return c.value
+
+    def tour_save(self, slot: int = 0):
+        self._ck(self.L.tspb200_tour_save(self.h, slot))
+
+    def tour_restore(self, slot: int = 0):
+        self._ck(self.L.tspb200_tour_restore(self.h, slot))
+
+    def vns_kick(self, idx1: int, idx2: int, idx3: int) -> float:
+        """reference kick() (src/vns.c:11-100) on the resident tour -> recomputed cost."""
+        c = C.c_double(0)
+        self._ck(self.L.tspb200_vns_kick(self.h, int(idx1), int(idx2), int(idx3), C.byref(c)))
+        return c.value
+
+    def tabu_begin(self):
+        self._ck(self.L.tspb200_tabu_begin(self.h))
+
+    def tabu_run(self, iter_: int, tenure: int, max_passes: int = -1) -> Stats:
+        st = _Stats()
+        self._ck(self.L.tspb200_tabu_run(self.h, int(iter_), int(tenure), int(max_passes), C.byref(st)))
+        return Stats.of(st)
+
+    def tabu_kick(self, pairs, iter_: int, tenure: int) -> int:
+        pairs = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
+        acc = C.c_int(-1)
+        self._ck(self.L.tspb200_tabu_kick(self.h, pairs.ctypes.data, len(pairs), int(iter_), int(tenure), C.byref(acc)))
+        return acc.value
+
+    def tabu_end(self, want_list: bool = False):
+        out = np.empty(self.n * (self.n - 1) // 2, dtype=np.int32) if want_list else None
+        self._ck(self.L.tspb200_tabu_end(self.h, out.ctypes.data if want_list else None))
+        return out
+
+    def population_upload(self, tours, slots=None, as_order: bool = True):
+        tours = np.ascontiguousarray(tours, dtype=np.int32).reshape(-1, self.n)
+        sl = None if slots is None else np.ascontiguousarray(slots, dtype=np.int32)
+        assert sl is None or len(sl) == len(tours)
+        self._ck(self.L.tspb200_population_upload(self.h, tours.ctypes.data, None if sl is None else sl.ctypes.data, len(tours),
+                                                  1 if as_order else 0))
+
+    def population_download(self, count=None, slots=None, as_order: bool = True) -> np.ndarray:
+        sl = None if slots is None else np.ascontiguousarray(slots, dtype=np.int32)
+        k = len(sl) if sl is not None else int(count)
+        out = np.empty((k, self.n), dtype=np.int32)
+        self._ck(self.L.tspb200_population_download(self.h, out.ctypes.data, None if sl is None else sl.ctypes.data, k,
+                                                    1 if as_order else 0))
+        return out
+
+    def population_costs(self, count=None, slots=None) -> np.ndarray:
+        sl = None if slots is None else np.ascontiguousarray(slots, dtype=np.int32)
+        k = len(sl) if sl is not None else int(count)
+        out = np.empty(k, dtype=np.float64)
+        self._ck(self.L.tspb200_population_costs(self.h, None if sl is None else sl.ctypes.data, k, out.ctypes.data))
+        return out
+
+    def population_two_opt(self, mode: int, count=None, slots=None, obj=None):
+        sl = None if slots is None else np.ascontiguousarray(slots, dtype=np.int32)
+        k = len(sl) if sl is not None else int(count)
+        o = np.zeros(k, dtype=np.float64) if obj is None else np.array(obj, dtype=np.float64, copy=True)
+        st = _Stats()
+        self._ck(self.L.tspb200_population_two_opt(self.h, mode, None if sl is None else sl.ctypes.data, k, o.ctypes.data, C.byref(st)))
+        return o, Stats.of(st)
 
     # -- multi-GPU
     @staticmethod

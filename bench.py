@@ -466,6 +466,23 @@ def main():
             else:
                 tlo["pruned"] = rec
         eng.set_option("prune", 0)
+        # first improvement (reference alg_2opt) on the same instance and start tour: on N GPUs the segments of the pair order
+        # are dealt over the ranks, the first improving pair is min-exchanged like the best-improvement keys
+        barrier()
+        w0 = time.perf_counter()
+        s_fi, obj_fi, st_fi, _ = eng.two_opt(FI, h_succ, nn_cost)
+        torch.cuda.synchronize()
+        fi_s = maxr(time.perf_counter() - w0)
+        hv = int(sha(s_fi)[:15], 16)
+        if world > 1:
+            t = torch.tensor([hv, -hv], dtype=torch.int64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            same = bool(t[0].item() == -t[1].item())
+        else:
+            same = True
+        tlo["uni100000_FI" if n == 100000 else f"uni{n}_FI"] = {
+            "time_to_local_optimum_s": fi_s, "sweeps": st_fi.passes, "moves": st_fi.moves, "final_cost": obj_fi,
+            "us_per_move": 1e6 * fi_s / max(1, st_fi.moves), "tour_sha256": sha(s_fi), "same_tour_on_all_ranks": same}
         if world == 1 and n != 10000:  # BASELINE configs[2]: uni10000, greedy start + 2-opt to the local optimum, 1 B200
             xy2 = uniform_instance(10000)
             eng.set_instance(xy2, 0)

@@ -119,6 +119,8 @@ int tspb200_dist_matrix_get(tspb200_ctx *ctx, int32_t *out);
 /* One call, host buffers: build + copy back. */
 int tspb200_dist_matrix(tspb200_ctx *ctx, int32_t *out);
 int tspb200_dist_matrix_free(tspb200_ctx *ctx);
+/* One row, out[j] = (int32) calc_dist(i, j) for j = 0..n-1, computed on the device without a resident matrix. */
+int tspb200_dist_row(tspb200_ctx *ctx, int i, int32_t *out);
 
 /* ---- tours ---------------------------------------------------------------------------------------- */
 /* succ[k] = successor of node k == reference inst->solution.edges[k].j (include/utility.h:131-134). */

@@ -860,3 +860,66 @@ def test_batches_of_tours_too_large_for_one_block_run_on_the_grid_path(engine, o
         es, eo, _, _ = engine.two_opt(FI, s, c)
         assert (sb[b] == es).all() and ob[b] == eo
     assert is_tour(sb[0]) and ob[0] == oracle.succ_cost(xy, 0, sb[0])
+
+
+def test_geo_matrix_reports_no_entry_on_a_rounding_boundary(engine, instances, oracle):
+    """GEO depends on library cos / acos (CUDA vs glibc): the matrix kernel counts entries whose value handed to nint() lies
+    within 1e-9 (1e-6 below 10 km) of a rounding boundary; none of the reference's GEO instances has one, so equality with
+    the CPU is not luck."""
+    seen = 0
+    for nm, (xy, wt) in sorted(instances.items()):
+        if wt != 4:
+            continue
+        engine.set_instance(xy, wt)
+        m = engine.dist_matrix()
+        assert (m == oracle.dist_matrix(xy, wt)).all(), nm
+        assert engine.info("geo_near_boundary") == 0, nm
+        engine.dist_matrix_free()
+        seen += 1
+    assert seen >= 5
+
+
+def test_rows_on_demand_and_limits_the_reference_does_not_have(engine, oracle):
+    """dist_row without a resident matrix; extra mileage with its state in global memory (forced at a size the oracle can
+    check); batched nearest neighbour beyond the shared-memory limit falls back to the grid kernel per start."""
+    xy = uniform_instance(1200)
+    engine.set_instance(xy, 0)
+    full = oracle.dist_matrix(xy, 0)
+    for i in (0, 7, 1199):
+        assert (engine.dist_row(i) == full[i]).all()
+    es, ec = oracle.extra_mileage(xy, 0)
+    for forced in (0, 1):
+        engine.set_option("em_global", forced)
+        s, c = engine.extra_mileage()
+        assert (s == es).all() and c == ec, forced
+    engine.set_option("em_global", 0)
+    big = uniform_instance(23000)
+    engine.set_instance(big, 0)
+    succ, costs = engine.nn_tour_batch(np.array([0, 11], dtype=np.int32))
+    for b, start in enumerate((0, 11)):
+        s1, c1 = engine.nn_tour(start)
+        assert (succ[b] == s1).all() and costs[b] == c1 and is_tour(succ[b])
+
+
+def test_dropin_calc_dist_beyond_the_host_mirror_and_after_in_place_edits(oracle):
+    """scalar calc_dist on an instance too large for the n x n host mirror (rows fetched from the device on demand, no abort),
+    and on an instance whose nodes[] the caller rewrote IN PLACE between two calls (same pointer, same n): the sampled
+    hash must notice and the stale matrix must not be served."""
+    L = C.CDLL(eng.DROPIN_PATH)
+    L.calc_dist.restype = C.c_double
+    L.calc_dist.argtypes = [C.c_int, C.c_int, C.c_void_p]
+    n = 17000
+    xy = uniform_instance(n)
+    succ = order_to_succ(np.arange(n, dtype=np.int32))
+    inst = RefInstance(xy, 0, succ, 0.0)
+    rng = np.random.default_rng(3)
+    for i, j in rng.integers(0, n, size=(200, 2)):
+        assert L.calc_dist(int(i), int(j), C.byref(inst.c)) == oracle.dist(xy, 0, int(i), int(j))
+    small = uniform_instance(400)
+    inst2 = RefInstance(small, 0, order_to_succ(np.arange(400, dtype=np.int32)), 0.0)
+    assert L.calc_dist(3, 9, C.byref(inst2.c)) == oracle.dist(small, 0, 3, 9)
+    moved = small[::-1].copy()
+    inst2.xy[...] = moved  # rewrite the coordinates in place: same nodes pointer, same n
+    for i, j in ((3, 9), (0, 399), (17, 250)):
+        assert L.calc_dist(i, j, C.byref(inst2.c)) == oracle.dist(moved, 0, i, j)
+    L.tspb200_dropin_reset()

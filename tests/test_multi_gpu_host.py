@@ -80,3 +80,76 @@ def test_sharded_argmin_equals_reference_moves(tmp_path, oracle):
     m1 = np.load(tmp_path / "moves_1.npy")
     assert (m0 == m1).all()
     assert m0.tolist() == log.tolist()
+
+
+def _fi_worker(rank, world, port, out_dir):
+    """first improvement, sharded like csrc/kernels_fi.cu: the row-major pair order from the cursor is cut into segments of SEG
+    pairs, rank r scans the segments r, r + world, ... and stops at ITS first improving pair; the min over the ranks of the
+    linear index i * n + j is the reference's next move."""
+    import sys
+    sys.path.insert(0, ROOT)
+    from oracle.oracle import Oracle
+    from tsp_optimization_b200.instances import uniform_instance
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    orc = Oracle()
+    n, SEG = 220, 512
+    xy = uniform_instance(n)
+    D = orc.dist_matrix(xy, 0).astype(np.int64)
+    succ, _ = orc.nn_tour(xy, 0, 0)
+    succ = succ.copy()
+    pairs = [(i, j) for i in range(n - 1) for j in range(i + 1, n)]  # the reference's enumeration (heuristics.c:466-467)
+    moves = []
+    cursor, sweep_moves = 0, 0
+    NONE = 1 << 40
+    while len(moves) < 60:
+        found = NONE
+        seg = rank
+        while cursor + seg * SEG < len(pairs):
+            lo = cursor + seg * SEG
+            for k in range(lo, min(lo + SEG, len(pairs))):
+                a, b = pairs[k]
+                a1, b1 = int(succ[a]), int(succ[b])
+                if b == a1 or b1 == a or a1 == b1:
+                    continue
+                if D[a, b] + D[a1, b1] - D[a, a1] - D[b, b1] < 0:
+                    found = a * n + b
+                    break
+            if found != NONE:
+                break
+            seg += world
+        t = torch.tensor([found], dtype=torch.int64)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        f = int(t.item())
+        if f == NONE:  # end of the sweep (heuristics.c:492-496)
+            if sweep_moves == 0:
+                break
+            cursor, sweep_moves = 0, 0
+            continue
+        i, j = divmod(f, n)
+        a1, b1 = int(succ[i]), int(succ[j])
+        moves.append((i, j, int(D[i, j] + D[a1, b1] - D[i, a1] - D[j, b1])))
+        prev = np.empty(n, dtype=np.int32)
+        prev[succ] = np.arange(n, dtype=np.int32)
+        succ[i] = j
+        succ[a1] = b1
+        orc.L.orc_reverse_path(n, succ, j, a1, prev)
+        sweep_moves += 1
+        cursor = pairs.index((i, j)) + 1
+    np.save(os.path.join(out_dir, f"fi_moves_{rank}.npy"), np.array(moves, dtype=np.int64))
+    dist.destroy_process_group()
+
+
+def test_sharded_first_improvement_equals_reference_moves(tmp_path, oracle):
+    world = 2
+    port = _free_port()
+    mp.spawn(_fi_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    from tsp_optimization_b200.instances import uniform_instance
+    xy = uniform_instance(220)
+    succ, cost = oracle.nn_tour(xy, 0, 0)
+    _, _, _, log = oracle.two_opt_fi(xy, 0, succ, cost, max_moves=60, log_cap=60)
+    m0 = np.load(tmp_path / "fi_moves_0.npy")
+    m1 = np.load(tmp_path / "fi_moves_1.npy")
+    assert (m0 == m1).all()
+    assert m0.tolist() == log.tolist()

@@ -22,9 +22,18 @@ struct Cache {
     const void *nodes = nullptr;
     int n = 0, wt = 0;
     uint64_t hash = 0;
-    std::vector<int32_t> matrix;  // host mirror for scalar calc_dist
+    uint64_t quick = 0;           // hash of 16 sampled points: the per-call staleness check of scalar calc_dist
+    std::vector<int32_t> matrix;  // host mirror for scalar calc_dist (n <= MIRROR_MAX_N)
     bool have_matrix = false;
+    // larger instances: a small cache of device-computed rows, replaced round-robin (reference callers walk along tours,
+    // src/genetic.c:51-60, src/vns.c:78-86: consecutive calls share the row of the previous node only now and then, so this
+    // is slow — the batched entry points are the fast path — but it is exact and it does not abort)
+    std::vector<int32_t> rows;
+    std::vector<int> row_of;
+    int row_next = 0;
 };
+constexpr int MIRROR_MAX_N = 16384;
+constexpr int ROW_CACHE = 64;
 Cache g_cache;
 std::mutex g_mu;
 
@@ -41,17 +50,32 @@ uint64_t hash_points(const tspb200_ref_point *p, int n) {
     return h;
 }
 
+// 16 points spread over the array: cheap enough for every scalar calc_dist call, catches a caller that rewrote nodes[] in
+// place (same pointer, same n) without paying the full hash
+uint64_t quick_hash(const tspb200_ref_point *p, int n) {
+    uint64_t h = 1469598103934665603ull;
+    const int step = n > 16 ? n / 16 : 1;
+    for (int k = 0; k < n; k += step) {
+        const unsigned char *b = reinterpret_cast<const unsigned char *>(p + k);
+        for (size_t t = 0; t < sizeof(tspb200_ref_point); ++t) { h ^= b[t]; h *= 1099511628211ull; }
+    }
+    const unsigned char *b = reinterpret_cast<const unsigned char *>(p + (n - 1));
+    for (size_t t = 0; t < sizeof(tspb200_ref_point); ++t) { h ^= b[t]; h *= 1099511628211ull; }
+    return h;
+}
+
 // device context holding this instance's coordinates; full_check re-hashes the coordinates
 tspb200_ctx *context_for(tspb200_ref_instance *inst, bool full_check) {
     if (!inst || !inst->nodes || inst->num_nodes < 1) die("instance has no nodes");
     if (inst->params.integer_cost != 1)
         die("--fcost (integer_cost=0) is outside the bit-exact contract of the GPU path; run with integer costs");
     const bool same_ptr = g_cache.ctx && g_cache.nodes == inst->nodes && g_cache.n == inst->num_nodes && g_cache.wt == inst->weight_type;
-    if (same_ptr && !full_check) return g_cache.ctx;
+    if (same_ptr && !full_check && quick_hash(inst->nodes, inst->num_nodes) == g_cache.quick) return g_cache.ctx;
     uint64_t h = hash_points(inst->nodes, inst->num_nodes);
     if (same_ptr && h == g_cache.hash) return g_cache.ctx;
     if (g_cache.ctx && g_cache.n == inst->num_nodes && g_cache.wt == inst->weight_type && h == g_cache.hash) {
         g_cache.nodes = inst->nodes;  // a copy_instance() clone of the same problem (reference utility.c:724-743)
+        g_cache.quick = quick_hash(inst->nodes, inst->num_nodes);
         return g_cache.ctx;
     }
     if (!g_cache.ctx) {
@@ -65,8 +89,12 @@ tspb200_ctx *context_for(tspb200_ref_instance *inst, bool full_check) {
     g_cache.n = inst->num_nodes;
     g_cache.wt = inst->weight_type;
     g_cache.hash = h;
+    g_cache.quick = quick_hash(inst->nodes, inst->num_nodes);
     g_cache.have_matrix = false;
     g_cache.matrix.clear();
+    g_cache.rows.clear();
+    g_cache.row_of.clear();
+    g_cache.row_next = 0;
     if (inst->weight_type == TSPB200_GEO || inst->weight_type == TSPB200_MAN_2D || inst->weight_type == TSPB200_MAX_2D) {
         // metrics without an FP32 filter path evaluate 2-opt on a resident matrix when it fits
         if ((size_t)inst->num_nodes * inst->num_nodes * 4 < (8ull << 30)) {
@@ -107,15 +135,30 @@ int run_two_opt(tspb200_ref_instance *inst, int mode, int *stored_prev, int *ski
 
 extern "C" {
 
-// Scalar distances are served from a host mirror of the device-built matrix: a GPU hop per call would be
-// meaningless.  Large instances must use the batched entry points (tspb200_tour_costs / tspb200_nn_tour).
+// Scalar distances are served from a host mirror of the device-built matrix (a GPU hop per call would be meaningless);
+// beyond MIRROR_MAX_N nodes from a small cache of device-computed rows.  Every value comes from the CUDA kernels.
 double calc_dist(int i, int j, tspb200_ref_instance *inst) {
     std::lock_guard<std::mutex> lk(g_mu);
     tspb200_ctx *ctx = context_for(inst, false);
     const int n = inst->num_nodes;
     if (i < 0 || j < 0 || i >= n || j >= n) die("calc_dist index out of range");
+    if (n > MIRROR_MAX_N) {
+        if (g_cache.row_of.empty()) {
+            g_cache.row_of.assign(ROW_CACHE, -1);
+            g_cache.rows.resize((size_t)ROW_CACHE * n);
+        }
+        for (int k = 0; k < ROW_CACHE; ++k)
+            if (g_cache.row_of[k] == i) return (double)g_cache.rows[(size_t)k * n + j];
+        for (int k = 0; k < ROW_CACHE; ++k)  // the matrices of this path are symmetric
+            if (g_cache.row_of[k] == j) return (double)g_cache.rows[(size_t)k * n + i];
+        const int k = g_cache.row_next;
+        g_cache.row_next = (k + 1) % ROW_CACHE;
+        int rc = tspb200_dist_row(ctx, i, g_cache.rows.data() + (size_t)k * n);
+        if (rc) die("distance row failed: ", tspb200_last_error(ctx));
+        g_cache.row_of[k] = i;
+        return (double)g_cache.rows[(size_t)k * n + j];
+    }
     if (!g_cache.have_matrix) {
-        if (n > 16384) die("scalar calc_dist needs the n*n host mirror (n <= 16384); use tspb200_tour_costs / tspb200_nn_tour / tspb200_two_opt for larger instances");
         g_cache.matrix.resize((size_t)n * n);
         int rc = tspb200_dist_matrix(ctx, g_cache.matrix.data());
         if (rc) die("distance matrix failed: ", tspb200_last_error(ctx));

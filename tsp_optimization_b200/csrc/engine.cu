@@ -33,9 +33,11 @@ cudaError_t launch_tile_prune(const BiArgs &a, int TI, int grid_bi, bool pdl, cu
 cudaError_t launch_rank_align(const XchgDev &x, int rank, int world, Ctl *ctl, cudaStream_t st);
 cudaError_t launch_rebuild_node_space(const TourDev &T, cudaStream_t st);
 cudaError_t launch_refresh_node_space(const TourDev &tour, int num_sms, bool pdl, cudaStream_t st);
-cudaError_t launch_fi_search(const InstDev &I, const TourDev &T, int grid, bool pdl, cudaStream_t st);
+cudaError_t launch_fi_search(const InstDev &I, const TourDev &T, int rank, int world, const XchgDev *xchg, int grid, bool pdl,
+                             cudaStream_t st);
+cudaError_t launch_fi_finish(const InstDev &I, const TourDev &T, cudaStream_t st);
 cudaError_t launch_dist_matrix(const InstDev &I, int *out, long long ld, int row_begin, int row_end, bool fast,
-                               cudaStream_t st);
+                               unsigned long long *geo_near, cudaStream_t st);
 cudaError_t launch_build_state(const InstDev &I, const TourDev &T, const int *order, cudaStream_t st);
 cudaError_t launch_export_state(const TourDev &T, int *succ, unsigned long long *cost, cudaStream_t st);
 cudaError_t launch_tour_cost(const InstDev &I, const int *tours, const int *slots, int as_order, long long *out, int batch,
@@ -43,7 +45,9 @@ cudaError_t launch_tour_cost(const InstDev &I, const int *tours, const int *slot
 cudaError_t launch_nn_tour(const NnArgs &a, int grid, cudaStream_t st);
 cudaError_t launch_prep_points(const double2 *raw, double2 *pt64, float2 *pt32, int n, int metric, cudaStream_t st);
 int nn_max_grid(int num_sms);
-cudaError_t launch_extra_mileage(const InstDev &I, int *succ_out, long long *cost_out, cudaStream_t st);
+cudaError_t launch_extra_mileage(const InstDev &I, int *succ_out, long long *cost_out, unsigned char *gwork, bool force_global,
+                                 cudaStream_t st);
+size_t extra_mileage_state_bytes(int n);
 cudaError_t launch_nn_batch(const InstDev &I, const int *starts, int batch, int *succ_out, long long *cost_out, float eps,
                             int num_sms, cudaStream_t st);
 cudaError_t launch_two_opt_batch(const InstDev &I, int mode, int *succ, const int *slots, long long *obj_delta, long long *counters,
@@ -112,6 +116,7 @@ struct tspb200_ctx {
     long long mat_ld = 0;
     double dmax = 0;
     float eps32 = 0;                  // bound of |FP32 distance - real distance| for this instance
+    unsigned long long geo_near = 0;  // GEO matrix entries within 1e-6 of a rounding boundary (last matrix build)
 
     // tour (device buffers are kept across set_instance / tour_upload calls while they are big enough: cudaMalloc is
     // a synchronising call, and a slow one once peer access is enabled)
@@ -148,6 +153,7 @@ struct tspb200_ctx {
     int opt_single_block = -1;
     int opt_prune = -1;         // exact tile pruning of the best-improvement scan: -1 auto, 0 off (exhaustive scan), 1 on
     int opt_timing = 0;         // accumulate the per-pass breakdown (scan / tail / exchange wait / apply) on the device
+    int opt_em_global = 0;      // tests: extra mileage keeps its state in the global work buffer even when it fits shared memory
     int opt_batch_kernel = 0;   // batched best improvement: 0 = position-space kernel when applicable, 1 = always the node-space kernel
     unsigned long long *d_dbg = nullptr;  // per-block time stamps of the last pass ("timing" = 2)
     int opt_debug_shard = 0;    // timing experiments only: (world << 8 | rank) -> scan that rank's share of the tiles on one GPU  // -1 auto, 0 never, 1 whenever the tour fits in shared memory
@@ -358,6 +364,8 @@ int tspb200_set_option(tspb200_ctx *ctx, const char *key, int64_t value) {
     } else if (k == "timing") {
         if (value < 0 || value > 2) return fail(ctx, TSPB200_E_ARG, "timing must be 0, 1 or 2");
         ctx->opt_timing = (int)value;
+    } else if (k == "em_global") {
+        ctx->opt_em_global = value ? 1 : 0;
     } else if (k == "batch_kernel") {
         ctx->opt_batch_kernel = value ? 1 : 0;
     } else if (k == "pdl") {
@@ -407,6 +415,7 @@ int64_t tspb200_get_info(const tspb200_ctx *ctx, const char *key) {
             if (k == names[t]) return (int64_t)ctx->h_ctl->tm_acc[t];
     }
     if (k == "dist_bound") return (int64_t)ctx->dist_bound;
+    if (k == "geo_near_boundary") return (int64_t)ctx->geo_near;
     if (k == "exchange_p2p") return ctx->xchg.enabled && ctx->opt_exchange == 0;
     if (k == "world") return ctx->world;
     if (k == "rank") return ctx->rank;
@@ -512,8 +521,15 @@ int tspb200_dist_matrix_build(tspb200_ctx *ctx, double *gpu_ms) {
     I.dmat = nullptr;  // the kernel computes, never gathers
     const bool fast = I.fp32_ok && I.exact32;
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
-    CK(launch_dist_matrix(I, ctx->d_mat, ld, 0, n, fast, ctx->stream));
+    unsigned long long *d_near = nullptr;
+    if (I.metric == TSPB200_GEO) {  // GEO: count entries that sit on a rounding boundary (library cos / acos, see tsp_device.cuh)
+        d_near = static_cast<unsigned long long *>(dev_scratch(ctx, 8, sizeof(unsigned long long)));
+        if (!d_near) return fail(ctx, TSPB200_E_CUDA, "cudaMalloc failed");
+        CK(cudaMemsetAsync(d_near, 0, sizeof(unsigned long long), ctx->stream));
+    }
+    CK(launch_dist_matrix(I, ctx->d_mat, ld, 0, n, fast, d_near, ctx->stream));
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    if (d_near) CK(cudaMemcpyAsync(&ctx->geo_near, d_near, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     if (gpu_ms) {
         float ms = 0;
@@ -539,6 +555,24 @@ int tspb200_dist_matrix(tspb200_ctx *ctx, int32_t *out) {
     int rc = tspb200_dist_matrix_build(ctx, nullptr);
     if (rc) return rc;
     return tspb200_dist_matrix_get(ctx, out);
+}
+
+// One row of the matrix, out[j] = (int32) calc_dist(i, j), computed on the device without building the matrix (instances whose
+// n x n matrix is not wanted on the host: the drop-in's scalar calc_dist fetches rows through this).
+int tspb200_dist_row(tspb200_ctx *ctx, int i, int32_t *out) {
+    if (!ctx || !ctx->stream) return fail(ctx, TSPB200_E_CUDA, "context has no CUDA device");
+    if (ctx->n < 1) return fail(ctx, TSPB200_E_STATE, "no instance");
+    if (!out || i < 0 || i >= ctx->n) return fail(ctx, TSPB200_E_ARG, "bad row %d", i);
+    CK(cudaSetDevice(ctx->device));
+    const int n = ctx->n;
+    const long long ld = ((long long)n + 3) / 4 * 4;
+    SCRATCH(d_row, int *, 13, sizeof(int) * (size_t)ld);
+    InstDev I = ctx->inst;
+    I.dmat = nullptr;
+    CK(launch_dist_matrix(I, d_row, ld, i, i + 1, I.fp32_ok && I.exact32, nullptr, ctx->stream));
+    CK(cudaMemcpyAsync(out, d_row, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return TSPB200_OK;
 }
 
 int tspb200_dist_matrix_free(tspb200_ctx *ctx) {
@@ -1068,19 +1102,40 @@ int tspb200_fi_run(tspb200_ctx *ctx, int64_t max_moves, tspb200_stats *st) {
     bool done = false;
     if (max_moves == 0) { done = false; status = TSPB200_STOPPED_BY_CAP; }
     else {
+        // several GPUs: the segments of the pair order are dealt over the ranks; the first improving pair of every rank is
+        // min-exchanged through the NVLink peer slots inside the search kernel (or by NCCL + fi_finish_kernel)
+        const bool use_xchg = ctx->world > 1 && ctx->xchg.enabled && ctx->opt_exchange == 0;
+        const bool pdl = ctx->opt_pdl != 0 && (ctx->world == 1 || use_xchg);
+        XchgDev xd = ctx->xchg;
         while (!done) {
             for (long long q = 0; q < batch; ++q) {
-                CK(launch_fi_search(I, ctx->tour, grid, ctx->opt_pdl != 0, ctx->stream));
-                CK(launch_apply_move(I, ctx->tour, ctx->num_sms, 0, 0, ctx->opt_pdl != 0, ctx->stream));
-                CK(launch_refresh_node_space(ctx->tour, ctx->num_sms, ctx->opt_pdl != 0, ctx->stream));
-                host_launches += 3;
+                CK(launch_fi_search(I, ctx->tour, ctx->rank, ctx->world, use_xchg ? &xd : nullptr, grid, pdl, ctx->stream));
+                host_launches++;
+                if (ctx->world > 1 && !use_xchg) {
+                    unsigned long long *p = &ctx->d_ctl->fi_found;
+                    int nr = g_nccl.AllReduce(p, p, 1, NCCL_UINT64, NCCL_MIN, ctx->comm, ctx->stream);
+                    if (nr != 0) return fail(ctx, TSPB200_E_NCCL, "ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(nr) : "?");
+                    CK(launch_fi_finish(I, ctx->tour, ctx->stream));
+                    host_launches++;
+                }
+                CK(launch_apply_move(I, ctx->tour, ctx->num_sms, 0, 0, pdl, ctx->stream));
+                CK(launch_refresh_node_space(ctx->tour, ctx->num_sms, pdl, ctx->stream));
+                host_launches += 2;
             }
             rc = sync_ctl(ctx);
             if (rc) return rc;
             done = ctx->h_ctl->done != 0;
             if (!done && ctx->opt_time_limit_ms > 0) {
                 auto el = std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - t_start).count();
-                if (el > ctx->opt_time_limit_ms) { status = TSPB200_TIME_LIMIT_EXCEEDED; break; }
+                int stop = el > ctx->opt_time_limit_ms ? 1 : 0;
+                if (ctx->world > 1) {  // collective decision, see tspb200_bi_run
+                    CK(cudaMemcpyAsync(ctx->d_stop, &stop, sizeof stop, cudaMemcpyHostToDevice, ctx->stream));
+                    int nr = g_nccl.AllReduce(ctx->d_stop, ctx->d_stop, 1, NCCL_INT32, NCCL_MAX, ctx->comm, ctx->stream);
+                    if (nr != 0) return fail(ctx, TSPB200_E_NCCL, "ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(nr) : "?");
+                    CK(cudaMemcpyAsync(&stop, ctx->d_stop, sizeof stop, cudaMemcpyDeviceToHost, ctx->stream));
+                    CK(cudaStreamSynchronize(ctx->stream));
+                }
+                if (stop) { status = TSPB200_TIME_LIMIT_EXCEEDED; break; }
             }
         }
         if (done && cap >= 0 && ctx->h_ctl->moves >= cap) status = TSPB200_STOPPED_BY_CAP;
@@ -1378,11 +1433,20 @@ int tspb200_nn_tour_batch(tspb200_ctx *ctx, const int32_t *starts, int batch, in
     }
     CK(cudaMemcpyAsync(d_starts, starts, sizeof(int) * (size_t)batch, cudaMemcpyHostToDevice, ctx->stream));
     cudaError_t le = launch_nn_batch(I, d_starts, batch, d_succ, d_cost, eps, ctx->num_sms, ctx->stream);
+    if (le == cudaErrorInvalidValue) {
+        // the coordinates do not fit one block's shared memory (n > ~22 000): one grid-wide nearest-neighbour run per start
+        cudaGetLastError();
+        std::vector<int32_t> tmp(succ ? 0 : (size_t)n);
+        for (int b = 0; b < batch; ++b) {
+            int rc = tspb200_nn_tour(ctx, starts[b], succ ? succ + (size_t)b * n : tmp.data(), &costs[b]);
+            if (rc) return rc;
+        }
+        return TSPB200_OK;
+    }
     std::vector<long long> h((size_t)batch);
     if (le == cudaSuccess && succ) le = cudaMemcpyAsync(succ, d_succ, sizeof(int) * (size_t)batch * n, cudaMemcpyDeviceToHost, ctx->stream);
     if (le == cudaSuccess) le = cudaMemcpyAsync(h.data(), d_cost, sizeof(long long) * (size_t)batch, cudaMemcpyDeviceToHost, ctx->stream);
     if (le == cudaSuccess) le = cudaStreamSynchronize(ctx->stream);
-    if (le == cudaErrorInvalidValue) return fail(ctx, TSPB200_E_UNSUPPORTED, "batched nearest neighbour keeps the coordinates in shared memory: n=%d is too large", n);
     if (le != cudaSuccess) return fail(ctx, TSPB200_E_CUDA, "batched nearest-neighbour kernel failed: %s", cudaGetErrorString(le));
     for (int b = 0; b < batch; ++b) costs[b] = (double)h[(size_t)b];
     return TSPB200_OK;
@@ -1400,12 +1464,13 @@ int tspb200_extra_mileage(tspb200_ctx *ctx, int32_t *succ, double *cost) {
     InstDev I = inst_for_path(ctx, path == 2 ? 2 : 1);
     SCRATCH(d_succ, int *, 12, sizeof(int) * (size_t)n);
     SCRATCH(d_cost, long long *, 13, sizeof(long long));
-    cudaError_t le = launch_extra_mileage(I, d_succ, d_cost, ctx->stream);
+    // instances whose insertion state (21 bytes per node) exceeds one block's shared memory keep it in a global work buffer
+    SCRATCH(d_work, unsigned char *, 14, extra_mileage_state_bytes(n));
+    cudaError_t le = launch_extra_mileage(I, d_succ, d_cost, d_work, ctx->opt_em_global != 0, ctx->stream);
     long long c = 0;
     if (le == cudaSuccess) le = cudaMemcpyAsync(succ, d_succ, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream);
     if (le == cudaSuccess) le = cudaMemcpyAsync(&c, d_cost, sizeof c, cudaMemcpyDeviceToHost, ctx->stream);
     if (le == cudaSuccess) le = cudaStreamSynchronize(ctx->stream);
-    if (le == cudaErrorInvalidValue) return fail(ctx, TSPB200_E_UNSUPPORTED, "extra mileage keeps its state in shared memory: n=%d is too large", n);
     if (le != cudaSuccess) return fail(ctx, TSPB200_E_CUDA, "extra-mileage kernel failed: %s", cudaGetErrorString(le));
     if (cost) *cost = (double)c;
     return TSPB200_OK;

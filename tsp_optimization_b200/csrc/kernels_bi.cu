@@ -198,6 +198,7 @@ __global__ void __launch_bounds__(BI_THREADS, (R >= 16 ? (BI_THREADS == 256 ? 1 
     const long long tiles_rank = PRUNED ? (long long)__ldcg(&ctl->live_count)
                                         : ((long long)A.ntiles - A.rank + A.world - 1) / A.world;
     unsigned scanned = 0;  // thread 0: tiles this block really scanned (statistics of the pruned mode)
+    unsigned next_raw = 0; // thread 0, pruned mode: ticket requested one draw ahead
     auto draw = [&](int b, bool first) {
         int P = 0, Q = 0, valid = 0;
         if (!PRUNED) {
@@ -208,11 +209,14 @@ __global__ void __launch_bounds__(BI_THREADS, (R >= 16 ? (BI_THREADS == 256 ? 1 
                 valid = 1;
             }
         } else {
+            // pruned tiles are small (a few us): the ticket of the NEXT draw is requested as soon as this one is taken, so the
+            // atomic's L2 round trip overlaps the tile instead of preceding it
+            const bool counted = tiles_rank > (long long)gridDim.x;
             for (;;) {
-                long long kl = first ? (long long)blockIdx.x : tiles_rank;
-                if (!first && tiles_rank > (long long)gridDim.x) kl = (long long)gridDim.x + (long long)atomicAdd(&ctl->tile_next, 1u);
+                long long kl = first ? (long long)blockIdx.x : (counted ? (long long)gridDim.x + (long long)next_raw : tiles_rank);
                 if (kl >= tiles_rank) break;
                 first = false;
+                if (counted) next_raw = atomicAdd(&ctl->tile_next, 1u);
                 if (__ldg(&A.tour.live_lb[kl]) > (float)(*((volatile int *)&s_hint))) continue;
                 decode(__ldg(&A.tour.live[kl]), P, Q);
                 valid = 1;
@@ -268,15 +272,6 @@ __global__ void __launch_bounds__(BI_THREADS, (R >= 16 ? (BI_THREADS == 256 ? 1 
         // pairs with q < p+2 exist in this tile?  (mask them; they are mirrored / adjacent pairs)
         const bool diag = (Q0 < P0 + TI + 1);
         const int NC = PRUNED ? NCv : TJ;  // columns of this tile
-        // In a diagonal tile a warp starts at the first column that holds a legal pair for its FIRST row (q >= p + 2), rounded
-        // down to the filter granularity: the columns before are masked for all its rows.  Diagonal tiles thus cost about
-        // half a regular tile instead of ~1.3 of one — they were the stragglers of a one-wave pass (n ~ 10^4).
-        int jbeg = 0;
-        if (diag) {
-            jbeg = P0 + (tid & ~31) * R + 2 - Q0;
-            jbeg = jbeg < 0 ? 0 : (jbeg & ~(BI_CB - 1));
-            if (jbeg > NC) jbeg = NC;
-        }
         // first column of the scan: D0 -> U2 (kept per variant so that the regular tile's shared-memory addressing stays uniform)
         float4 c0, cnext;
         f32x2 U2[R / 2];
@@ -312,7 +307,7 @@ __global__ void __launch_bounds__(BI_THREADS, (R >= 16 ? (BI_THREADS == 256 ? 1 
 
 // BI_CB columns, then ONE filter check per warp (ballot); hits are resolved one lane at a time by the whole warp
 #define BI_BLOCK(DIAG)                                                                                 \
-    for (int jj = (DIAG) ? jbeg : 0; jj < NC; jj += BI_CB) {                                           \
+    for (int jj = 0; jj < NC; jj += BI_CB) {                                                           \
         float M = TSPB_BIG;                                                                            \
         _Pragma("unroll") for (int c = 0; c < BI_CB; ++c) BI_COL(DIAG, jj + c)                         \
         unsigned hits = __ballot_sync(0xffffffffu, M <= thr);                                          \
@@ -349,7 +344,7 @@ __global__ void __launch_bounds__(BI_THREADS, (R >= 16 ? (BI_THREADS == 256 ? 1 
             BI_INIT(0)
             BI_BLOCK(false)
         } else {
-            BI_INIT(jbeg)
+            BI_INIT(0)
             BI_BLOCK(true)
         }
 #undef BI_INIT

@@ -21,12 +21,15 @@ __device__ __forceinline__ unsigned long long em_key(long long delta, int slot) 
 }
 __device__ __forceinline__ long long em_delta(unsigned long long k) { return (long long)(unsigned)(k >> 32) - (1ll << 31); }
 
-__global__ void __launch_bounds__(EM_THREADS) extra_mileage_kernel(const InstDev I, int *succ_out, long long *cost_out) {
+__global__ void __launch_bounds__(EM_THREADS) extra_mileage_kernel(const InstDev I, int *succ_out, long long *cost_out,
+                                                                   unsigned char *gwork) {
     extern __shared__ __align__(16) unsigned char em_smem[];
     __shared__ unsigned long long s_red[EM_THREADS / 32];
     __shared__ int s_qn;
     const int n = I.n;
-    unsigned long long *key = reinterpret_cast<unsigned long long *>(em_smem);  // [n] best (delta, slot) of an unvisited node
+    // the state lives in shared memory when it fits (21 bytes per node), else in a global work buffer (same code, L2 latency)
+    unsigned char *state = gwork ? gwork : em_smem;
+    unsigned long long *key = reinterpret_cast<unsigned long long *>(state);  // [n] best (delta, slot) of an unvisited node
     int *ea = reinterpret_cast<int *>(key + n);                                  // [n] tour edges in edges_visited[] order
     int *eb = ea + n;
     int *queue = eb + n;                                                         // [n] nodes to rescan
@@ -49,20 +52,32 @@ __global__ void __launch_bounds__(EM_THREADS) extra_mileage_kernel(const InstDev
     };
 
     // ---- the two farthest nodes: strict '>' over the row-major (i<j) scan -> largest distance, then lowest (i,j) ----
+    // two reductions: the largest distance, then the lowest (i, j) that attains it (any n)
     unsigned long long far = EM_NONE;
     for (long long p = tid; p < (long long)n * n; p += EM_THREADS) {
         const int i = (int)(p / n), j = (int)(p % n);
         if (j <= i) continue;
         const long long d = dist_nodes(I, i, j);
         if (d <= 0) continue;  // max_dist starts at 0 and the test is strict
-        const unsigned long long k = ((unsigned long long)(unsigned)((1ll << 31) - d) << 32) | ((unsigned long long)i << 16) | (unsigned)j;
+        const unsigned long long k = (unsigned long long)((1ll << 40) - d);
         far = k < far ? k : far;
     }
     far = block_min(far);
     int nodeA = 0, nodeB = 1;  // the reference's defaults when every distance is 0
     if (far != EM_NONE) {
-        nodeA = (int)((far >> 16) & 0xffffu);
-        nodeB = (int)(far & 0xffffu);
+        const long long dmax = (1ll << 40) - (long long)far;
+        unsigned long long who = EM_NONE;
+        for (long long p = tid; p < (long long)n * n; p += EM_THREADS) {
+            const int i = (int)(p / n), j = (int)(p % n);
+            if (j <= i) continue;
+            if (dist_nodes(I, i, j) == dmax) {
+                const unsigned long long k = ((unsigned long long)i << 32) | (unsigned)j;
+                who = k < who ? k : who;
+            }
+        }
+        who = block_min(who);
+        nodeA = (int)(who >> 32);
+        nodeB = (int)(who & 0xffffffffu);
     }
     const long long dAB = dist_nodes(I, nodeA, nodeB);
     for (int k = tid; k < n; k += EM_THREADS) vis[k] = (k == nodeA || k == nodeB) ? 1 : 0;
@@ -156,12 +171,18 @@ __global__ void __launch_bounds__(EM_THREADS) extra_mileage_kernel(const InstDev
     if (tid == 0) *cost_out = obj;
 }
 
-cudaError_t launch_extra_mileage(const InstDev &I, int *succ_out, long long *cost_out, cudaStream_t st) {
-    const size_t smem = (size_t)I.n * (8 + 4 + 4 + 4 + 1) + 64;
-    if (smem > 200 * 1024 || I.n > 65535) return cudaErrorInvalidValue;
-    cudaError_t e = cudaFuncSetAttribute(extra_mileage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+size_t extra_mileage_state_bytes(int n) { return (size_t)n * (8 + 4 + 4 + 4 + 1) + 64; }
+
+// gwork: extra_mileage_state_bytes(n) bytes of global memory, used when the state does not fit one block's shared memory
+cudaError_t launch_extra_mileage(const InstDev &I, int *succ_out, long long *cost_out, unsigned char *gwork, bool force_global,
+                                 cudaStream_t st) {
+    size_t smem = extra_mileage_state_bytes(I.n);
+    const bool in_smem = smem <= 200 * 1024 && !(force_global && gwork);
+    if (!in_smem && !gwork) return cudaErrorInvalidValue;
+    if (!in_smem) smem = 0;
+    cudaError_t e = cudaFuncSetAttribute(extra_mileage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(in_smem ? smem : 0));
     if (e != cudaSuccess) return e;
-    extra_mileage_kernel<<<1, EM_THREADS, smem, st>>>(I, succ_out, cost_out);
+    extra_mileage_kernel<<<1, EM_THREADS, smem, st>>>(I, succ_out, cost_out, in_smem ? nullptr : gwork);
     return cudaGetLastError();
 }
 

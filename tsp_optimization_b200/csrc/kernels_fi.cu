@@ -46,8 +46,63 @@ __device__ __forceinline__ void fi_locate(long long A, int n, int &row, int &j) 
     j = (int)(r + 1 + (A - fi_pairs_before_row(r, n)));
 }
 
+// Several GPUs (world > 1): the segments are dealt round-robin over the ranks (rank r scans the segments r, r + world, ...),
+// every rank finds the first improving pair among ITS segments, and the minimum over the ranks — exchanged through the same
+// NVLink peer slots as the best-improvement keys (xchg_min), or min-allreduced by NCCL and finished by fi_finish_kernel — is
+// the reference's pair: the rank that owns the winning segment scanned all of its earlier segments to their end.
+struct FiShard {
+    int rank, world;
+    int finish_here;  // 1: the search kernel's last block publishes the move; 0: fi_finish_kernel does (NCCL exchange)
+    XchgDev xchg;
+};
+
+// What happens once the first improving pair f (FI_NONE: none left in this sweep) is known: publish the move for the apply
+// launch, advance the cursor, close the sweep (reference src/heuristics.c:476-496).  One thread.
+__device__ __forceinline__ void fi_finish(const InstDev &I, const TourDev &T, unsigned long long f, int i0, int j0) {
+    Ctl *ctl = T.ctl;
+    const int n = T.n;
+    int ci = 0, cj = 0;
+    bool sweep_end = false;
+    if (f != FI_NONE) {
+        const int i = (int)(f / (unsigned long long)n), j = (int)(f % (unsigned long long)n);
+        const long long delta = move_delta_nodes(I, T, i, j);
+        if (delta >= 0) ctl->error = 1;  // cannot happen: the searching thread saw delta < 0
+        publish_move(T, i, j, delta);    // reference heuristics.c:476-486; applied by the next two launches
+        ctl->sweep_moves += 1;
+        ctl->pairs_swept += (long long)(f - ((unsigned long long)i0 * n + j0)) + 1;
+        ci = i;
+        cj = j + 1;
+        if (cj >= n) { ci = i + 1; cj = ci + 1; }
+        if (ci >= n - 1) sweep_end = true;
+    } else {
+        sweep_end = true;
+        ctl->ap_valid = 0;
+        ctl->pairs_swept += (long long)((unsigned long long)(n - 1) * n - ((unsigned long long)i0 * n + j0));
+    }
+    ctl->launches += 1;
+    if (sweep_end) {
+        ctl->passes += 1;
+        if (ctl->sweep_moves == 0) {  // reference heuristics.c:492: the sweep brought no gain
+            ctl->done = 1;
+            ctl->done_reason = DONE_OPTIMUM;
+        }
+        ctl->sweep_moves = 0;
+        ci = 0;
+        cj = 1;
+    }
+    if (ctl->max_moves >= 0 && ctl->moves >= ctl->max_moves && !ctl->done) {  // a capped run may be continued later
+        ctl->done = 1;
+        ctl->done_reason = DONE_CAP;
+    }
+    ctl->cur_i = ci;
+    ctl->cur_j = cj;
+    ctl->fi_found = FI_NONE;
+    ctl->fi_seg = 0;
+    ctl->ticket = 0;
+}
+
 template <bool ATT, bool EXACT32, bool FP32_OK>
-__global__ void __launch_bounds__(FI_THREADS) fi_search_kernel(const InstDev I, const TourDev T) {
+__global__ void __launch_bounds__(FI_THREADS) fi_search_kernel(const InstDev I, const TourDev T, const FiShard S) {
     __shared__ int s_seg;
     __shared__ int s_minhit;
     __shared__ int s_last;
@@ -75,7 +130,7 @@ __global__ void __launch_bounds__(FI_THREADS) fi_search_kernel(const InstDev I, 
             s_found = *((volatile unsigned long long *)&ctl->fi_found);  // one read per block: the exit below must be uniform
         }
         __syncthreads();
-        const long long Abase = A0 + (long long)s_seg * SEG;
+        const long long Abase = A0 + ((long long)S.rank + (long long)S.world * (long long)s_seg) * SEG;
         if (Abase >= total) break;  // past the end of the sweep
         {
             int rb, jb;
@@ -148,7 +203,7 @@ __global__ void __launch_bounds__(FI_THREADS) fi_search_kernel(const InstDev I, 
         __syncthreads();  // s_seg / s_minhit are rewritten by the next round
     }
 
-    // ---- last block: apply the winning move / close the sweep ------------------------------------
+    // ---- last block: exchange (several GPUs), then publish the winning move / close the sweep ---------------
     __syncthreads();
     if (tid == 0) {
         __threadfence();
@@ -158,60 +213,58 @@ __global__ void __launch_bounds__(FI_THREADS) fi_search_kernel(const InstDev I, 
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    const unsigned long long f = *((volatile unsigned long long *)&ctl->fi_found);
-    int ci = 0, cj = 0;
-    bool sweep_end = false;
-    if (f != FI_NONE) {
-        const int i = (int)(f / (unsigned long long)n), j = (int)(f % (unsigned long long)n);
-        if (tid == 0) {
-            const long long delta = move_delta_nodes(I, T, i, j);
-            if (delta >= 0) ctl->error = 1;  // cannot happen: the searching thread saw delta < 0
-            publish_move(T, i, j, delta);    // reference heuristics.c:476-486; applied by the next two launches
-            ctl->sweep_moves += 1;
-            ctl->pairs_swept += (long long)(f - ((unsigned long long)i0 * n + j0)) + 1;
+    unsigned long long f = *((volatile unsigned long long *)&ctl->fi_found);
+    if (S.world > 1) {
+        if (!S.finish_here) {  // NCCL min-allreduce of ctl->fi_found follows, then fi_finish_kernel
+            if (tid == 0) ctl->ticket = 0;
+            return;
         }
-        ci = i;
-        cj = j + 1;
-        if (cj >= n) { ci = i + 1; cj = ci + 1; }
-        if (ci >= n - 1) sweep_end = true;
-    } else {
-        sweep_end = true;
-        if (tid == 0) ctl->ap_valid = 0;
-        if (tid == 0) ctl->pairs_swept += (long long)((unsigned long long)(n - 1) * n - ((unsigned long long)i0 * n + j0));
-    }
-    if (tid == 0) {
-        ctl->launches += 1;
-        if (sweep_end) {
-            ctl->passes += 1;
-            if (ctl->sweep_moves == 0) {  // reference heuristics.c:492: the sweep brought no gain
+        __shared__ unsigned long long s_x[XCHG_MAX_WORLD];
+        __shared__ int s_err;
+        if (tid == 0) s_err = 0;
+        __syncthreads();
+        const unsigned long long none62 = (1ull << 62) - 1ull;
+        const unsigned long long win = xchg_min(S.xchg, S.rank, S.world, f == FI_NONE ? none62 : f, s_x, &s_err, nullptr);
+        if (tid == 0) {
+            f = win == none62 ? FI_NONE : win;
+            if (s_err) {
+                ctl->error = 2;
                 ctl->done = 1;
                 ctl->done_reason = DONE_OPTIMUM;
+                f = FI_NONE;
             }
-            ctl->sweep_moves = 0;
-            ci = 0;
-            cj = 1;
         }
-        if (ctl->max_moves >= 0 && ctl->moves >= ctl->max_moves && !ctl->done) {  // a capped run may be continued later
-            ctl->done = 1;
-            ctl->done_reason = DONE_CAP;
-        }
-        ctl->cur_i = ci;
-        ctl->cur_j = cj;
-        ctl->fi_found = FI_NONE;
-        ctl->fi_seg = 0;
-        ctl->ticket = 0;
     }
+    if (tid == 0) fi_finish(I, T, f, i0, j0);
 }
 
-cudaError_t launch_fi_search(const InstDev &I, const TourDev &T, int grid, bool pdl, cudaStream_t st) {
+// NCCL variant: after ncclAllReduce(min) of ctl->fi_found every rank finishes the launch with the same pair.
+__global__ void fi_finish_kernel(const InstDev I, const TourDev T) {
+    Ctl *ctl = T.ctl;
+    if (ctl->done) { ctl->ap_valid = 0; return; }
+    fi_finish(I, T, ctl->fi_found, ctl->cur_i, ctl->cur_j);
+}
+
+cudaError_t launch_fi_finish(const InstDev &I, const TourDev &T, cudaStream_t st) {
+    fi_finish_kernel<<<1, 1, 0, st>>>(I, T);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fi_search(const InstDev &I, const TourDev &T, int rank, int world, const XchgDev *xchg, int grid, bool pdl,
+                             cudaStream_t st) {
     const bool att = (I.metric == M_ATT);
     const bool ex = I.exact32 != 0;
     const dim3 g(grid), b(FI_THREADS);
-    if (!I.fp32_ok) return launch_maybe_pdl(fi_search_kernel<false, false, false>, g, b, 0, st, pdl, I, T);
-    if (att && ex) return launch_maybe_pdl(fi_search_kernel<true, true, true>, g, b, 0, st, pdl, I, T);
-    if (att) return launch_maybe_pdl(fi_search_kernel<true, false, true>, g, b, 0, st, pdl, I, T);
-    if (ex) return launch_maybe_pdl(fi_search_kernel<false, true, true>, g, b, 0, st, pdl, I, T);
-    return launch_maybe_pdl(fi_search_kernel<false, false, true>, g, b, 0, st, pdl, I, T);
+    FiShard S{};
+    S.rank = rank;
+    S.world = world;
+    S.finish_here = (world == 1 || xchg != nullptr) ? 1 : 0;
+    if (xchg) S.xchg = *xchg;
+    if (!I.fp32_ok) return launch_maybe_pdl(fi_search_kernel<false, false, false>, g, b, 0, st, pdl, I, T, S);
+    if (att && ex) return launch_maybe_pdl(fi_search_kernel<true, true, true>, g, b, 0, st, pdl, I, T, S);
+    if (att) return launch_maybe_pdl(fi_search_kernel<true, false, true>, g, b, 0, st, pdl, I, T, S);
+    if (ex) return launch_maybe_pdl(fi_search_kernel<false, true, true>, g, b, 0, st, pdl, I, T, S);
+    return launch_maybe_pdl(fi_search_kernel<false, false, true>, g, b, 0, st, pdl, I, T, S);
 }
 
 }  // namespace tspb

@@ -69,7 +69,10 @@ __global__ void __launch_bounds__(MAT_THREADS) dist_matrix_kernel(const InstDev 
     const int nrows = min(MAT_ROWS, row_end - r0);
     const float MAGIC = 12582912.0f;  // 1.5 * 2^23: (r + MAGIC) holds rint(r) in its low mantissa bits
     const int MAGIC_BITS = 0x4B400000;
-    const float BAND = (KIND == MK_ATT) ? 4.76837158203125e-07f : 2.384185791015625e-07f;  // 2^-21 / 2^-22
+    // FP32 error of r relative to the real distance: dx, dy exact for integer coordinates (<= 3 roundings + MUFU.SQRT's
+    // 2^-23: below 2^-22); FP32-exact NON-integer coordinates add the roundings of dx and dy themselves (worst case 4 u =
+    // 2^-22 exactly), so their band is doubled instead of leaving the bound without margin.  ATT has one more multiply.
+    const float BAND = ((KIND == MK_ATT) ? 4.76837158203125e-07f : 2.384185791015625e-07f) * (I.int_coords ? 1.0f : 2.0f);
     float cx[4], cy[4];
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
@@ -155,7 +158,7 @@ __global__ void __launch_bounds__(MAT_THREADS) dist_matrix_kernel(const InstDev 
 
 // Any metric / any coordinates: every entry in FP64 with the reference's operation order.
 __global__ void __launch_bounds__(MAT_THREADS) dist_matrix_exact_kernel(const InstDev I, int *__restrict__ out, long long ld,
-                                                                        int row_begin, int row_end) {
+                                                                        int row_begin, int row_end, unsigned long long *geo_near) {
     const int n = I.n;
     const int j4 = (blockIdx.x * MAT_THREADS + threadIdx.x) * 4;
     if (j4 >= n) return;
@@ -171,11 +174,18 @@ __global__ void __launch_bounds__(MAT_THREADS) dist_matrix_exact_kernel(const In
 #pragma unroll
         for (int c = 0; c < 4; ++c) v[c] = (int)exact_dist(metric, pi, pj[c]);
         *reinterpret_cast<int4 *>(out + (long long)(i - row_begin) * ld + j4) = make_int4(v[0], v[1], v[2], v[3]);
+        if (metric == M_GEO && geo_near) {  // entries that sit on a rounding boundary (see geo_near_boundary)
+            int cnt = 0;
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                if (j4 + c < n && geo_near_boundary(exact_geo_len(pi.x, pi.y, pj[c].x, pj[c].y))) cnt++;
+            if (cnt) atomicAdd(geo_near, (unsigned long long)cnt);
+        }
     }
 }
 
 cudaError_t launch_dist_matrix(const InstDev &I, int *out, long long ld, int row_begin, int row_end, bool fast,
-                               cudaStream_t st) {
+                               unsigned long long *geo_near, cudaStream_t st) {
     int rows = row_end - row_begin;
     if (rows <= 0) return cudaSuccess;
     const unsigned gx = (unsigned)((I.n + MAT_THREADS * 4 - 1) / (MAT_THREADS * 4));
@@ -186,7 +196,7 @@ cudaError_t launch_dist_matrix(const InstDev &I, int *out, long long ld, int row
         else dist_matrix_kernel<MK_NINT><<<grid, MAT_THREADS, 0, st>>>(I, out, ld, row_begin, row_end);
     } else {
         dim3 grid(gx, (unsigned)((rows + MAT_ROWS_SLOW - 1) / MAT_ROWS_SLOW));
-        dist_matrix_exact_kernel<<<grid, MAT_THREADS, 0, st>>>(I, out, ld, row_begin, row_end);
+        dist_matrix_exact_kernel<<<grid, MAT_THREADS, 0, st>>>(I, out, ld, row_begin, row_end, geo_near);
     }
     return cudaGetLastError();
 }

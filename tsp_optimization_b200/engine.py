@@ -29,7 +29,7 @@ LOCAL_OPTIMUM, TIME_LIMIT_EXCEEDED, STOPPED_BY_CAP = 0, 2, 3
 ABI_SYMBOLS = [
     "tspb200_create", "tspb200_destroy", "tspb200_last_error", "tspb200_set_option", "tspb200_get_info",
     "tspb200_set_instance", "tspb200_dist_matrix_build", "tspb200_dist_matrix_get", "tspb200_dist_matrix",
-    "tspb200_dist_matrix_free", "tspb200_tour_upload", "tspb200_tour_download", "tspb200_tour_log",
+    "tspb200_dist_matrix_free", "tspb200_dist_row", "tspb200_tour_upload", "tspb200_tour_download", "tspb200_tour_log",
     "tspb200_bi_run", "tspb200_fi_run", "tspb200_two_opt", "tspb200_two_opt_tabu", "tspb200_two_opt_batch", "tspb200_nn_tour", "tspb200_nn_tour_batch", "tspb200_extra_mileage",
     "tspb200_tour_costs", "tspb200_comm_unique_id", "tspb200_comm_init", "tspb200_comm_destroy",
     "tspb200_debug_tile_plan", "tspb200_debug_fetch",
@@ -121,6 +121,8 @@ def load_library() -> C.CDLL:
     L.tspb200_comm_destroy.argtypes = [vp]
     L.tspb200_debug_tile_plan.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, i32p, i32p, i32p,
                                           C.c_void_p, C.c_void_p, C.c_int, i32p]
+    if hasattr(L, "tspb200_dist_row"):
+        L.tspb200_dist_row.argtypes = [vp, C.c_int, C.c_void_p]
     if hasattr(L, "tspb200_tour_cost"):
         L.tspb200_tour_cost.argtypes = [vp, C.POINTER(C.c_double)]
         L.tspb200_tour_save.argtypes = [vp, C.c_int]
@@ -235,6 +237,11 @@ class Engine:
     def dist_matrix_get(self) -> np.ndarray:
         out = np.empty((self.n, self.n), dtype=np.int32)
         self._ck(self.L.tspb200_dist_matrix_get(self.h, out.ctypes.data))
+        return out
+
+    def dist_row(self, i: int) -> np.ndarray:
+        out = np.empty(self.n, dtype=np.int32)
+        self._ck(self.L.tspb200_dist_row(self.h, int(i), out.ctypes.data))
         return out
 
     def dist_matrix_free(self):

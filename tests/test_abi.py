@@ -99,3 +99,20 @@ def test_c_example_compiles_against_the_public_header(tmp_path):
         assert r.returncode == 0 and "2-opt (first improvement)" in r.stdout, r.stdout + r.stderr
     else:
         assert r.returncode == 1 and "no CPU fallback" in r.stderr
+
+
+def test_vns_session_example_compiles_and_runs(tmp_path):
+    """examples/vns_resident.c: the reference's HEU_VNS loop on the resident-session entry points, plain C.  On a GPU it must
+    finish with the restored incumbent equal to the best cost it saw; without one it stops with the library's error."""
+    import subprocess
+    exe = str(tmp_path / "vns_resident")
+    lib = os.path.dirname(eng.LIB_PATH)
+    r = subprocess.run(["gcc", "-O2", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "examples", "vns_resident.c"), "-L" + lib, "-ltspb200", "-Wl,-rpath," + lib, "-o", exe],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe, "1500", "12", "123"], capture_output=True, text=True)
+    if HAVE_GPU:
+        assert r.returncode == 0 and "best tour after 12 kicks" in r.stdout, r.stdout + r.stderr
+    else:
+        assert r.returncode == 1 and "no CPU fallback" in r.stderr

@@ -8,6 +8,7 @@ from tsp_optimization_b200.instances import uniform_instance
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 100000
 passes = int(sys.argv[2]) if len(sys.argv) > 2 else 6
 eng = Engine(0)
+eng.set_option("prune", 0 if "exhaustive" in sys.argv else -1)  # the headline (roofline) kernel is the exhaustive scan
 xy = uniform_instance(n)
 eng.set_instance(xy, 0)
 z = np.load("tests/golden/nn_uni100000.npz") if n == 100000 else None

@@ -115,6 +115,7 @@ struct tspb200_ctx {
     int *d_mat = nullptr;
     long long mat_ld = 0;
     double dmax = 0;
+    std::vector<double> h_xy;         // host copy of the coordinates of the resident instance (set_instance short cut)
     float eps32 = 0;                  // bound of |FP32 distance - real distance| for this instance
     unsigned long long geo_near = 0;  // GEO matrix entries within 1e-6 of a rounding boundary (last matrix build)
 
@@ -143,6 +144,8 @@ struct tspb200_ctx {
 
     // BI tiling
     int T = 256, R = 8, TJ = 256, grid_bi = 296, ntr = 0, ntiles = 0;
+    long long shape_key[6] = {-1, -1, -1, -1, -1, -1};
+    int shape_T = 64, shape_R = 8, shape_TJ = 256;
     int *d_tile_row_start = nullptr, *d_tile_row_j0 = nullptr;
 
     // options
@@ -232,6 +235,7 @@ static void free_tour(tspb200_ctx *c) {
     cudaFree(c->tour.rec); cudaFree(c->tour.pos); cudaFree(c->tour.nrec); cudaFree(c->tour.nds);
     cudaFree(c->tour.nsucc); cudaFree(c->tour.block_best); cudaFree(c->tour.log);
     cudaFree(c->tour.rowbox); cudaFree(c->tour.colbox); cudaFree(c->tour.rowmaxds); cudaFree(c->tour.colmaxds);
+    cudaFree(c->tour.colbox2); cudaFree(c->tour.colmaxds2);
     cudaFree(c->tour.live); cudaFree(c->tour.live_lb);
     cudaFree(c->d_order); cudaFree(c->d_succ); cudaFree(c->d_cost);
     cudaFree(c->d_tile_row_start); cudaFree(c->d_tile_row_j0);
@@ -284,6 +288,7 @@ static void free_instance(tspb200_ctx *c) {
     c->d_raw = c->d_pt64 = nullptr; c->d_pt32 = nullptr; c->d_mat = nullptr;
     c->n = 0;
     c->inst_cap = 0;
+    c->h_xy.clear();
 }
 
 extern "C" {
@@ -428,6 +433,11 @@ int tspb200_set_instance(tspb200_ctx *ctx, const double *xy, int n, int weight_t
     if (!ctx || !ctx->stream) return fail(ctx, TSPB200_E_CUDA, "context has no CUDA device");
     if (!xy || n < 1) return fail(ctx, TSPB200_E_ARG, "bad instance (n=%d)", n);
     CK(cudaSetDevice(ctx->device));
+    // the very same instance again (callers such as the reference's drivers re-enter with unchanged coordinates): nothing to do,
+    // the device tables, a resident matrix and the sessions stay valid
+    if (n == ctx->n && weight_type == ctx->metric && ctx->h_xy.size() == (size_t)2 * n &&
+        memcmp(ctx->h_xy.data(), xy, sizeof(double) * 2 * (size_t)n) == 0)
+        return TSPB200_OK;
     if (n > ctx->inst_cap) {
         free_instance(ctx);
     } else {  // same buffers, new contents: whatever was derived from the old instance is void
@@ -450,7 +460,8 @@ int tspb200_set_instance(tspb200_ctx *ctx, const double *xy, int n, int weight_t
         if (!std::isfinite(x) || !std::isfinite(y)) finite = false;
         float fx = (float)x, fy = (float)y;
         if ((double)fx != x || (double)fy != y) exact32 = false;
-        if (x != std::nearbyint(x) || y != std::nearbyint(y)) int_coords = false;
+        if (int_coords && (std::fabs(x) >= 9.0e15 || std::fabs(y) >= 9.0e15 || x != (double)(long long)x || y != (double)(long long)y))
+            int_coords = false;
         dc = std::fmax(dc, std::fmax(std::fabs((double)fx - x), std::fabs((double)fy - y)));
         xmin = std::fmin(xmin, x); xmax = std::fmax(xmax, x);
         ymin = std::fmin(ymin, y); ymax = std::fmax(ymax, y);
@@ -498,6 +509,7 @@ int tspb200_set_instance(tspb200_ctx *ctx, const double *xy, int n, int weight_t
     ctx->inst.pt32 = ctx->d_pt32;
     ctx->inst.dmat = nullptr;
     ctx->inst.dmat_ld = 0;
+    ctx->h_xy.assign(xy, xy + 2 * (size_t)n);
     return TSPB200_OK;
 }
 
@@ -661,7 +673,13 @@ static bool prune_wanted(const tspb200_ctx *ctx) {
 
 static void plan_tiles(tspb200_ctx *ctx, std::vector<int> &row_start, std::vector<int> &row_j0) {
     const int world_eff = ctx->opt_debug_shard ? (ctx->opt_debug_shard >> 8) : ctx->world;
-    choose_tile_shape(ctx->n, ctx->num_sms, world_eff, ctx->opt_T, ctx->opt_R, ctx->opt_TJ, &ctx->T, &ctx->R, &ctx->TJ);
+    // the shape search costs ~0.2 ms of host time: remembered per (n, ranks, options)
+    const long long key[6] = {ctx->n, world_eff, ctx->opt_T, ctx->opt_R, ctx->opt_TJ, ctx->num_sms};
+    if (memcmp(key, ctx->shape_key, sizeof key) != 0) {
+        choose_tile_shape(ctx->n, ctx->num_sms, world_eff, ctx->opt_T, ctx->opt_R, ctx->opt_TJ, &ctx->shape_T, &ctx->shape_R, &ctx->shape_TJ);
+        memcpy(ctx->shape_key, key, sizeof key);
+    }
+    ctx->T = ctx->shape_T; ctx->R = ctx->shape_R; ctx->TJ = ctx->shape_TJ;
     // A pruned pass scans a few per cent of the tiles: small tiles (256 positions x 64 columns) hug the live region much
     // more tightly than the throughput shape (measured on uni100000: 64 x 4 x 64 -> 76 us per pass, 64 x 8 x 256 -> 130 us).
     if (prune_wanted(ctx) && ctx->inst.fp32_ok && ctx->opt_force_path <= 0 && ctx->n >= PRUNE_AUTO_MIN_N) {
@@ -774,13 +792,16 @@ int tspb200_tour_upload(tspb200_ctx *ctx, const int32_t *succ, int64_t log_cap) 
         const int box_need = n / 32 + 8;  // >= tile-columns at the smallest tile width and >= tile-rows
         if (box_need > ctx->box_cap) {
             cudaFree(ctx->tour.rowbox); cudaFree(ctx->tour.colbox); cudaFree(ctx->tour.rowmaxds); cudaFree(ctx->tour.colmaxds);
-            ctx->tour.rowbox = ctx->tour.colbox = nullptr;
-            ctx->tour.rowmaxds = ctx->tour.colmaxds = nullptr;
+            cudaFree(ctx->tour.colbox2); cudaFree(ctx->tour.colmaxds2);
+            ctx->tour.rowbox = ctx->tour.colbox = ctx->tour.colbox2 = nullptr;
+            ctx->tour.rowmaxds = ctx->tour.colmaxds = ctx->tour.colmaxds2 = nullptr;
             ctx->box_cap = 0;
             CK(cudaMalloc(&ctx->tour.rowbox, sizeof(float4) * (size_t)box_need));
             CK(cudaMalloc(&ctx->tour.colbox, sizeof(float4) * (size_t)box_need));
             CK(cudaMalloc(&ctx->tour.rowmaxds, sizeof(float) * (size_t)box_need));
             CK(cudaMalloc(&ctx->tour.colmaxds, sizeof(float) * (size_t)box_need));
+            CK(cudaMalloc(&ctx->tour.colbox2, sizeof(float4) * (size_t)box_need));
+            CK(cudaMalloc(&ctx->tour.colmaxds2, sizeof(float) * (size_t)box_need));
             ctx->box_cap = box_need;
         }
         const long long live_need = (long long)ctx->ntiles + 32;
@@ -935,6 +956,10 @@ int tspb200_bi_run(tspb200_ctx *ctx, int64_t max_passes, tspb200_stats *st) {
     a.xchg.enabled = use_xchg ? 1 : 0;
     // programmatic dependent launch along the (prune ->) scan -> apply chain; not across a NCCL collective
     const bool pdl = path == 0 && !ctx->tabu_on && ctx->opt_pdl && (ctx->world == 1 || use_xchg);
+    // "seed_hint" = 2: the apply launch's last block re-evaluates every block winner of the pass and seeds the next pass's
+    // filter with the best one that is still legal.  It halves the exact-path calls of a one-wave pass (n = 10 000: 356 k ->
+    // 188 k per run) but lengthens the serial section by ~5 us, a net loss (36.4 vs 32.3 us per pass): off by default.
+    const bool seed_all = path == 0 && !prune && ctx->opt_seed_hint >= 2;
     int rc = sync_ctl(ctx);
     if (rc) return rc;
     rc = prepare_run(ctx, false, -1);
@@ -1004,8 +1029,9 @@ int tspb200_bi_run(tspb200_ctx *ctx, int64_t max_passes, tspb200_stats *st) {
                 host_launches++;
             }
             if (!fuse_in_kernel) {
-                CK(launch_apply_move(I, ctx->tour, ctx->num_sms, (path == 0 && ctx->opt_seed_hint >= 2) ? 1 : 0, ctx->opt_timing,
-                                     pdl, ctx->stream));
+                // exhaustive scan: the apply launch's last block seeds the next pass's filter from all block winners (the
+                // pruned mode's tile_boxes_kernel does the same before its filter)
+                CK(launch_apply_move(I, ctx->tour, ctx->num_sms, seed_all ? ctx->grid_bi : 0, ctx->opt_timing, pdl, ctx->stream));
                 host_launches++;
             }
             if (flush) CK(cudaEventRecord(ctx->pass_events[2 * q + 1], ctx->stream));

@@ -529,6 +529,7 @@ __global__ void bi_decode_packed_kernel(const TourDev tour) {
 }
 
 // Grid-wide application of the published move (see apply_swap_range).
+// seed: number of block_best[] entries (the scan's grid size) to re-evaluate as seeds of the next pass's filter, 0 = none
 __global__ void __launch_bounds__(256) apply_move_kernel(const InstDev inst, const TourDev tour, int seed, int timing) {
     __shared__ int s_last;
     Ctl *ctl = tour.ctl;
@@ -542,7 +543,10 @@ __global__ void __launch_bounds__(256) apply_move_kernel(const InstDev inst, con
         if (threadIdx.x == 0) atomicMax(&ctl->tm_apply_end, globaltimer_ns());
     }
     if (!seed) return;
-    // last block done: seed the next pass's filter from the runner-up moves (BI only)
+    // last block done: seed the next pass's filter (BI only).  Every block winner of the pass that just ended is re-evaluated in
+    // the tour as it is NOW; the best one that is still a legal move bounds the next pass's minimum, so every block of the
+    // next scan starts with a tight threshold instead of re-discovering its own local winner through the exact path
+    // (~700 exact-path calls per pass at n = 10 000 without it, a handful with it).
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -553,7 +557,14 @@ __global__ void __launch_bounds__(256) apply_move_kernel(const InstDev inst, con
     if (!s_last) return;
     __threadfence();
     if (threadIdx.x == 0) ctl->apply_ticket = 0;
-    seed_hint_from_candidates(inst, tour, threadIdx.x);
+    int best = 0;
+    for (int c = threadIdx.x; c < seed; c += 256) {
+        const long long d = legal_move_delta_cg(inst, tour, key_load_cg(&tour.block_best[c]));
+        if (d < best) best = (int)d;
+    }
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, m));
+    if ((threadIdx.x & 31) == 0 && best < 0) atomicMin(&ctl->hint, best);
 }
 
 __global__ void __launch_bounds__(256) refresh_node_space_kernel(const TourDev tour) {
@@ -576,7 +587,7 @@ __global__ void __launch_bounds__(256) refresh_node_space_kernel(const TourDev t
 // FP32 records; W (>= 2 + the FP32 / coordinate-rounding error of a distance, see set_instance) plus 1 is subtracted,
 // far more than the roundings of the few operations below can add up to.
 __global__ void __launch_bounds__(64) tile_boxes_kernel(const InstDev inst, const TourDev tour, int TI, int TJ, int ntr, int ncb,
-                                                        int nseed) {
+                                                        int ncb2, int nseed) {
     __shared__ float s_r[2][5];
     Ctl *ctl = tour.ctl;
     pdl_launch_dependents();
@@ -585,18 +596,18 @@ __global__ void __launch_bounds__(64) tile_boxes_kernel(const InstDev inst, cons
     const int n = tour.n;
     const int tid = threadIdx.x;
     const int b = blockIdx.x;
-    if (b >= ntr + ncb) {
+    if (b >= ntr + ncb + ncb2) {
         // every block winner of the previous pass that is still a legal move bounds this pass's minimum
-        const int c = (b - ntr - ncb) * 64 + tid;
+        const int c = (b - ntr - ncb - ncb2) * 64 + tid;
         if (c < nseed) {
             const long long d = legal_move_delta_cg(inst, tour, key_load_cg(&tour.block_best[c]));
             if (d < 0) atomicMin(&ctl->hint, (int)d);
         }
         return;
     }
-    const bool is_row = b < ntr;
-    const int start = is_row ? b * TI : (b - ntr) * TJ;
-    const int len = is_row ? TI : TJ;
+    const bool is_row = b < ntr, is_coarse = b >= ntr + ncb;
+    const int start = is_row ? b * TI : (is_coarse ? (b - ntr - ncb) * PRUNE_GROUP * TJ : (b - ntr) * TJ);
+    const int len = is_row ? TI : (is_coarse ? PRUNE_GROUP * TJ : TJ);
     const int end = min(start + len, n);  // inclusive: the successor of the last position (position n mirrors position 0)
     float xmin = TSPB_BIG, ymin = TSPB_BIG, xmax = -TSPB_BIG, ymax = -TSPB_BIG, mds = -TSPB_BIG;
     for (int p = start + tid; p <= end; p += 64) {
@@ -623,35 +634,56 @@ __global__ void __launch_bounds__(64) tile_boxes_kernel(const InstDev inst, cons
                                        fmaxf(s_r[0][3], s_r[1][3]));
         const float m = fmaxf(s_r[0][4], s_r[1][4]);
         if (is_row) { tour.rowbox[b] = box; tour.rowmaxds[b] = m; }
+        else if (is_coarse) { tour.colbox2[b - ntr - ncb] = box; tour.colmaxds2[b - ntr - ncb] = m; }
         else { tour.colbox[b - ntr] = box; tour.colmaxds[b - ntr] = m; }
     }
 }
 
-// One thread per tile of this rank (tile ids rank, rank + world, ...): live tiles are appended to tour.live / live_lb.
-__global__ void __launch_bounds__(256) tile_filter_kernel(const BiArgs A) {
+// Two-level filter, one block per tile-row: first the coarse boxes (PRUNE_GROUP tile-columns each — a superset of their
+// tiles' boxes, so a dead group has only dead tiles), then the tiles of the surviving groups.  With a few per cent of the
+// tiles alive the second level touches a small fraction of the ~3*10^5 tiles of a 100 000-node tour.  Live tiles of this rank
+// (tile ids rank, rank + world, ...) are appended to tour.live / live_lb.
+__device__ __forceinline__ float tile_lower_bound(const float4 rb, float rmax, const float4 cb, float cmax, float scale, float W) {
+    const float dx = fmaxf(0.f, fmaxf(rb.x - cb.z, cb.x - rb.z));
+    const float dy = fmaxf(0.f, fmaxf(rb.y - cb.w, cb.y - rb.w));
+    const float bd = sqrtf(fmaf(dy, dy, dx * dx)) * scale;
+    return 2.0f * bd - rmax - cmax - W - 1.0f;
+}
+
+__global__ void __launch_bounds__(128) tile_filter_kernel(const BiArgs A) {
+    extern __shared__ int s_groups[];
+    __shared__ int s_ng;
     Ctl *ctl = A.tour.ctl;
     pdl_launch_dependents();
     pdl_wait();
     if (*((volatile int *)&ctl->done)) return;
-    const int I = blockIdx.y;
+    const int I = blockIdx.x;
     const int rs = A.tile_row_start[I], cnt = A.tile_row_start[I + 1] - rs, j0 = A.tile_row_j0[I];
     const float hint = (float)__ldcg(&ctl->hint);
     const float4 rb = __ldcg(&A.tour.rowbox[I]);
     const float rmax = __ldcg(&A.tour.rowmaxds[I]);
     const float scale = (A.inst.metric == M_ATT) ? 0.31622773f : 0.99999905f;  // just below 1/sqrt(10) and 1
-    const int lane = threadIdx.x & 31;
-    const int cnt32 = (cnt + 31) & ~31;
-    for (int c = blockIdx.x * 256 + threadIdx.x; c < cnt32; c += gridDim.x * 256) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (tid == 0) s_ng = 0;
+    __syncthreads();
+    const int K0 = j0 / PRUNE_GROUP, K1 = (j0 + cnt - 1) / PRUNE_GROUP;
+    for (int K = K0 + tid; K <= K1; K += 128) {
+        const float lb2 = tile_lower_bound(rb, rmax, __ldcg(&A.tour.colbox2[K]), __ldcg(&A.tour.colmaxds2[K]), scale, A.inst.W);
+        if (!(lb2 > hint)) s_groups[atomicAdd(&s_ng, 1)] = K;
+    }
+    __syncthreads();
+    const int total = s_ng * PRUNE_GROUP;
+    for (int w = tid; w < ((total + 31) & ~31); w += 128) {
         bool live = false;
         float lb = 0.f;
-        if (c < cnt && (rs + c) % A.world == A.rank) {
-            const int J = j0 + c;
-            const float4 cb = __ldcg(&A.tour.colbox[J]);
-            const float dx = fmaxf(0.f, fmaxf(rb.x - cb.z, cb.x - rb.z));
-            const float dy = fmaxf(0.f, fmaxf(rb.y - cb.w, cb.y - rb.w));
-            const float bd = sqrtf(fmaf(dy, dy, dx * dx)) * scale;
-            lb = 2.0f * bd - rmax - __ldcg(&A.tour.colmaxds[J]) - A.inst.W - 1.0f;
-            live = !(lb > hint);
+        int t = 0;
+        if (w < total) {
+            const int J = s_groups[w / PRUNE_GROUP] * PRUNE_GROUP + (w % PRUNE_GROUP);
+            t = rs + (J - j0);
+            if (J >= j0 && J < j0 + cnt && t % A.world == A.rank) {
+                lb = tile_lower_bound(rb, rmax, __ldcg(&A.tour.colbox[J]), __ldcg(&A.tour.colmaxds[J]), scale, A.inst.W);
+                live = !(lb > hint);
+            }
         }
         const unsigned mask = __ballot_sync(0xffffffffu, live);
         if (mask) {
@@ -660,7 +692,7 @@ __global__ void __launch_bounds__(256) tile_filter_kernel(const BiArgs A) {
             base = __shfl_sync(0xffffffffu, base, __ffs(mask) - 1);
             if (live) {
                 const unsigned idx = base + __popc(mask & ((1u << lane) - 1u));
-                A.tour.live[idx] = rs + c;
+                A.tour.live[idx] = t;
                 A.tour.live_lb[idx] = lb;
             }
         }
@@ -669,15 +701,13 @@ __global__ void __launch_bounds__(256) tile_filter_kernel(const BiArgs A) {
 
 cudaError_t launch_tile_prune(const BiArgs &a, int TI, int grid_bi, bool pdl, cudaStream_t st) {
     const int ncb = (a.tour.n - 1) / a.TJ + 1;
+    const int ncb2 = (ncb + PRUNE_GROUP - 1) / PRUNE_GROUP;
     const int nseed = grid_bi;
-    const int gb = a.ntr + ncb + (nseed + 63) / 64;
-    cudaError_t e = launch_maybe_pdl(tile_boxes_kernel, dim3(gb), dim3(64), 0, st, pdl, a.inst, a.tour, TI, a.TJ, a.ntr, ncb, nseed);
+    const int gb = a.ntr + ncb + ncb2 + (nseed + 63) / 64;
+    cudaError_t e = launch_maybe_pdl(tile_boxes_kernel, dim3(gb), dim3(64), 0, st, pdl, a.inst, a.tour, TI, a.TJ, a.ntr, ncb, ncb2, nseed);
     if (e != cudaSuccess) return e;
-    int maxcnt = 1;
-    if (a.ntr > 0) maxcnt = (a.tour.n - 1) / a.TJ + 1;
-    dim3 gf((unsigned)((maxcnt + 255) / 256), (unsigned)(a.ntr > 0 ? a.ntr : 1));
     if (a.ntr == 0) return cudaSuccess;
-    return launch_maybe_pdl(tile_filter_kernel, gf, dim3(256), 0, st, pdl, a);
+    return launch_maybe_pdl(tile_filter_kernel, dim3((unsigned)a.ntr), dim3(128), sizeof(int) * (size_t)(ncb2 + 2), st, pdl, a);
 }
 
 // ---- cross-rank alignment barrier (benchmarks): every rank bumps its counter in every peer's XchgMem and waits until all

@@ -68,6 +68,7 @@ struct Ctl {
     unsigned long long tm_acc[8];   // see TM_* below
 };
 constexpr int CTL_NCAND = 4;
+constexpr int PRUNE_GROUP = 16;  // tile-columns per coarse box of the two-level tile filter
 enum { DONE_NONE = 0, DONE_OPTIMUM = 1, DONE_CAP = 2 };
 // tm_acc slots, all in ns summed over passes: gap between the previous apply's end and the first scan block's start,
 // scan (first block start -> last block's ticket), spread (first block end -> last block end), tail (ticket -> move
@@ -88,8 +89,8 @@ struct TourDev {
     long long log_cap;
     // exact tile pruning: bounding boxes {xmin, ymin, xmax, ymax} and largest edge length of every tile-row (TI positions
     // + the successor of the last one) and tile-column (TJ positions + successor); live tile ids + their lower bounds
-    float4 *rowbox, *colbox;
-    float *rowmaxds, *colmaxds;
+    float4 *rowbox, *colbox, *colbox2;   // colbox2: groups of PRUNE_GROUP consecutive tile-columns (first level of the filter)
+    float *rowmaxds, *colmaxds, *colmaxds2;
     int *live;
     float *live_lb;
 };

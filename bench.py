@@ -380,6 +380,8 @@ def main():
     eng.set_option("l2_flush_bytes", 0)
     gpu_ms, launches, moves, done_passes = maxr(st.gpu_ms), st.launches, st.moves, st.passes
     value = done_passes * pairs / (gpu_ms * 1e-3)
+    # the tile shape / grid `value` was measured with (later legs — pruned runs, other sizes — re-plan the tiles)
+    shape_value = {k: eng.info(k) for k in ("block_threads", "rows_per_thread", "tile_cols", "grid_bi", "ntiles")}
     tour_after, _ = eng.tour_download()
     chk_value = fixture.check_after_passes(tour_after, args.warmup + done_passes)
     clocks = sampler.stop(t_region0, t_region1)
@@ -548,7 +550,7 @@ def main():
     # (one sqrt) per evaluated move: every D[p][q] is shared by the two moves that use it.
     sqrt_peak = num_sms * 16 * sm_mhz * 1e6
     fp32_peak = num_sms * 128 * sm_mhz * 1e6
-    T, R, TJ = eng.info("block_threads"), eng.info("rows_per_thread"), eng.info("tile_cols")
+    T, R, TJ = shape_value["block_threads"], shape_value["rows_per_thread"], shape_value["tile_cols"]
     ncu = {}
     if os.path.exists(NCU_KEYED):
         with open(NCU_KEYED) as f:
@@ -596,7 +598,7 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": gpu_ms / max(1, done_passes), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": cfg,
-            "engine": {"block_threads": T, "rows_per_thread": R, "tile_cols": TJ, "grid": eng.info("grid_bi"), "tiles": eng.info("ntiles"),
+            "engine": {"block_threads": T, "rows_per_thread": R, "tile_cols": TJ, "grid": shape_value["grid_bi"], "tiles": shape_value["ntiles"],
                        "sharding": ("tiles round-robin over ranks; per pass each rank's 8-byte argmin key is " +
                                     ("stored into every peer's slots over NVLink by the scan kernel (CUDA IPC peer memory)"
                                      if eng.info("exchange_p2p") else "min-allreduced by NCCL")) if world > 1 else "single GPU",

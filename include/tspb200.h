@@ -102,7 +102,9 @@ const char *tspb200_last_error(const tspb200_ctx *ctx);
  * "prune" (exact tile pruning of the best-improvement scan: -1 auto = on for n >= 3000, 0 = exhaustive scan, 1 = on;
  * the selected moves are identical either way), "timing" (1 = accumulate the per-pass breakdown read back through
  * tspb200_get_info("tm_scan" ...), 2 = also per-block time stamps), "batch_kernel" (batched best improvement: 0 =
- * position-space block kernel where applicable, 1 = node-space kernel). */
+ * position-space block kernel where applicable, 1 = node-space kernel), "nn_grid" (tspb200_nn_tour: -1 auto = the
+ * bucket-grid walk for EUC_2D / CEIL_2D / ATT with n >= 256, 0 = always the grid-wide scan, 1 = the walk whenever the metric
+ * allows; same tour either way), "fi_shard_min_gap" (several GPUs, see below). */
 int tspb200_set_option(tspb200_ctx *ctx, const char *key, int64_t value);
 int64_t tspb200_get_info(const tspb200_ctx *ctx, const char *key);
 
@@ -210,7 +212,9 @@ int tspb200_population_two_opt(tspb200_ctx *ctx, int mode, const int32_t *slots,
  * per pass every rank's packed (delta, i, j) key is stored into every peer's exchange slots over NVLink by the scan kernel
  * itself (CUDA IPC peer memory mapped at comm_init; option "exchange" = 1 or a failed mapping falls back to one 8-byte
  * NCCL min-allreduce per pass) and every rank applies the same move to its own replica of the tour.  tspb200_fi_run
- * shards the first-improvement search the same way (segments of the pair order dealt over the ranks). */
+ * shards the first-improvement search the same way (segments of the pair order dealt over the ranks) whenever the previous
+ * search had to sweep more than "fi_shard_min_gap" pairs (default 4 000 000; 0 = always): while moves are dense an exchange
+ * per move costs more than the search, so every rank then searches alone — identical results either way. */
 int tspb200_comm_unique_id(void *id128); /* 128 bytes out (ncclUniqueId), call on rank 0 */
 int tspb200_comm_init(tspb200_ctx *ctx, const void *id128, int rank, int world);
 int tspb200_comm_destroy(tspb200_ctx *ctx);

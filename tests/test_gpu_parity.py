@@ -656,6 +656,60 @@ def test_nn_uni100000_equals_committed_fixture(engine):
     assert (succ == z["succ"]).all() and cost == float(z["cost"])
 
 
+def _nn_grid_cases():
+    rng = np.random.default_rng(77)
+    cases = []
+    cases.append(("uniform_int_ties", np.floor(rng.random((3000, 2)) * 60.0), 0))            # small integer box: masses of equal distances
+    cases.append(("duplicates", np.repeat(np.floor(rng.random((500, 2)) * 1000.0), 4, axis=0), 0))
+    cl = np.concatenate([rng.normal(c, 30.0, (600, 2)) for c in ((0, 0), (5000, 200), (-3000, 9000), (100000, 100000))])
+    cases.append(("clusters_far_apart", np.round(cl, 3), 0))                                 # long jumps: rings run out, whole-block scan
+    cases.append(("collinear", np.stack([np.floor(rng.random(2000) * 1e5), np.zeros(2000)], axis=1), 0))
+    cases.append(("ceil_decimal", np.round(rng.random((2500, 2)) * 5000.0, 2), 3))
+    cases.append(("att", np.floor(rng.random((2500, 2)) * 8000.0), 5))
+    cases.append(("negative_half_integers", np.floor(rng.random((2000, 2)) * 4000.0) / 2.0 - 1000.0, 0))
+    cases.append(("tall_box", np.stack([np.floor(rng.random(1500) * 30.0), np.floor(rng.random(1500) * 1e6)], axis=1), 0))
+    return cases
+
+
+@pytest.mark.parametrize("case", _nn_grid_cases(), ids=lambda c: c[0])
+def test_nn_bucket_grid_walk_equals_oracle(engine, oracle, case):
+    """reference src/heuristics.c:18-78 greedy on the bucket grid (csrc/kernels_nn.cu): the tour of the oracle's full scan, node
+    for node, whatever the ties / empty neighbourhoods, and the same tour as the grid-wide kernel it replaces."""
+    nm, xy, wt = case
+    engine.set_instance(xy, wt)
+    try:
+        for start in (0, len(xy) - 1, len(xy) // 3):
+            engine.set_option("nn_grid", 1)
+            s, c = engine.nn_tour(start)
+            es, ec = oracle.nn_tour(xy, wt, start)
+            assert (s == es).all() and c == ec, (nm, start)
+        engine.set_option("nn_grid", 0)
+        s0, c0 = engine.nn_tour(0)
+        es, ec = oracle.nn_tour(xy, wt, 0)
+        assert (s0 == es).all() and c0 == ec, nm
+    finally:
+        engine.set_option("nn_grid", -1)
+
+
+def test_nn_bucket_grid_small_and_degenerate(engine, oracle):
+    """forced onto the bucket grid: tiny instances, all points equal, two points"""
+    for n in (2, 3, 5, 17, 64, 255):
+        xy = np.floor(np.random.default_rng(n).random((n, 2)) * 50.0)
+        engine.set_instance(xy, 0)
+        engine.set_option("nn_grid", 1)
+        try:
+            s, c = engine.nn_tour(n - 1)
+        finally:
+            engine.set_option("nn_grid", -1)
+        es, ec = oracle.nn_tour(xy, 0, n - 1)
+        assert (s == es).all() and c == ec, n
+    xy = np.full((300, 2), 7.0)
+    engine.set_instance(xy, 0)
+    s, c = engine.nn_tour(5)
+    es, ec = oracle.nn_tour(xy, 0, 5)
+    assert (s == es).all() and c == ec
+
+
 # ---- extra mileage (reference HEU_extramileage, src/heuristics.c:208-314) and the remaining published CSV columns ------
 @pytest.mark.parametrize("nm", ["berlin52", "pr299", "att532", "gr666", "dsj1000", "ulysses22", "eil51"])
 def test_extra_mileage_equals_reference_driver(engine, reflib, instances, nm):

@@ -51,10 +51,13 @@ def main():
             s2, o2, st2, log2 = eng.two_opt(BI, succ0, 0.0, max_iters=passes, log_cap=passes + 8)
             times[name + ("_pruned" if prune else "")] = st2.gpu_ms
             ok = ok and (s1 == s2).all() and o1 == o2 and log1.tolist() == log2.tolist() and st1.passes == st2.passes
-        # first improvement: the segments of the pair order dealt over the ranks
-        f2, fo2, fst2, flog2 = eng.two_opt(FI, succ0, c0, max_iters=fi_moves, log_cap=fi_moves + 8)
-        times["fi_" + name] = fst2.gpu_ms
-        ok = ok and (f1 == f2).all() and fo1 == fo2 and flog1.tolist() == flog2.tolist() and fst1.moves == fst2.moves
+        # first improvement: the segments of the pair order dealt over the ranks — for every search (gap 0), only after a
+        # search longer than 20 000 pairs (the decision flips many times in a run of this size), and with the default threshold
+        for gap, tag in ((0, ""), (20000, "_mixed"), (4000000, "_auto")):
+            eng.set_option("fi_shard_min_gap", gap)
+            f2, fo2, fst2, flog2 = eng.two_opt(FI, succ0, c0, max_iters=fi_moves, log_cap=fi_moves + 8)
+            times["fi_" + name + tag] = fst2.gpu_ms
+            ok = ok and (f1 == f2).all() and fo1 == fo2 and flog1.tolist() == flog2.tolist() and fst1.moves == fst2.moves
     eng.set_option("exchange", 0)
     eng.set_option("prune", -1)
     p2p = eng.info("exchange_p2p")
@@ -67,7 +70,7 @@ def main():
         print(f"MGPU_CHECK world={world} n={n} passes={st2.passes} moves={st2.moves} "
               f"single_ms={st1.gpu_ms:.2f} sharded_p2p_ms={times['p2p']:.2f} sharded_nccl_ms={times['nccl']:.2f} "
               f"pruned_p2p_ms={times['p2p_pruned']:.2f} fi_moves={fst2.moves} fi_single_ms={fst1.gpu_ms:.2f} fi_p2p_ms={times['fi_p2p']:.2f} "
-              f"fi_nccl_ms={times['fi_nccl']:.2f} "
+              f"fi_nccl_ms={times['fi_nccl']:.2f} fi_p2p_mixed_ms={times['fi_p2p_mixed']:.2f} fi_p2p_auto_ms={times['fi_p2p_auto']:.2f} "
               f"p2p_enabled={p2p} {'OK' if same else 'MISMATCH'}", flush=True)
     eng.close()
     dist.destroy_process_group()

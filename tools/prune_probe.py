@@ -28,7 +28,10 @@ def main():
         eng.set_instance(xy, 0)
         succ0, _ = eng.nn_tour(0)
         for prune, cap in ((0, 300 if n > 20000 else -1), (1, -1)):
-            for shape in ([None] if prune == 0 else [None, (64, 8, 128), (64, 8, 64), (64, 4, 128), (64, 4, 64), (128, 8, 128)]):
+            shapes = [None, (64, 8, 128), (64, 8, 64), (64, 4, 128), (64, 4, 64), (128, 8, 128)]
+            if os.environ.get("PRUNE_SHAPES"):  # e.g. PRUNE_SHAPES=64x2x64,64x4x32
+                shapes = [None] + [tuple(int(v) for v in t.split("x")) for t in os.environ["PRUNE_SHAPES"].split(",")]
+            for shape in ([None] if prune == 0 else shapes):
                 if shape:
                     eng.set_option("block_threads", shape[0]); eng.set_option("rows_per_thread", shape[1]); eng.set_option("tile_cols", shape[2])
                 else:

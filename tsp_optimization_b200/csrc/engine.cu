@@ -27,12 +27,11 @@ cudaError_t launch_bi_scan_exact(const InstDev &inst, const TourDev &tour, int r
 cudaError_t launch_bi_scan_tabu(const InstDev &inst, const TourDev &tour, int *skip, int iter, int tenure, long long *zl,
                                 unsigned long long *zl_count, long long zl_cap, int grid, cudaStream_t st);
 cudaError_t launch_bi_decode_packed(const TourDev &tour, cudaStream_t st);
-cudaError_t launch_apply_move(const InstDev &inst, const TourDev &tour, int num_sms, int seed, int timing, bool pdl,
+cudaError_t launch_apply_move(const InstDev &inst, const TourDev &tour, int num_sms, int seed, int timing, bool pdl, bool node_space,
                               cudaStream_t st);
 cudaError_t launch_tile_prune(const BiArgs &a, int TI, int grid_bi, bool pdl, cudaStream_t st);
 cudaError_t launch_rank_align(const XchgDev &x, int rank, int world, Ctl *ctl, cudaStream_t st);
 cudaError_t launch_rebuild_node_space(const TourDev &T, cudaStream_t st);
-cudaError_t launch_refresh_node_space(const TourDev &tour, int num_sms, bool pdl, cudaStream_t st);
 cudaError_t launch_fi_search(const InstDev &I, const TourDev &T, int rank, int world, const XchgDev *xchg, int grid, bool pdl,
                              cudaStream_t st);
 cudaError_t launch_fi_finish(const InstDev &I, const TourDev &T, cudaStream_t st);
@@ -43,6 +42,22 @@ cudaError_t launch_export_state(const TourDev &T, int *succ, unsigned long long 
 cudaError_t launch_tour_cost(const InstDev &I, const int *tours, const int *slots, int as_order, long long *out, int batch,
                              cudaStream_t st);
 cudaError_t launch_nn_tour(const NnArgs &a, int grid, cudaStream_t st);
+struct NnGridArgs {  // kernels_nn.cu
+    InstDev inst;
+    int start;
+    int GX, GY;
+    double xmin, ymin, h, inv_h;
+    double scale;
+    int *cell_cnt;
+    int *cell_fill;
+    double2 *spt;
+    int *snode;
+    int *start_spos;
+    int *succ;
+    long long *cost;
+};
+size_t nn_grid_smem_bytes(int n, int ncell);
+cudaError_t launch_nn_grid(const NnGridArgs &a, int num_sms, cudaStream_t st);
 cudaError_t launch_prep_points(const double2 *raw, double2 *pt64, float2 *pt32, int n, int metric, cudaStream_t st);
 int nn_max_grid(int num_sms);
 cudaError_t launch_extra_mileage(const InstDev &I, int *succ_out, long long *cost_out, unsigned char *gwork, bool force_global,
@@ -115,6 +130,9 @@ struct tspb200_ctx {
     int *d_mat = nullptr;
     long long mat_ld = 0;
     double dmax = 0;
+    double bb_xmin = 0, bb_xmax = 0, bb_ymin = 0, bb_ymax = 0;  // bounding box of the coordinates (bucket grid of the NN walk)
+    bool coords_finite = true;
+    int opt_nn_grid = -1;             // nearest neighbour on the bucket grid: -1 auto (planar metrics, n >= 256), 0 off, 1 on
     std::vector<double> h_xy;         // host copy of the coordinates of the resident instance (set_instance short cut)
     float eps32 = 0;                  // bound of |FP32 distance - real distance| for this instance
     unsigned long long geo_near = 0;  // GEO matrix entries within 1e-6 of a rounding boundary (last matrix build)
@@ -129,12 +147,12 @@ struct tspb200_ctx {
     int tile_cap = 0;                 // ints allocated in each tile table
     int box_cap = 0;                  // entries allocated in each of the pruning box arrays
     long long live_cap = 0;           // entries allocated in the live-tile list
-    bool node_dirty = false;          // best-improvement moves were applied since the node-space tables were built
+    bool node_dirty = false;          // the tour changed (upload, best-improvement moves, kicks, restore) since the node-space tables were built
     bool fi_cursor_stale = false;     // ... and the first-improvement sweep state refers to a tour that no longer exists
     double dist_bound = 0;            // upper bound of any distance of the instance (edge lengths live in FP32 words)
     // grow-only scratch buffers of the one-shot entry points (batched 2-opt, NN, tour costs, extra mileage)
-    void *scratch_ptr[16] = {};
-    size_t scratch_cap[16] = {};
+    void *scratch_ptr[24] = {};
+    size_t scratch_cap[24] = {};
     TourDev tour{};
     int *d_order = nullptr, *d_succ = nullptr;
     unsigned long long *d_cost = nullptr;
@@ -196,6 +214,7 @@ struct tspb200_ctx {
     void *peer_mapped[XCHG_MAX_WORLD] = {};
     std::string xchg_note;
     int opt_exchange = 0;  // 0 = peer memory when available, 1 = NCCL allreduce
+    long long opt_fi_shard_min_gap = 4000000;  // first improvement on several GPUs: searches longer than this many pairs are followed by a sharded one
 };
 
 static int fail(tspb200_ctx *c, int code, const char *fmt, ...) {
@@ -232,11 +251,11 @@ static void *dev_scratch(tspb200_ctx *c, int slot, size_t bytes) {
     } while (0)
 
 static void free_tour(tspb200_ctx *c) {
-    cudaFree(c->tour.rec); cudaFree(c->tour.pos); cudaFree(c->tour.nrec); cudaFree(c->tour.nds);
-    cudaFree(c->tour.nsucc); cudaFree(c->tour.block_best); cudaFree(c->tour.log);
+    cudaFree(c->tour.rec); cudaFree(c->tour.pos); cudaFree(c->tour.nrec); cudaFree(c->tour.nlnk);
+    cudaFree(c->tour.npxy); cudaFree(c->tour.block_best); cudaFree(c->tour.log);
     cudaFree(c->tour.rowbox); cudaFree(c->tour.colbox); cudaFree(c->tour.rowmaxds); cudaFree(c->tour.colmaxds);
     cudaFree(c->tour.colbox2); cudaFree(c->tour.colmaxds2);
-    cudaFree(c->tour.live); cudaFree(c->tour.live_lb);
+    cudaFree(c->tour.live);
     cudaFree(c->d_order); cudaFree(c->d_succ); cudaFree(c->d_cost);
     cudaFree(c->d_tile_row_start); cudaFree(c->d_tile_row_j0);
     c->tour = TourDev{};
@@ -369,6 +388,12 @@ int tspb200_set_option(tspb200_ctx *ctx, const char *key, int64_t value) {
     } else if (k == "timing") {
         if (value < 0 || value > 2) return fail(ctx, TSPB200_E_ARG, "timing must be 0, 1 or 2");
         ctx->opt_timing = (int)value;
+    } else if (k == "fi_shard_min_gap") {
+        if (value < 0) return fail(ctx, TSPB200_E_ARG, "fi_shard_min_gap must be >= 0 (0 = every search is sharded)");
+        ctx->opt_fi_shard_min_gap = value;
+    } else if (k == "nn_grid") {
+        if (value < -1 || value > 1) return fail(ctx, TSPB200_E_ARG, "nn_grid must be -1 (auto), 0 or 1");
+        ctx->opt_nn_grid = (int)value;
     } else if (k == "em_global") {
         ctx->opt_em_global = value ? 1 : 0;
     } else if (k == "batch_kernel") {
@@ -468,6 +493,8 @@ int tspb200_set_instance(tspb200_ctx *ctx, const double *xy, int n, int weight_t
     }
     double dmax = std::hypot(xmax - xmin, ymax - ymin);
     ctx->dmax = dmax;
+    ctx->bb_xmin = xmin; ctx->bb_xmax = xmax; ctx->bb_ymin = ymin; ctx->bb_ymax = ymax;
+    ctx->coords_finite = finite;
     // upper bound of any distance: the 2-opt state keeps edge lengths as exact integers in FP32 words (< 2^24)
     if (!finite) ctx->dist_bound = INFINITY;
     else if (weight_type == TSPB200_GEO) ctx->dist_bound = 20040.0;                        // pi * 6378.388 + 2
@@ -682,10 +709,13 @@ static void plan_tiles(tspb200_ctx *ctx, std::vector<int> &row_start, std::vecto
     ctx->T = ctx->shape_T; ctx->R = ctx->shape_R; ctx->TJ = ctx->shape_TJ;
     // A pruned pass scans a few per cent of the tiles: small tiles (256 positions x 64 columns) hug the live region much
     // more tightly than the throughput shape (measured on uni100000: 64 x 4 x 64 -> 76 us per pass, 64 x 8 x 256 -> 130 us).
+    // Mid-size tours have so few live tiles that a pass is one tile per block, i.e. as long as its slowest tile: smaller
+    // tiles still (n = 10 000: 64 x 2 x 32 -> 25.7 us per pass, 64 x 4 x 64 -> 28.1; n = 20 000: 64 x 4 x 32 -> 31.5, 64 x 4 x 64 -> 32.2;
+    // profiles/r2_prune_probe_small_tiles.jsonl).
     if (prune_wanted(ctx) && ctx->inst.fp32_ok && ctx->opt_force_path <= 0 && ctx->n >= PRUNE_AUTO_MIN_N) {
         if (!ctx->opt_T) ctx->T = 64;
-        if (!ctx->opt_R) ctx->R = 4;
-        if (!ctx->opt_TJ) ctx->TJ = 64;
+        if (!ctx->opt_R) ctx->R = ctx->n < 15000 ? 2 : 4;
+        if (!ctx->opt_TJ) ctx->TJ = ctx->n < 40000 ? 32 : 64;
         if (!bi_shape_supported(ctx->T, ctx->R)) { ctx->T = 64; ctx->R = 4; }
     }
     const int slots = ctx->num_sms * bi_blocks_per_sm(ctx->T, ctx->R);
@@ -702,10 +732,11 @@ static void plan_tiles(tspb200_ctx *ctx, std::vector<int> &row_start, std::vecto
 // last best-improvement pass run with option "timing" = 2).
 int tspb200_debug_fetch(tspb200_ctx *ctx, const char *what, void *out, int64_t bytes) {
     if (!ctx || !ctx->stream || !what || !out) return TSPB200_E_ARG;
-    if (std::string(what) != "block_times" || !ctx->d_dbg) return fail(ctx, TSPB200_E_STATE, "nothing recorded for %s", what);
-    const int64_t have = (int64_t)sizeof(unsigned long long) * 2 * 4096;
+    const bool phases = std::string(what) == "block_phases";  // [grid][8]: start, drawn, loaded, scanned, folded, tiles, ticket, -
+    if ((std::string(what) != "block_times" && !phases) || !ctx->d_dbg) return fail(ctx, TSPB200_E_STATE, "nothing recorded for %s", what);
+    const int64_t have = (int64_t)sizeof(unsigned long long) * (phases ? 8 : 2) * 4096;
     CK(cudaSetDevice(ctx->device));
-    CK(cudaMemcpyAsync(out, ctx->d_dbg, (size_t)(bytes < have ? bytes : have), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(out, ctx->d_dbg + (phases ? 8192 : 0), (size_t)(bytes < have ? bytes : have), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return TSPB200_OK;
 }
@@ -761,8 +792,8 @@ int tspb200_tour_upload(tspb200_ctx *ctx, const int32_t *succ, int64_t log_cap) 
         CK(cudaMalloc(&ctx->tour.rec, sizeof(float4) * (size_t)alloc));
         CK(cudaMalloc(&ctx->tour.pos, sizeof(int) * (size_t)n));
         CK(cudaMalloc(&ctx->tour.nrec, sizeof(float4) * (size_t)n));
-        CK(cudaMalloc(&ctx->tour.nds, sizeof(float) * (size_t)n));
-        CK(cudaMalloc(&ctx->tour.nsucc, sizeof(int) * (size_t)n));
+        CK(cudaMalloc(&ctx->tour.nlnk, sizeof(float4) * (size_t)n));
+        CK(cudaMalloc(&ctx->tour.npxy, sizeof(float2) * (size_t)n));
         CK(cudaMalloc(&ctx->tour.block_best, sizeof(MoveKey) * 4096));
         if (log_cap > 0) CK(cudaMalloc(&ctx->tour.log, sizeof(MoveRec) * (size_t)log_cap));
         CK(cudaMalloc(&ctx->d_order, sizeof(int) * (size_t)n));
@@ -804,13 +835,14 @@ int tspb200_tour_upload(tspb200_ctx *ctx, const int32_t *succ, int64_t log_cap) 
             CK(cudaMalloc(&ctx->tour.colmaxds2, sizeof(float) * (size_t)box_need));
             ctx->box_cap = box_need;
         }
-        const long long live_need = (long long)ctx->ntiles + 32;
+        // at least one entry per block of the scan grid: a block reads entry blockIdx.x before it knows how many are live
+        const long long live_need = (long long)(ctx->ntiles > 4096 ? ctx->ntiles : 4096) + 32;
         if (live_need > ctx->live_cap) {
-            cudaFree(ctx->tour.live); cudaFree(ctx->tour.live_lb);
-            ctx->tour.live = nullptr; ctx->tour.live_lb = nullptr;
+            cudaFree(ctx->tour.live);
+            ctx->tour.live = nullptr;
             ctx->live_cap = 0;
-            CK(cudaMalloc(&ctx->tour.live, sizeof(int) * (size_t)live_need));
-            CK(cudaMalloc(&ctx->tour.live_lb, sizeof(float) * (size_t)live_need));
+            CK(cudaMalloc(&ctx->tour.live, sizeof(int2) * (size_t)live_need));
+            CK(cudaMemsetAsync(ctx->tour.live, 0, sizeof(int2) * (size_t)live_need, ctx->stream));
             ctx->live_cap = live_need;
         }
     }
@@ -827,7 +859,7 @@ int tspb200_tour_upload(tspb200_ctx *ctx, const int32_t *succ, int64_t log_cap) 
     c0.pass_min = KEY_PACK_NONE;
     c0.tm_scan_first = c0.tm_blk_end_min = c0.tm_apply_first = ~0ull;
     *ctx->h_ctl = c0;
-    ctx->node_dirty = false;
+    ctx->node_dirty = true;  // the node-space tables are built by the first first-improvement run that needs them
     ctx->fi_cursor_stale = false;
     ctx->tour_changed = false;
     CK(cudaMemcpyAsync(ctx->d_ctl, ctx->h_ctl, sizeof(Ctl), cudaMemcpyHostToDevice, ctx->stream));
@@ -904,6 +936,8 @@ static int prepare_run(tspb200_ctx *ctx, bool reset_fi_cursor, long long max_mov
         h->fi_seg = 0;
     }
     h->max_moves = max_moves_abs;
+    h->fi_shard_min_gap = ctx->opt_fi_shard_min_gap;
+    if (reset_fi_cursor || ctx->opt_fi_shard_min_gap == 0) h->fi_shard = ctx->opt_fi_shard_min_gap == 0 ? 1 : 0;
     CK(cudaMemcpyAsync(ctx->d_ctl, h, sizeof(Ctl), cudaMemcpyHostToDevice, ctx->stream));
     return TSPB200_OK;
 }
@@ -945,7 +979,7 @@ int tspb200_bi_run(tspb200_ctx *ctx, int64_t max_passes, tspb200_stats *st) {
     a.seed_hint = ctx->opt_seed_hint;
     a.packed_tail = (path == 0 && packable && ctx->opt_seed_hint < 2) ? 1 : 0;
     a.timing = ctx->opt_timing;
-    if (a.timing == 2 && !ctx->d_dbg) CK(cudaMalloc(&ctx->d_dbg, sizeof(unsigned long long) * 2 * 4096));
+    if (a.timing == 2 && !ctx->d_dbg) CK(cudaMalloc(&ctx->d_dbg, sizeof(unsigned long long) * (2 + 8) * 4096));  // {start, end} + 8 phase stamps per block
     a.dbg = ctx->d_dbg;
     // exact tile pruning: same moves, fewer evaluated pairs (the throughput benchmarks switch it off: "prune" = 0)
     const bool prune = path == 0 && !ctx->tabu_on && ctx->ntr > 0 && prune_wanted(ctx);
@@ -1031,7 +1065,7 @@ int tspb200_bi_run(tspb200_ctx *ctx, int64_t max_passes, tspb200_stats *st) {
             if (!fuse_in_kernel) {
                 // exhaustive scan: the apply launch's last block seeds the next pass's filter from all block winners (the
                 // pruned mode's tile_boxes_kernel does the same before its filter)
-                CK(launch_apply_move(I, ctx->tour, ctx->num_sms, seed_all ? ctx->grid_bi : 0, ctx->opt_timing, pdl, ctx->stream));
+                CK(launch_apply_move(I, ctx->tour, ctx->num_sms, seed_all ? ctx->grid_bi : 0, ctx->opt_timing, pdl, false, ctx->stream));
                 host_launches++;
             }
             if (flush) CK(cudaEventRecord(ctx->pass_events[2 * q + 1], ctx->stream));
@@ -1114,7 +1148,7 @@ int tspb200_fi_run(tspb200_ctx *ctx, int64_t max_moves, tspb200_stats *st) {
         if (st) { memset(st, 0, sizeof *st); st->passes = 1; st->path = path; }
         return TSPB200_OK;
     }
-    if (ctx->node_dirty) {  // best-improvement moves do not maintain the node-space tables
+    if (ctx->node_dirty) {  // only the first-improvement apply launches keep the node-space tables current
         CK(launch_rebuild_node_space(ctx->tour, ctx->stream));
         ctx->node_dirty = false;
     }
@@ -1144,9 +1178,8 @@ int tspb200_fi_run(tspb200_ctx *ctx, int64_t max_moves, tspb200_stats *st) {
                     CK(launch_fi_finish(I, ctx->tour, ctx->stream));
                     host_launches++;
                 }
-                CK(launch_apply_move(I, ctx->tour, ctx->num_sms, 0, 0, pdl, ctx->stream));
-                CK(launch_refresh_node_space(ctx->tour, ctx->num_sms, pdl, ctx->stream));
-                host_launches += 2;
+                CK(launch_apply_move(I, ctx->tour, ctx->num_sms, 0, 0, pdl, true, ctx->stream));
+                host_launches += 1;
             }
             rc = sync_ctl(ctx);
             if (rc) return rc;
@@ -1412,6 +1445,47 @@ int tspb200_nn_tour(tspb200_ctx *ctx, int start, int32_t *succ, double *cost) {
     if (path == 2 && !ctx->d_mat) path = 1;
     InstDev I = inst_for_path(ctx, path == 2 ? 2 : 1);
     SCRATCH(d_succ, int *, 4, sizeof(int) * (size_t)n);
+    // Planar metrics: the walk over a bucket grid (kernels_nn.cu) — same tour, ~10x fewer microseconds per step.
+    const bool planar = ctx->metric == TSPB200_EUC_2D || ctx->metric == TSPB200_CEIL_2D || ctx->metric == TSPB200_ATT;
+    const bool grid_wanted = ctx->opt_nn_grid >= 0 ? ctx->opt_nn_grid == 1 : n >= 256;
+    if (planar && path != 2 && ctx->coords_finite && grid_wanted && n >= 2) {
+        const double W = ctx->bb_xmax - ctx->bb_xmin, H = ctx->bb_ymax - ctx->bb_ymin;
+        const long long nwords = ((long long)n + 31) / 32;
+        const long long cap = (200ll * 1024 - 4 * nwords) / 4 - 2;  // cells whose table fits one block's shared memory next to the bitmask
+        if (cap >= 16) {
+            double cells = std::fmin(std::fmax((double)n / 2.5, 1.0), (double)(cap < 40000 ? cap : 40000));
+            double h = (W > 0 && H > 0) ? std::sqrt(W * H / cells) : std::fmax(W, H) / cells;
+            if (!(h > 0)) h = 1.0;
+            long long gx, gy;
+            for (;;) {
+                gx = (long long)std::floor(W / h) + 1;
+                gy = (long long)std::floor(H / h) + 1;
+                if (gx * gy <= cap) break;
+                h *= 1.1;
+            }
+            NnGridArgs g;
+            g.inst = I; g.start = start; g.GX = (int)gx; g.GY = (int)gy;
+            g.xmin = ctx->bb_xmin; g.ymin = ctx->bb_ymin;
+            g.inv_h = 1.0 / h; g.h = 1.0 / g.inv_h;
+            g.scale = ctx->metric == TSPB200_ATT ? 3.1622776601683795 * (1.0 + 1e-12) : 1.0;
+            const size_t ncell = (size_t)(gx * gy);
+            SCRATCH(d_cells, int *, 16, sizeof(int) * (2 * ncell + 2));
+            SCRATCH(d_spt, double2 *, 17, sizeof(double2) * (size_t)n);
+            SCRATCH(d_snode, int *, 18, sizeof(int) * ((size_t)n + 1));
+            SCRATCH(d_gcost, long long *, 8, sizeof(long long));
+            g.cell_cnt = d_cells; g.cell_fill = d_cells + ncell + 1;
+            g.spt = d_spt; g.snode = d_snode; g.start_spos = d_snode + n;
+            g.succ = d_succ; g.cost = d_gcost;
+            cudaError_t ge = launch_nn_grid(g, ctx->num_sms, ctx->stream);
+            long long gc = 0;
+            if (ge == cudaSuccess) ge = cudaMemcpyAsync(succ, d_succ, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream);
+            if (ge == cudaSuccess) ge = cudaMemcpyAsync(&gc, d_gcost, sizeof gc, cudaMemcpyDeviceToHost, ctx->stream);
+            if (ge == cudaSuccess) ge = cudaStreamSynchronize(ctx->stream);
+            if (ge != cudaSuccess) return fail(ctx, TSPB200_E_CUDA, "nearest-neighbour grid kernels failed: %s", cudaGetErrorString(ge));
+            if (cost) *cost = (double)gc;
+            return TSPB200_OK;
+        }
+    }
     SCRATCH(d_vis, unsigned char *, 5, (size_t)n);
     SCRATCH(d_slots, unsigned long long *, 6, sizeof(unsigned long long) * 3);
     SCRATCH(d_bar, unsigned *, 7, sizeof(unsigned));
@@ -1584,6 +1658,7 @@ int tspb200_vns_kick(tspb200_ctx *ctx, int idx1, int idx2, int idx3, double *cos
     SCRATCH(d_scr, float4 *, 3, sizeof(float4) * (size_t)n);
     CK(launch_vns_kick(I, ctx->tour, idx1, idx2, idx3, d_scr, ctx->stream));
     ctx->fi_cursor_stale = true;  // the next alg_2opt starts a fresh sweep on the kicked tour
+    ctx->node_dirty = true;       // ... and rebuilds its node-space tables from the kicked records
     ctx->tour_changed = true;
     if (cost) return tspb200_tour_cost(ctx, cost);
     return TSPB200_OK;
@@ -1652,7 +1727,7 @@ int tspb200_tabu_kick(tspb200_ctx *ctx, const int32_t *pairs, int count, int ite
     int *d_acc = d_pairs + 2 * (size_t)count;
     CK(cudaMemcpyAsync(d_pairs, pairs, sizeof(int) * 2 * (size_t)count, cudaMemcpyHostToDevice, ctx->stream));
     CK(launch_tabu_kick_select(ctx->tour, ctx->d_skip, d_pairs, count, iter, tenure, d_acc, ctx->stream));
-    CK(launch_apply_move(I, ctx->tour, ctx->num_sms, 0, 0, false, ctx->stream));
+    CK(launch_apply_move(I, ctx->tour, ctx->num_sms, 0, 0, false, false, ctx->stream));
     int acc = -1;
     CK(cudaMemcpyAsync(&acc, d_acc, sizeof acc, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));

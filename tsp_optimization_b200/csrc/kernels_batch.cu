@@ -593,7 +593,7 @@ __global__ void __launch_bounds__(BPOS_THREADS) two_opt_batch_bi_kernel(const In
                 }
                 const int wpa = pos[win.i], wpb = pos[win.j];
                 __syncthreads();  // everybody has read the two positions before the swap rewrites pos[]
-                apply_swap_range(I, T, wpa, wpb, tid, BPOS_THREADS);
+                apply_swap_range<false>(I, T, wpa, wpb, tid, BPOS_THREADS);
                 moves++;
                 __syncthreads();
                 // the runner-up of every warp is most likely still a legal move: its exact delta now seeds the next pass's filter

@@ -136,8 +136,14 @@ __global__ void __launch_bounds__(BI_THREADS, (R >= 16 ? (BI_THREADS == 256 ? 1 
         mbar_fence_init();
     }
     pdl_wait();  // the previous kernel of the stream (apply / upload) is complete and its writes are visible
+    // everything the prologue needs from global memory is requested at once (ONE L2 round trip instead of a chain of four
+    // dependent ones, ~0.5 us each: at n = 10 000 a pruned pass has one small tile per block and nothing to hide them behind)
     const int done = *((volatile int *)&ctl->done);
-    if (tid == 0) s_hint = *((volatile int *)&ctl->hint);
+    const int hint0 = *((volatile int *)&ctl->hint);
+    const unsigned live_count0 = PRUNED ? __ldcg(&ctl->live_count) : 0u;
+    int2 live_first = make_int2(0, 0);
+    if (PRUNED && tid == 0) live_first = __ldcg(&A.tour.live[blockIdx.x]);  // in bounds whatever live_count is (engine.cu)
+    if (tid == 0) s_hint = hint0;
     if (done) {  // local optimum already reached: later launches of the same batch return at once
         if (blockIdx.x == 0 && tid == 0) ctl->ap_valid = 0;
         return;
@@ -145,7 +151,13 @@ __global__ void __launch_bounds__(BI_THREADS, (R >= 16 ? (BI_THREADS == 256 ? 1 
     if (A.timing && tid == 0) {
         const unsigned long long t = globaltimer_ns();
         atomicMin(&ctl->tm_scan_first, t);
-        if (A.timing == 2) A.dbg[2 * blockIdx.x] = t;
+        if (A.timing == 2) {
+            A.dbg[2 * blockIdx.x] = t;
+            if (PRUNED) {  // phase stamps: pruned variants only, so that the exhaustive (headline) kernel's code is not touched
+                for (int k = 0; k < 8; ++k) A.dbg[8192 + 8 * blockIdx.x + k] = 0;
+                A.dbg[8192 + 8 * blockIdx.x] = t;
+            }
+        }
     }
     __syncthreads();
 
@@ -195,7 +207,7 @@ __global__ void __launch_bounds__(BI_THREADS, (R >= 16 ? (BI_THREADS == 256 ? 1 
     // a tie: ties need delta == best).  The exhaustive kernel keeps the loop-free draw: a loop inside this thread-0-only
     // region makes the compiler give up the uniform datapath for the hot loop's counter and shared-memory addresses
     // (+4 % pass time at n = 100 000, measured).
-    const long long tiles_rank = PRUNED ? (long long)__ldcg(&ctl->live_count)
+    const long long tiles_rank = PRUNED ? (long long)live_count0
                                         : ((long long)A.ntiles - A.rank + A.world - 1) / A.world;
     unsigned scanned = 0;  // thread 0: tiles this block really scanned (statistics of the pruned mode)
     unsigned next_raw = 0; // thread 0, pruned mode: ticket requested one draw ahead
@@ -215,10 +227,11 @@ __global__ void __launch_bounds__(BI_THREADS, (R >= 16 ? (BI_THREADS == 256 ? 1 
             for (;;) {
                 long long kl = first ? (long long)blockIdx.x : (counted ? (long long)gridDim.x + (long long)next_raw : tiles_rank);
                 if (kl >= tiles_rank) break;
+                const int2 ent = first ? live_first : __ldcg(&A.tour.live[kl]);
                 first = false;
                 if (counted) next_raw = atomicAdd(&ctl->tile_next, 1u);
-                if (__ldg(&A.tour.live_lb[kl]) > (float)(*((volatile int *)&s_hint))) continue;
-                decode(__ldg(&A.tour.live[kl]), P, Q);
+                if (__int_as_float(ent.y) > (float)(*((volatile int *)&s_hint))) continue;
+                decode(ent.x, P, Q);
                 valid = 1;
                 scanned += 1;
                 break;
@@ -238,6 +251,7 @@ __global__ void __launch_bounds__(BI_THREADS, (R >= 16 ? (BI_THREADS == 256 ? 1 
     __syncthreads();
     int P0 = s_tile[0][0], Q0 = s_tile[0][1], NCv = s_tile[0][3];
     bool have = s_tile[0][2] != 0;
+    if (PRUNED && A.timing == 2 && tid == 0) A.dbg[8192 + 8 * blockIdx.x + 1] = globaltimer_ns();  // first tile drawn, its copy in flight
 
     for (int it = 0; have; ++it) {
         const int buf = it & 1;
@@ -268,6 +282,7 @@ __global__ void __launch_bounds__(BI_THREADS, (R >= 16 ? (BI_THREADS == 256 ? 1 
         thr = fminf(thr, (float)(*((volatile int *)&s_hint)) + W);
 
         mbar_wait(&bars[buf], parity);
+        if (PRUNED && A.timing == 2 && tid == 0 && it == 0) A.dbg[8192 + 8 * blockIdx.x + 2] = globaltimer_ns();  // rows and columns of the first tile are here
 
         // pairs with q < p+2 exist in this tile?  (mask them; they are mirrored / adjacent pairs)
         const bool diag = (Q0 < P0 + TI + 1);
@@ -353,6 +368,10 @@ __global__ void __launch_bounds__(BI_THREADS, (R >= 16 ? (BI_THREADS == 256 ? 1 
 #undef UU
 
         __syncthreads();  // every thread is done with this stage before the next prefetch overwrites it
+        if (PRUNED && A.timing == 2 && tid == 0) {
+            if (it == 0) A.dbg[8192 + 8 * blockIdx.x + 3] = globaltimer_ns();  // first tile scanned
+            A.dbg[8192 + 8 * blockIdx.x + 5] = (unsigned long long)(it + 1);
+        }
         // publish the best exact delta to the other blocks (fire and forget; theirs arrive through pend_hint above)
         if (tid == 0 && s_hint < 0) atomicMin(&ctl->hint, s_hint);
         P0 = s_tile[buf ^ 1][0];
@@ -377,11 +396,15 @@ __global__ void __launch_bounds__(BI_THREADS, (R >= 16 ? (BI_THREADS == 256 ? 1 
             if (A.timing) {
                 const unsigned long long t = globaltimer_ns();
                 atomicMin(&ctl->tm_blk_end_min, t);
-                if (A.timing == 2) A.dbg[2 * blockIdx.x + 1] = t;
+                if (A.timing == 2) {
+                    A.dbg[2 * blockIdx.x + 1] = t;
+                    if (PRUNED) A.dbg[8192 + 8 * blockIdx.x + 4] = t;  // block key folded, about to take the ticket
+                }
             }
             __threadfence();
             unsigned tk = atomicAdd(&ctl->ticket, 1u);
             s_last = (tk == gridDim.x - 1);
+            if (PRUNED && A.timing == 2) A.dbg[8192 + 8 * blockIdx.x + 6] = globaltimer_ns();  // ticket taken
         }
     }
     __syncthreads();
@@ -508,7 +531,7 @@ __global__ void __launch_bounds__(BI_THREADS, (R >= 16 ? (BI_THREADS == 256 ? 1 
     if (A.fuse_apply == 2) {
         __syncthreads();  // s_ap[] (thread 0 knows the winner; in packed_tail mode nobody else does)
         if (!s_ap[2]) return;
-        apply_swap_range(A.inst, A.tour, s_ap[0], s_ap[1], tid, BI_THREADS);
+        apply_swap_range<false>(A.inst, A.tour, s_ap[0], s_ap[1], tid, BI_THREADS);
         if (tid == 0) ctl->ap_valid = 0;
         __threadfence();
         __syncthreads();
@@ -530,6 +553,8 @@ __global__ void bi_decode_packed_kernel(const TourDev tour) {
 
 // Grid-wide application of the published move (see apply_swap_range).
 // seed: number of block_best[] entries (the scan's grid size) to re-evaluate as seeds of the next pass's filter, 0 = none
+// NODE: also keep the node-space view of the first-improvement search current (see apply_swap_range)
+template <bool NODE>
 __global__ void __launch_bounds__(256) apply_move_kernel(const InstDev inst, const TourDev tour, int seed, int timing) {
     __shared__ int s_last;
     Ctl *ctl = tour.ctl;
@@ -537,7 +562,7 @@ __global__ void __launch_bounds__(256) apply_move_kernel(const InstDev inst, con
     pdl_wait();
     if (!ctl->ap_valid) return;
     if (timing && threadIdx.x == 0) atomicMin(&ctl->tm_apply_first, globaltimer_ns());
-    apply_swap_range(inst, tour, ctl->ap_pa, ctl->ap_pb, blockIdx.x * 256 + threadIdx.x, gridDim.x * 256);
+    apply_swap_range<NODE>(inst, tour, ctl->ap_pa, ctl->ap_pb, blockIdx.x * 256 + threadIdx.x, gridDim.x * 256);
     if (timing) {
         __syncthreads();
         if (threadIdx.x == 0) atomicMax(&ctl->tm_apply_end, globaltimer_ns());
@@ -565,14 +590,6 @@ __global__ void __launch_bounds__(256) apply_move_kernel(const InstDev inst, con
 #pragma unroll
     for (int m = 16; m > 0; m >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, m));
     if ((threadIdx.x & 31) == 0 && best < 0) atomicMin(&ctl->hint, best);
-}
-
-__global__ void __launch_bounds__(256) refresh_node_space_kernel(const TourDev tour) {
-    const Ctl *ctl = tour.ctl;
-    pdl_launch_dependents();
-    pdl_wait();
-    if (!ctl->ap_valid) return;
-    refresh_node_space(tour, ctl->ap_pa, ctl->ap_pb, blockIdx.x * 256 + threadIdx.x, gridDim.x * 256);
 }
 
 // ---- exact tile pruning ---------------------------------------------------------------------------
@@ -692,8 +709,7 @@ __global__ void __launch_bounds__(128) tile_filter_kernel(const BiArgs A) {
             base = __shfl_sync(0xffffffffu, base, __ffs(mask) - 1);
             if (live) {
                 const unsigned idx = base + __popc(mask & ((1u << lane) - 1u));
-                A.tour.live[idx] = t;
-                A.tour.live_lb[idx] = lb;
+                A.tour.live[idx] = make_int2(t, __float_as_int(lb));
             }
         }
     }
@@ -948,19 +964,14 @@ cudaError_t launch_bi_decode_packed(const TourDev &tour, cudaStream_t st) {
 }
 
 // grid sized for one swap per thread (at most n/2 swaps), capped at 4 blocks per SM
+// node_space: the first-improvement runs keep their node-space tables current inside the same launch
 cudaError_t launch_apply_move(const InstDev &inst, const TourDev &tour, int num_sms, int seed, int timing, bool pdl,
-                              cudaStream_t st) {
+                              bool node_space, cudaStream_t st) {
     int grid = (tour.n / 2 + 255) / 256;
     if (grid < 1) grid = 1;
     if (grid > 4 * num_sms) grid = 4 * num_sms;
-    return launch_maybe_pdl(apply_move_kernel, dim3(grid), dim3(256), 0, st, pdl, inst, tour, seed, timing);
-}
-
-cudaError_t launch_refresh_node_space(const TourDev &tour, int num_sms, bool pdl, cudaStream_t st) {
-    int grid = (tour.n + 255) / 256;  // one node per thread
-    if (grid < 1) grid = 1;
-    if (grid > 4 * num_sms) grid = 4 * num_sms;
-    return launch_maybe_pdl(refresh_node_space_kernel, dim3(grid), dim3(256), 0, st, pdl, tour);
+    if (node_space) return launch_maybe_pdl(apply_move_kernel<true>, dim3(grid), dim3(256), 0, st, pdl, inst, tour, seed, timing);
+    return launch_maybe_pdl(apply_move_kernel<false>, dim3(grid), dim3(256), 0, st, pdl, inst, tour, seed, timing);
 }
 
 }  // namespace tspb

@@ -23,13 +23,19 @@ __device__ __forceinline__ float fi_dist32(float ax, float ay, float bx, float b
 // FP32_OK = false: no filter, every pair is evaluated exactly (GEO, matrix mode, oversized coordinates).
 //
 // Work distribution: the sweep's pairs in row-major order, counted from the cursor, are cut into SEGMENTS of
-// FI_SEG_CHUNKS x 256 consecutive pairs (crossing row ends).  Blocks draw segments in increasing order from an atomic
-// counter; a block scans its segment chunk by chunk (256 pairs at a time, so the first hit inside a segment is found in
-// order), publishes a hit with atomicMin on the (row*n + j) index and stops; blocks whose next segment starts behind a
-// published hit stop as well.  Every segment before the winning one has been scanned to its end without a hit, so the
-// minimum is exactly the reference's "first improving pair at or after the cursor", and the work past the hit is
-// bounded by the segments in flight instead of by whole rows (at n = 100 000 a row is 25x the average gap between moves).
-constexpr int FI_SEG_CHUNKS = 16;
+// FI_SEG_CHUNKS x FI_CHUNK consecutive pairs (crossing row ends).  Blocks draw segments in increasing order from an atomic
+// counter; a block scans its segment chunk by chunk — FI_CHUNK = 256 threads x FI_U pairs, every thread's FI_U pairs are
+// loaded before the first one is evaluated so that their L2 round trips overlap — and after every chunk the block votes:
+// a hit inside the chunk (the smallest offset is the first one in order) is published with atomicMin on the (row*n + j)
+// index and ends the block; so does a hit that ANOTHER block has published in the meantime at a pair in front of this
+// chunk (thread 0 polls ctl->fi_found along with its own loads).  Blocks whose next segment starts behind a published hit
+// stop as well.  Every segment before the winning one has been scanned to its end without a hit, so the minimum is exactly
+// the reference's "first improving pair at or after the cursor"; the work past the hit is bounded by one chunk per block
+// (while moves are dense — a move every ~10^5 pairs at the start of a 100 000-node sweep — the launch is over after its
+// first chunk; without the poll every block finished its 4096-pair segment, 22 us instead of ~4).
+constexpr int FI_U = 4;
+constexpr int FI_CHUNK = FI_THREADS * FI_U;
+constexpr int FI_SEG_CHUNKS = 4;
 
 // number of pairs (i<j) in rows 0..r-1 of the row-major enumeration: sum_{q<r} (n-1-q)
 __device__ __forceinline__ long long fi_pairs_before_row(long long r, long long n) { return r * (n - 1) - r * (r - 1) / 2; }
@@ -69,7 +75,9 @@ __device__ __forceinline__ void fi_finish(const InstDev &I, const TourDev &T, un
         if (delta >= 0) ctl->error = 1;  // cannot happen: the searching thread saw delta < 0
         publish_move(T, i, j, delta);    // reference heuristics.c:476-486; applied by the next two launches
         ctl->sweep_moves += 1;
-        ctl->pairs_swept += (long long)(f - ((unsigned long long)i0 * n + j0)) + 1;
+        const long long gap = (long long)(f - ((unsigned long long)i0 * n + j0)) + 1;
+        ctl->pairs_swept += gap;
+        ctl->fi_shard = gap > ctl->fi_shard_min_gap;
         ci = i;
         cj = j + 1;
         if (cj >= n) { ci = i + 1; cj = ci + 1; }
@@ -77,7 +85,9 @@ __device__ __forceinline__ void fi_finish(const InstDev &I, const TourDev &T, un
     } else {
         sweep_end = true;
         ctl->ap_valid = 0;
-        ctl->pairs_swept += (long long)((unsigned long long)(n - 1) * n - ((unsigned long long)i0 * n + j0));
+        const long long gap = (long long)((unsigned long long)(n - 1) * n - ((unsigned long long)i0 * n + j0));
+        ctl->pairs_swept += gap;
+        ctl->fi_shard = gap > ctl->fi_shard_min_gap;
     }
     ctl->launches += 1;
     if (sweep_end) {
@@ -109,91 +119,116 @@ __global__ void __launch_bounds__(FI_THREADS) fi_search_kernel(const InstDev I, 
     __shared__ unsigned long long s_found;
     Ctl *ctl = T.ctl;
     pdl_launch_dependents();  // the apply launch may queue up behind this kernel
-    pdl_wait();               // the refresh launch of the previous move is complete
-    if (ctl->done) {
+    pdl_wait();               // the apply launch of the previous move is complete
+    // one round trip for the run state (the loads are issued together; the exit test comes after)
+    const int done = *((volatile int *)&ctl->done);
+    const int i0 = *((volatile int *)&ctl->cur_i), j0 = *((volatile int *)&ctl->cur_j);
+    // Several GPUs: while moves are dense (a hit within the first round of segments) an exchange per move costs more than the
+    // search itself; every rank then searches alone — same pair, same tour — and the ranks only share the work of the long
+    // searches of the late sweeps (ctl->fi_shard, set by fi_finish from the length of the previous search).
+    const bool shard = S.world > 1 && *((volatile int *)&ctl->fi_shard) != 0;
+    const int s_rank = shard ? S.rank : 0, s_world = shard ? S.world : 1;
+    if (done) {
         // a capped run stops right after publishing a move: make sure later apply launches are no-ops
         if (blockIdx.x == 0 && threadIdx.x == 0) ctl->ap_valid = 0;
         return;
     }
     const int n = T.n;
     const int tid = threadIdx.x;
-    const int i0 = ctl->cur_i, j0 = ctl->cur_j;
     const float thrW = -1.0f + I.W;  // candidates: exact delta <= -1
     const long long total = (long long)n * (n - 1) / 2;
     const long long A0 = fi_pairs_before_row(i0, n) + (j0 - i0 - 1);  // absolute index of the cursor pair
-    constexpr long long SEG = (long long)FI_SEG_CHUNKS * FI_THREADS;
+    constexpr long long SEG = (long long)FI_SEG_CHUNKS * FI_CHUNK;
 
-    for (;;) {
+    for (bool first = true;; first = false) {
         if (tid == 0) {
-            s_seg = (int)atomicAdd(&ctl->fi_seg, 1u);
+            // a block's first segment is its block index (no atomic on the critical path of the launch: while moves are
+            // dense the launch ends in the first round); the following ones are drawn from the counter
+            s_seg = first ? (int)blockIdx.x : (int)gridDim.x + (int)atomicAdd(&ctl->fi_seg, 1u);
             s_minhit = 0x7fffffff;
-            s_found = *((volatile unsigned long long *)&ctl->fi_found);  // one read per block: the exit below must be uniform
+            s_found = first ? FI_NONE : *((volatile unsigned long long *)&ctl->fi_found);  // one read per block: the exit below must be uniform
         }
         __syncthreads();
-        const long long Abase = A0 + ((long long)S.rank + (long long)S.world * (long long)s_seg) * SEG;
+        const long long Abase = A0 + ((long long)s_rank + (long long)s_world * (long long)s_seg) * SEG;
         if (Abase >= total) break;  // past the end of the sweep
-        {
-            int rb, jb;
-            fi_locate(Abase, n, rb, jb);
-            if (s_found < (unsigned long long)rb * (unsigned long long)n + (unsigned long long)jb) break;  // an earlier pair already won
-        }
-        // this thread's first pair of the segment, then +256 per chunk
+        int rb, jb;
+        fi_locate(Abase, n, rb, jb);
+        if (s_found < (unsigned long long)rb * (unsigned long long)n + (unsigned long long)jb) break;  // an earlier pair already won
+        // this thread's first pair of the segment (tid pairs behind the segment's first one); its further pairs follow at a
+        // stride of 256
         long long A = Abase + tid;
         int row = n, j = 0;
-        if (A < total) fi_locate(A, n, row, j);
-        int crow = -1, si = 0;
-        float4 ri = make_float4(0.f, 0.f, 0.f, 0.f);
-        float dsi = 0.f;
+        if (A < total) {
+            row = rb;
+            long long jn = (long long)jb + tid;
+            while (row < n - 1 && jn >= n) { jn -= n; row += 1; jn += row + 1; }
+            j = (int)jn;
+        }
         bool stop = false;
         for (int c = 0; c < FI_SEG_CHUNKS && !stop; ++c) {
-            bool hit = false;
-            if (A < total) {
-                if (row != crow) {
-                    crow = row;
-                    ri = T.nrec[row];
-                    dsi = T.nds[row];
-                    si = T.nsucc[row];
-                }
-                const int sj = T.nsucc[j];
-                // reference heuristics.c:471: skip a1==b1 (impossible in a tour), a==b1, b==a1
-                if (sj != row && si != j && si != sj) {
-                    bool cand = true;
-                    float4 rj;
-                    float dsj = 0.f;
-                    if (FP32_OK) {
-                        rj = T.nrec[j];
-                        dsj = T.nds[j];
-                        float q = fi_dist32<ATT>(ri.x, ri.y, rj.x, rj.y) + fi_dist32<ATT>(ri.z, ri.w, rj.z, rj.w) - dsi - dsj;
-                        cand = (q <= thrW);
-                    }
-                    if (cand) {
-                        long long delta;
-                        if (FP32_OK && EXACT32) {
-                            delta = exact_dist(I.metric, make_double2((double)ri.x, (double)ri.y),
-                                               make_double2((double)rj.x, (double)rj.y)) +
-                                    exact_dist(I.metric, make_double2((double)ri.z, (double)ri.w),
-                                               make_double2((double)rj.z, (double)rj.w)) -
-                                    (long long)dsi - (long long)dsj;
-                        } else {
-                            delta = dist_nodes(I, row, j) + dist_nodes(I, si, sj) - (long long)dsi - (long long)T.nds[j];
-                        }
-                        hit = delta < 0;
-                    }
-                }
-            }
-            if (hit) atomicMin(&s_minhit, c * FI_THREADS + tid);  // offset inside the segment == row-major order
-            if (__syncthreads_or((int)hit)) {
-                stop = true;
-            } else {
-                // next chunk: 256 pairs further
-                A += FI_THREADS;
+            // thread 0: has another block meanwhile published a hit in front of this chunk?  (requested with the chunk's loads)
+            unsigned long long f_now = FI_NONE;
+            const unsigned long long chunk_first = (unsigned long long)row * (unsigned long long)n + (unsigned long long)j;
+            if (tid == 0) f_now = *((volatile unsigned long long *)&ctl->fi_found);
+            int rows[FI_U], js[FI_U];
+            float4 ri[FI_U], rj[FI_U];
+            float2 li[FI_U], lj[FI_U];  // {ds, succ}
+#pragma unroll
+            for (int k = 0; k < FI_U; ++k) {
+                rows[k] = (A + (long long)k * FI_THREADS < total) ? row : -1;
+                js[k] = j;
+                // next pair of this thread: 256 pairs further in the row-major order
                 long long jn = (long long)j + FI_THREADS;
                 while (row < n - 1 && jn >= n) { jn -= n; row += 1; jn += row + 1; }
                 j = (int)jn;
             }
+#pragma unroll
+            for (int k = 0; k < FI_U; ++k) {
+                if (rows[k] >= 0) {
+                    // the row record is loaded for every pair (usually the same address for the whole warp and for all k: one
+                    // broadcast line): re-using pair k-1's registers would chain this pair's loads behind that pair's round trip
+                    ri[k] = T.nrec[rows[k]];
+                    li[k] = *reinterpret_cast<const float2 *>(&T.nlnk[rows[k]]);
+                    lj[k] = *reinterpret_cast<const float2 *>(&T.nlnk[js[k]]);
+                    if (FP32_OK) rj[k] = T.nrec[js[k]];
+                }
+            }
+            int myhit = 0x7fffffff;
+#pragma unroll
+            for (int k = FI_U - 1; k >= 0; --k) {
+                if (rows[k] < 0) continue;
+                const int r = rows[k], jj = js[k];
+                const int si = __float_as_int(li[k].y), sj = __float_as_int(lj[k].y);
+                const float dsi = li[k].x, dsj = lj[k].x;
+                // reference heuristics.c:471: skip a1==b1 (impossible in a tour), a==b1, b==a1
+                if (sj == r || si == jj || si == sj) continue;
+                bool cand = true;
+                if (FP32_OK) {
+                    const float q = fi_dist32<ATT>(ri[k].x, ri[k].y, rj[k].x, rj[k].y) + fi_dist32<ATT>(ri[k].z, ri[k].w, rj[k].z, rj[k].w) - dsi - dsj;
+                    cand = (q <= thrW);
+                }
+                if (cand) {
+                    long long delta;
+                    if (FP32_OK && EXACT32) {
+                        delta = exact_dist(I.metric, make_double2((double)ri[k].x, (double)ri[k].y),
+                                           make_double2((double)rj[k].x, (double)rj[k].y)) +
+                                exact_dist(I.metric, make_double2((double)ri[k].z, (double)ri[k].w),
+                                           make_double2((double)rj[k].z, (double)rj[k].w)) -
+                                (long long)dsi - (long long)dsj;
+                    } else {
+                        delta = dist_nodes(I, r, jj) + dist_nodes(I, si, sj) - (long long)dsi - (long long)dsj;
+                    }
+                    if (delta < 0) myhit = k * FI_THREADS + tid;  // k runs downwards: the smallest offset survives
+                }
+            }
+            const bool hit = myhit != 0x7fffffff;
+            if (hit) atomicMin(&s_minhit, c * FI_CHUNK + myhit);  // offset inside the segment == row-major order
+            const bool overtaken = (tid == 0) && f_now < chunk_first;
+            if (__syncthreads_or((int)(hit || overtaken))) stop = true;
+            A += FI_CHUNK;
         }
         if (stop) {
-            if (tid == 0) {
+            if (tid == 0 && s_minhit != 0x7fffffff) {
                 int hr, hj;
                 fi_locate(Abase + s_minhit, n, hr, hj);
                 atomicMin(&ctl->fi_found, (unsigned long long)hr * (unsigned long long)n + (unsigned long long)hj);
@@ -214,11 +249,11 @@ __global__ void __launch_bounds__(FI_THREADS) fi_search_kernel(const InstDev I, 
     if (!s_last) return;
     __threadfence();
     unsigned long long f = *((volatile unsigned long long *)&ctl->fi_found);
-    if (S.world > 1) {
-        if (!S.finish_here) {  // NCCL min-allreduce of ctl->fi_found follows, then fi_finish_kernel
-            if (tid == 0) ctl->ticket = 0;
-            return;
-        }
+    if (S.world > 1 && !S.finish_here) {  // NCCL min-allreduce of ctl->fi_found follows, then fi_finish_kernel
+        if (tid == 0) ctl->ticket = 0;
+        return;
+    }
+    if (shard) {
         __shared__ unsigned long long s_x[XCHG_MAX_WORLD];
         __shared__ int s_err;
         if (tid == 0) s_err = 0;

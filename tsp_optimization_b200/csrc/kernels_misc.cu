@@ -213,12 +213,6 @@ __global__ void build_state_kernel(const InstDev I, const TourDev T, const int *
             float ds = (float)dist_nodes(I, u, v);
             T.rec[p] = make_float4(c.x, c.y, ds, __int_as_float(u));
             T.pos[u] = p;
-            if (T.nrec) {
-                float2 cn = I.pt32[v];
-                T.nrec[u] = make_float4(c.x, c.y, cn.x, cn.y);
-                T.nds[u] = ds;
-                T.nsucc[u] = v;
-            }
         } else if (p == n) {
             int u = order[0];
             float2 c = I.pt32[u];
@@ -243,16 +237,18 @@ __global__ void export_state_kernel(const TourDev T, int *succ, unsigned long lo
     if ((threadIdx.x & 31) == 0 && local) atomicAdd(cost, local);
 }
 
-// Node-space tables rebuilt from the position-space records (after best-improvement moves, which only maintain rec/pos).
+// Node-space tables (first-improvement search) built from the position-space records: on every first-improvement run
+// that follows an upload or moves applied by anything else (best-improvement passes, kicks, a restore).
 __global__ void rebuild_node_space_kernel(const TourDev T) {
     const int n = T.n;
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
         const float4 rp = T.rec[p];
         const float4 rn = T.rec[p + 1];  // rec[n] mirrors rec[0]
+        const float4 rv = T.rec[p == 0 ? n - 1 : p - 1];
         const int k = node_of(rp);
         T.nrec[k] = make_float4(rp.x, rp.y, rn.x, rn.y);
-        T.nds[k] = rp.z;
-        T.nsucc[k] = node_of(rn);
+        T.nlnk[k] = make_float4(rp.z, rn.w, rv.z, rv.w);
+        T.npxy[k] = make_float2(rv.x, rv.y);
     }
 }
 

@@ -49,12 +49,6 @@ __global__ void __launch_bounds__(256) vns_kick_scatter_kernel(const InstDev I, 
             const float4 rd = scratch[L1];
             const float ds = (float)dist_nodes(I, node_of(ra), node_of(rd));
             T.rec[pa].z = ds;
-            const int a = node_of(ra);
-            if (T.nrec) {
-                T.nrec[a] = make_float4(ra.x, ra.y, rd.x, rd.y);
-                T.nds[a] = ds;
-                T.nsucc[a] = node_of(rd);
-            }
             continue;
         }
         const float4 r = src(k);
@@ -75,11 +69,6 @@ __global__ void __launch_bounds__(256) vns_kick_scatter_kernel(const InstDev I, 
         if (p == 0) {  // rec[n] mirrors rec[0] (wrap-around successor of position n-1)
             *reinterpret_cast<float2 *>(&T.rec[n].x) = make_float2(r.x, r.y);
             T.rec[n].w = r.w;
-        }
-        if (T.nrec) {
-            T.nrec[u] = make_float4(r.x, r.y, nxt.x, nxt.y);
-            T.nds[u] = ds;
-            T.nsucc[u] = node_of(nxt);
         }
     }
 }

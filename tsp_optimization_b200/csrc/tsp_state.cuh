@@ -6,8 +6,10 @@
 //                   rec[n] mirrors rec[0]'s coordinates with ds = -BIG (wrap-around successor of p=n-1);
 //                   everything after is padding with ds = -BIG (never a candidate).
 //                   pos[node] = p.
-//   node space      nrec[k] = {x_k, y_k, x_succ(k), y_succ(k)}, nds[k] = d(k, succ k), nsucc[k]
-//                   (only what the first-improvement search needs: it scans node-index order).
+//   node space      nrec[k] = {x_k, y_k, x_succ(k), y_succ(k)}, nlnk[k] = {d(k, succ k), succ k, d(pred k, k), pred k},
+//                   npxy[k] = {x_pred(k), y_pred(k)}  (first-improvement search only: it scans node-index order).
+//                   Doubly linked so that a reversal is a LOCAL update of every node on the reversed path — its successor
+//                   and predecessor halves trade places — which the apply kernel does in the same pass as the swap.
 // The reference keeps edges[k].j = succ(k) and a prev[] array (reference include/utility.h:131-145,
 // src/heuristics.c:444-448); succ[] is rebuilt from rec[] when a tour is downloaded.
 #pragma once
@@ -60,6 +62,11 @@ struct Ctl {
     unsigned long long cold_calls;  // statistics: filter hits that went through the exact (cold) path
     unsigned long long pass_min;    // BI: packed (delta,i,j) minimum of the running pass (one atomicMin per block)
     int done_reason;                // why `done` is set: DONE_OPTIMUM or DONE_CAP (a capped run may be continued)
+    // first improvement on several GPUs: 1 = the next search deals its segments over the ranks and exchanges the winner,
+    // 0 = every rank searches alone from the cursor (identical results, no exchange).  Decided after every search from the
+    // number of pairs it had to sweep — the same number on every rank — so all ranks always agree.
+    int fi_shard;
+    long long fi_shard_min_gap;     // pairs swept by the last search above which the next one is sharded
     // exact tile pruning: this rank's live tiles of the coming pass, built by tile_filter_kernel
     unsigned live_count;            // entries in TourDev::live
     unsigned long long tiles_scanned, tiles_skipped;  // statistics over all pruned passes
@@ -80,9 +87,9 @@ struct TourDev {
     int alloc;        // entries allocated in rec
     float4 *rec;
     int *pos;
-    float4 *nrec;     // may be nullptr when FI is not in use
-    float *nds;
-    int *nsucc;
+    float4 *nrec;     // node space (first improvement): {x, y, x_succ, y_succ}
+    float4 *nlnk;     //   {ds = d(k, succ), succ (int bits), pds = d(pred, k), pred (int bits)}
+    float2 *npxy;     //   {x_pred, y_pred}
     Ctl *ctl;
     MoveKey *block_best;
     MoveRec *log;
@@ -91,8 +98,7 @@ struct TourDev {
     // + the successor of the last one) and tile-column (TJ positions + successor); live tile ids + their lower bounds
     float4 *rowbox, *colbox, *colbox2;   // colbox2: groups of PRUNE_GROUP consecutive tile-columns (first level of the filter)
     float *rowmaxds, *colmaxds, *colmaxds2;
-    int *live;
-    float *live_lb;
+    int2 *live;       // {tile id, lower bound of the tile's deltas (float bits)}: one 8-byte load per draw
 };
 
 #define FI_NONE 0xffffffffffffffffull
@@ -116,6 +122,21 @@ __device__ __forceinline__ long long dist_nodes(const InstDev &I, int u, int v) 
 // threads) with no synchronisation at all: every swap t touches only positions s+t and e-t, the edge-length
 // reversal touches only the .z words of s..e-1, and the thread that owns swap 0 knows all four end nodes
 // (a, a1, b, b1) from its own loads, so it also writes the two new edge lengths.
+// NODE = true (first improvement) also keeps the node-space view current, with no extra launch and no extra
+// synchronisation: on the reversed path a1..b every node's successor and predecessor trade places, which touches only
+// that node's own node-space words; the thread that swaps positions s+t and e-t owns the two nodes it moves (the middle
+// node of an odd-length path gets an iteration of its own), and the thread of swap 0 — which holds a1 and b and reads a
+// and b1 anyway — writes the four boundary links (a -> b, a1 -> b1 and their back links).
+__device__ __forceinline__ void node_flip(const TourDev &T, int k) {
+    const float4 r = T.nrec[k];
+    const float4 l = T.nlnk[k];
+    const float2 p = T.npxy[k];
+    T.nrec[k] = make_float4(r.x, r.y, p.x, p.y);
+    T.nlnk[k] = make_float4(l.z, l.w, l.x, l.y);
+    T.npxy[k] = make_float2(r.z, r.w);
+}
+
+template <bool NODE>
 __device__ __forceinline__ void apply_swap_range(const InstDev &I, const TourDev &T, int pa, int pb, int gtid, int gthreads) {
     const int n = T.n;
     float4 *rec = T.rec;
@@ -126,11 +147,16 @@ __device__ __forceinline__ void apply_swap_range(const InstDev &I, const TourDev
     const int e = pb;
     const int half = len >> 1;         // record swaps: positions s+t <-> e-t
     const int mhalf = (len - 1) >> 1;  // inner edge lengths (positions s .. e-1) reversed among themselves: s+t <-> e-1-t
+    const int iters = NODE ? half + (len & 1) : half;
     // One iteration = record swap t AND edge-length swap t, all loads issued before the first store: one L2 round trip.
     // No two threads touch the same word: swap t owns {x,y,node} of s+t and e-t and the edge lengths of s+t and e-1-t.
-    for (int t = gtid; t < half; t += gthreads) {
+    for (int t = gtid; t < iters; t += gthreads) {
         int A = s + t;
         if (A >= n) A -= n;
+        if (NODE && t == half) {  // middle node of an odd-length path: it stays where it is, only its links flip
+            node_flip(T, node_of(rec[A]));
+            continue;
+        }
         int B = e - t;
         if (B < 0) B += n;
         int Bm = B - 1;
@@ -145,6 +171,13 @@ __device__ __forceinline__ void apply_swap_range(const InstDev &I, const TourDev
             za = rec[A].z;
             zc = rec[Bm].z;
         }
+        const int ka = __float_as_int(wa), kb = __float_as_int(wb);
+        float4 nra, nla, nrb, nlb;
+        float2 npa, npb;
+        if (NODE) {  // second (dependent) round trip, issued before the stores below
+            nra = T.nrec[ka]; nla = T.nlnk[ka]; npa = T.npxy[ka];
+            nrb = T.nrec[kb]; nlb = T.nlnk[kb]; npb = T.npxy[kb];
+        }
         *reinterpret_cast<float2 *>(&rec[A].x) = xb;
         rec[A].w = wb;
         *reinterpret_cast<float2 *>(&rec[B].x) = xa;
@@ -153,8 +186,8 @@ __device__ __forceinline__ void apply_swap_range(const InstDev &I, const TourDev
             rec[A].z = zc;
             rec[Bm].z = za;
         }
-        T.pos[__float_as_int(wb)] = A;
-        T.pos[__float_as_int(wa)] = B;
+        T.pos[kb] = A;
+        T.pos[ka] = B;
         if (A == 0) {  // rec[n] mirrors rec[0] (wrap-around successor of position n-1)
             *reinterpret_cast<float2 *>(&rec[n].x) = xb;
             rec[n].w = wb;
@@ -167,31 +200,42 @@ __device__ __forceinline__ void apply_swap_range(const InstDev &I, const TourDev
             // new edges: (a, b) at position pa and (a1, b1) at position pb; a and b1 are outside the range
             int pb1 = pb + 1;
             if (pb1 >= n) pb1 -= n;
-            const int na = node_of(rec[pa]);
-            const int nb1 = (pb1 == pa) ? na : node_of(rec[pb1]);
-            rec[pa].z = (float)dist_nodes(I, na, __float_as_int(wb));
-            rec[pb].z = (float)dist_nodes(I, __float_as_int(wa), nb1);
+            float4 ra, rb1;
+            int na, nb1;
+            if (NODE) {
+                ra = rec[pa];
+                rb1 = (pb1 == pa) ? ra : rec[pb1];
+                na = node_of(ra);
+                nb1 = node_of(rb1);
+            } else {
+                na = node_of(rec[pa]);
+                nb1 = (pb1 == pa) ? na : node_of(rec[pb1]);
+            }
+            const float dab = (float)dist_nodes(I, na, kb);
+            const float da1b1 = (float)dist_nodes(I, ka, nb1);
+            rec[pa].z = dab;
+            rec[pb].z = da1b1;
+            if (NODE) {
+                // ka = a1 (was at s), kb = b (was at e):  a -> b -> ... -> a1 -> b1
+                T.nrec[ka] = make_float4(nra.x, nra.y, rb1.x, rb1.y);                       // a1: successor b1, predecessor = old successor
+                T.nlnk[ka] = make_float4(da1b1, __int_as_float(nb1), nla.x, nla.y);
+                T.npxy[ka] = make_float2(nra.z, nra.w);
+                T.nrec[kb] = make_float4(nrb.x, nrb.y, npb.x, npb.y);                       // b: successor = old predecessor, predecessor a
+                T.nlnk[kb] = make_float4(nlb.z, nlb.w, dab, __int_as_float(na));
+                T.npxy[kb] = make_float2(ra.x, ra.y);
+                *reinterpret_cast<float2 *>(&T.nrec[na].z) = xb;                            // a: successor b
+                *reinterpret_cast<float2 *>(&T.nlnk[na].x) = make_float2(dab, __int_as_float(kb));
+                *reinterpret_cast<float2 *>(&T.nlnk[nb1].z) = make_float2(da1b1, __int_as_float(ka));  // b1: predecessor a1
+                T.npxy[nb1] = xa;
+            }
+        } else if (NODE) {
+            T.nrec[ka] = make_float4(nra.x, nra.y, npa.x, npa.y);
+            T.nlnk[ka] = make_float4(nla.z, nla.w, nla.x, nla.y);
+            T.npxy[ka] = make_float2(nra.z, nra.w);
+            T.nrec[kb] = make_float4(nrb.x, nrb.y, npb.x, npb.y);
+            T.nlnk[kb] = make_float4(nlb.z, nlb.w, nlb.x, nlb.y);
+            T.npxy[kb] = make_float2(nrb.z, nrb.w);
         }
-    }
-}
-
-// Node-space view refresh after a move (separate launch, first-improvement search only): every node at
-// positions pa..pb (cyclic) got a new successor.
-__device__ __forceinline__ void refresh_node_space(const TourDev &T, int pa, int pb, int gtid, int gthreads) {
-    const int n = T.n;
-    int len = pb - pa;
-    if (len < 0) len += n;
-    for (int t = gtid; t <= len; t += gthreads) {
-        int P = pa + t;
-        if (P >= n) P -= n;
-        int Pn = P + 1;
-        if (Pn >= n) Pn -= n;
-        const float4 rp = T.rec[P];
-        const float4 rn = T.rec[Pn];
-        const int k = node_of(rp);
-        T.nrec[k] = make_float4(rp.x, rp.y, rn.x, rn.y);
-        T.nds[k] = rp.z;
-        T.nsucc[k] = node_of(rn);
     }
 }
 

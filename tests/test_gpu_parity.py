@@ -797,6 +797,49 @@ def test_synthetic_full_runs_reach_the_reference_known_answers(engine):
         engine.set_option("single_block", -1)
 
 
+def test_fi_late_selection_equals_published_move_path(engine, oracle):
+    """first improvement on one GPU: the apply launch that reads the search's winner itself (option fi_late = 1, the default;
+    csrc/kernels_bi.cu apply_move_kernel) against the search kernel's last-block tail (fi_late = 0) and the oracle — move logs,
+    tours, costs — in one go, in single moves (every run ends with a parked position entry to flush and starts with fresh
+    hit words) and interleaved with best-improvement passes, which read the position table first improvement only writes."""
+    xy = uniform_instance(1800)
+    succ0, c0 = oracle.nn_tour(xy, 0, 0)
+    engine.set_instance(xy, 0)
+    engine.set_option("single_block", 0)
+    try:
+        fs, fobj, fst, flog = oracle.two_opt_fi(xy, 0, succ0, c0, log_cap=100000)
+        for late in (1, 0):
+            engine.set_option("fi_late", late)
+            s, obj, st, log = engine.two_opt(FI, succ0, c0, log_cap=100000)
+            assert log.tolist() == flog.tolist() and (s == fs).all() and obj == fobj and st.moves == fst.moves, late
+        engine.set_option("fi_late", 1)
+        # one move per run, 40 runs: the log must be the oracle's first 40 moves and the tour what they lead to
+        engine.tour_upload(succ0, log_cap=64)
+        for _ in range(40):
+            st = engine.fi_run(1)
+            assert st.moves == 1
+        es, eobj, est, elog = oracle.two_opt_fi(xy, 0, succ0, c0, max_moves=40, log_cap=64)
+        s, cost = engine.tour_download()
+        assert engine.tour_log(64).tolist() == elog.tolist() and (s == es).all() and cost == eobj
+        # fi_run(k) -> bi_run(m) -> fi_run(-1), each checked against the oracle started from the previous stage's tour
+        engine.tour_upload(succ0)
+        engine.fi_run(25)
+        s1, c1 = engine.tour_download()
+        e1, o1, _, _ = oracle.two_opt_fi(xy, 0, succ0, c0, max_moves=25)
+        assert (s1 == e1).all() and c1 == o1
+        engine.bi_run(9)
+        s2, c2 = engine.tour_download()
+        e2, o2, _, _ = oracle.two_opt_bi(xy, 0, e1, max_passes=9)
+        assert (s2 == e2).all() and c2 == o2
+        engine.fi_run(-1)
+        s3, c3 = engine.tour_download()
+        e3, o3, _, _ = oracle.two_opt_fi(xy, 0, e2, float(o2))
+        assert (s3 == e3).all() and c3 == o3
+    finally:
+        engine.set_option("fi_late", 1)
+        engine.set_option("single_block", -1)
+
+
 def test_capped_runs_can_be_continued_in_either_mode(engine, oracle):
     """include/tspb200.h: repeated calls on the resident tour continue where the previous one stopped.  fi_run(k) then
     fi_run(-1) is the oracle's full first-improvement run; bi_run(k) then fi_run(-1) is the oracle's first-improvement

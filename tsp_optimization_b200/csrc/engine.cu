@@ -28,11 +28,12 @@ cudaError_t launch_bi_scan_tabu(const InstDev &inst, const TourDev &tour, int *s
                                 unsigned long long *zl_count, long long zl_cap, int grid, cudaStream_t st);
 cudaError_t launch_bi_decode_packed(const TourDev &tour, cudaStream_t st);
 cudaError_t launch_apply_move(const InstDev &inst, const TourDev &tour, int num_sms, int seed, int timing, bool pdl, bool node_space,
-                              cudaStream_t st);
+                              int fi_late, cudaStream_t st);
 cudaError_t launch_tile_prune(const BiArgs &a, int TI, int grid_bi, bool pdl, cudaStream_t st);
 cudaError_t launch_rank_align(const XchgDev &x, int rank, int world, Ctl *ctl, cudaStream_t st);
 cudaError_t launch_rebuild_node_space(const TourDev &T, cudaStream_t st);
-cudaError_t launch_fi_search(const InstDev &I, const TourDev &T, int rank, int world, const XchgDev *xchg, int grid, bool pdl,
+cudaError_t launch_fi_flush(const TourDev &T, cudaStream_t st);
+cudaError_t launch_fi_search(const InstDev &I, const TourDev &T, int rank, int world, const XchgDev *xchg, int late, int grid, bool pdl,
                              cudaStream_t st);
 cudaError_t launch_fi_finish(const InstDev &I, const TourDev &T, cudaStream_t st);
 cudaError_t launch_dist_matrix(const InstDev &I, int *out, long long ld, int row_begin, int row_end, bool fast,
@@ -214,6 +215,8 @@ struct tspb200_ctx {
     void *peer_mapped[XCHG_MAX_WORLD] = {};
     std::string xchg_note;
     int opt_exchange = 0;  // 0 = peer memory when available, 1 = NCCL allreduce
+    int opt_fi_late = 1;              // first improvement on one GPU: the apply launch selects the winner itself (no search-kernel tail)
+    unsigned long long fi_parity = 0; // launches of the late-selection search so far in this run (its hit word alternates)
     long long opt_fi_shard_min_gap = 4000000;  // first improvement on several GPUs: searches longer than this many pairs are followed by a sharded one
 };
 
@@ -388,6 +391,8 @@ int tspb200_set_option(tspb200_ctx *ctx, const char *key, int64_t value) {
     } else if (k == "timing") {
         if (value < 0 || value > 2) return fail(ctx, TSPB200_E_ARG, "timing must be 0, 1 or 2");
         ctx->opt_timing = (int)value;
+    } else if (k == "fi_late") {
+        ctx->opt_fi_late = value ? 1 : 0;
     } else if (k == "fi_shard_min_gap") {
         if (value < 0) return fail(ctx, TSPB200_E_ARG, "fi_shard_min_gap must be >= 0 (0 = every search is sharded)");
         ctx->opt_fi_shard_min_gap = value;
@@ -937,6 +942,9 @@ static int prepare_run(tspb200_ctx *ctx, bool reset_fi_cursor, long long max_mov
     }
     h->max_moves = max_moves_abs;
     h->fi_shard_min_gap = ctx->opt_fi_shard_min_gap;
+    h->fi_pend_node = -1;
+    h->fi_sel[0] = h->fi_sel[1] = FI_NONE;  // both hit words of the late-selection search start clean, parity 0 first
+    ctx->fi_parity = 0;
     if (reset_fi_cursor || ctx->opt_fi_shard_min_gap == 0) h->fi_shard = ctx->opt_fi_shard_min_gap == 0 ? 1 : 0;
     CK(cudaMemcpyAsync(ctx->d_ctl, h, sizeof(Ctl), cudaMemcpyHostToDevice, ctx->stream));
     return TSPB200_OK;
@@ -1065,7 +1073,7 @@ int tspb200_bi_run(tspb200_ctx *ctx, int64_t max_passes, tspb200_stats *st) {
             if (!fuse_in_kernel) {
                 // exhaustive scan: the apply launch's last block seeds the next pass's filter from all block winners (the
                 // pruned mode's tile_boxes_kernel does the same before its filter)
-                CK(launch_apply_move(I, ctx->tour, ctx->num_sms, seed_all ? ctx->grid_bi : 0, ctx->opt_timing, pdl, false, ctx->stream));
+                CK(launch_apply_move(I, ctx->tour, ctx->num_sms, seed_all ? ctx->grid_bi : 0, ctx->opt_timing, pdl, false, 0, ctx->stream));
                 host_launches++;
             }
             if (flush) CK(cudaEventRecord(ctx->pass_events[2 * q + 1], ctx->stream));
@@ -1169,7 +1177,9 @@ int tspb200_fi_run(tspb200_ctx *ctx, int64_t max_moves, tspb200_stats *st) {
         XchgDev xd = ctx->xchg;
         while (!done) {
             for (long long q = 0; q < batch; ++q) {
-                CK(launch_fi_search(I, ctx->tour, ctx->rank, ctx->world, use_xchg ? &xd : nullptr, grid, pdl, ctx->stream));
+                // one GPU: the search only folds its hits into ctl->fi_sel[parity]; the apply launch takes the winner from there
+                const int late = (ctx->world == 1 && ctx->opt_fi_late) ? 1 + (int)(ctx->fi_parity++ & 1) : 0;
+                CK(launch_fi_search(I, ctx->tour, ctx->rank, ctx->world, use_xchg ? &xd : nullptr, late, grid, pdl, ctx->stream));
                 host_launches++;
                 if (ctx->world > 1 && !use_xchg) {
                     unsigned long long *p = &ctx->d_ctl->fi_found;
@@ -1178,7 +1188,7 @@ int tspb200_fi_run(tspb200_ctx *ctx, int64_t max_moves, tspb200_stats *st) {
                     CK(launch_fi_finish(I, ctx->tour, ctx->stream));
                     host_launches++;
                 }
-                CK(launch_apply_move(I, ctx->tour, ctx->num_sms, 0, 0, pdl, true, ctx->stream));
+                CK(launch_apply_move(I, ctx->tour, ctx->num_sms, 0, 0, pdl, true, late, ctx->stream));
                 host_launches += 1;
             }
             rc = sync_ctl(ctx);
@@ -1198,6 +1208,7 @@ int tspb200_fi_run(tspb200_ctx *ctx, int64_t max_moves, tspb200_stats *st) {
             }
         }
         if (done && cap >= 0 && ctx->h_ctl->moves >= cap) status = TSPB200_STOPPED_BY_CAP;
+        if (ctx->world == 1 && ctx->opt_fi_late) CK(launch_fi_flush(ctx->tour, ctx->stream));  // the last apply's parked pos[] entry
     }
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -1727,7 +1738,7 @@ int tspb200_tabu_kick(tspb200_ctx *ctx, const int32_t *pairs, int count, int ite
     int *d_acc = d_pairs + 2 * (size_t)count;
     CK(cudaMemcpyAsync(d_pairs, pairs, sizeof(int) * 2 * (size_t)count, cudaMemcpyHostToDevice, ctx->stream));
     CK(launch_tabu_kick_select(ctx->tour, ctx->d_skip, d_pairs, count, iter, tenure, d_acc, ctx->stream));
-    CK(launch_apply_move(I, ctx->tour, ctx->num_sms, 0, 0, false, false, ctx->stream));
+    CK(launch_apply_move(I, ctx->tour, ctx->num_sms, 0, 0, false, false, 0, ctx->stream));
     int acc = -1;
     CK(cudaMemcpyAsync(&acc, d_acc, sizeof acc, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));

@@ -554,12 +554,57 @@ __global__ void bi_decode_packed_kernel(const TourDev tour) {
 // Grid-wide application of the published move (see apply_swap_range).
 // seed: number of block_best[] entries (the scan's grid size) to re-evaluate as seeds of the next pass's filter, 0 = none
 // NODE: also keep the node-space view of the first-improvement search current (see apply_swap_range)
+// fi_late (first improvement on one GPU): 1 + parity — nobody has published a move; every thread reads the search's winner
+// ctl->fi_sel[parity] = (i << 32) | j and the two positions itself (two round trips, one more than reading a published
+// move, instead of the search kernel's whole "last block" tail), global thread 0 — which applies swap 0 and therefore
+// holds the four edge lengths of the move — logs it and advances the sweep.
 template <bool NODE>
-__global__ void __launch_bounds__(256) apply_move_kernel(const InstDev inst, const TourDev tour, int seed, int timing) {
+__global__ void __launch_bounds__(256) apply_move_kernel(const InstDev inst, const TourDev tour, int seed, int timing, int fi_late) {
     __shared__ int s_last;
     Ctl *ctl = tour.ctl;
     pdl_launch_dependents();
     pdl_wait();
+    if (NODE && fi_late) {
+        const int gtid = blockIdx.x * 256 + threadIdx.x;
+        const unsigned long long f = *((volatile unsigned long long *)&ctl->fi_sel[fi_late - 1]);
+        int done = 0, i0 = 0, j0 = 0;
+        if (gtid == 0) {  // only thread 0 may look at these: it is also the one that rewrites them below
+            done = *((volatile int *)&ctl->done);
+            i0 = *((volatile int *)&ctl->cur_i);
+            j0 = *((volatile int *)&ctl->cur_j);
+        }
+        long long delta = 0;
+        int i = 0, j = 0;
+        int2 park = make_int2(-1, 0);
+        if (f != FI_NONE) {  // (after `done` the searches return at once and the word stays FI_NONE)
+            i = (int)(f >> 32);
+            j = (int)(f & 0xffffffffull);
+            // pos[i] (a, outside the reversed path) is not touched by this launch; pos[j] (b) would be, by swap 0: parked instead
+            apply_swap_range<true>(inst, tour, tour.pos[i], tour.pos[j], gtid, gridDim.x * 256, &delta, &park);
+        }
+        if (gtid == 0 && !done) {
+            ctl->fi_pend_node = park.x;
+            ctl->fi_pend_pos = park.y;
+            if (f != FI_NONE) {
+                if (delta >= 0) ctl->error = 1;  // cannot happen: the searching thread saw delta < 0
+                ctl->moves += 1;                 // reference heuristics.c:476-486
+                ctl->obj_delta += delta;
+                const long long lc = ctl->log_count;
+                if (tour.log && lc < tour.log_cap) {
+                    MoveRec mr;
+                    mr.i = i; mr.j = j; mr.delta = delta;
+                    tour.log[lc] = mr;
+                }
+                ctl->log_count = lc + 1;
+            }
+            ctl->ap_valid = 0;
+            fi_advance(tour, f, i0, j0);
+        }
+        // The next search's word; this launch's own word is reset by the next apply launch — also by the no-op launches that
+        // follow a finished run inside a batch, or the launch after them would find this move again.
+        if (gtid == 0) ctl->fi_sel[(fi_late - 1) ^ 1] = FI_NONE;
+        return;
+    }
     if (!ctl->ap_valid) return;
     if (timing && threadIdx.x == 0) atomicMin(&ctl->tm_apply_first, globaltimer_ns());
     apply_swap_range<NODE>(inst, tour, ctl->ap_pa, ctl->ap_pb, blockIdx.x * 256 + threadIdx.x, gridDim.x * 256);
@@ -966,12 +1011,12 @@ cudaError_t launch_bi_decode_packed(const TourDev &tour, cudaStream_t st) {
 // grid sized for one swap per thread (at most n/2 swaps), capped at 4 blocks per SM
 // node_space: the first-improvement runs keep their node-space tables current inside the same launch
 cudaError_t launch_apply_move(const InstDev &inst, const TourDev &tour, int num_sms, int seed, int timing, bool pdl,
-                              bool node_space, cudaStream_t st) {
+                              bool node_space, int fi_late, cudaStream_t st) {
     int grid = (tour.n / 2 + 255) / 256;
     if (grid < 1) grid = 1;
     if (grid > 4 * num_sms) grid = 4 * num_sms;
-    if (node_space) return launch_maybe_pdl(apply_move_kernel<true>, dim3(grid), dim3(256), 0, st, pdl, inst, tour, seed, timing);
-    return launch_maybe_pdl(apply_move_kernel<false>, dim3(grid), dim3(256), 0, st, pdl, inst, tour, seed, timing);
+    if (node_space) return launch_maybe_pdl(apply_move_kernel<true>, dim3(grid), dim3(256), 0, st, pdl, inst, tour, seed, timing, fi_late);
+    return launch_maybe_pdl(apply_move_kernel<false>, dim3(grid), dim3(256), 0, st, pdl, inst, tour, seed, timing, 0);
 }
 
 }  // namespace tspb

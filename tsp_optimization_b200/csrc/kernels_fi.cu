@@ -37,9 +37,6 @@ constexpr int FI_U = 4;
 constexpr int FI_CHUNK = FI_THREADS * FI_U;
 constexpr int FI_SEG_CHUNKS = 4;
 
-// number of pairs (i<j) in rows 0..r-1 of the row-major enumeration: sum_{q<r} (n-1-q)
-__device__ __forceinline__ long long fi_pairs_before_row(long long r, long long n) { return r * (n - 1) - r * (r - 1) / 2; }
-
 // (row, column) of the pair with absolute index A in the row-major enumeration of all i<j; A < n(n-1)/2
 __device__ __forceinline__ void fi_locate(long long A, int n, int &row, int &j) {
     const double b = 2.0 * n - 1.0;
@@ -59,55 +56,21 @@ __device__ __forceinline__ void fi_locate(long long A, int n, int &row, int &j) 
 struct FiShard {
     int rank, world;
     int finish_here;  // 1: the search kernel's last block publishes the move; 0: fi_finish_kernel does (NCCL exchange)
+    int late;         // 1 + parity: single GPU, hits go to ctl->fi_sel[parity] and the apply launch takes it from there (no tail)
     XchgDev xchg;
 };
 
-// What happens once the first improving pair f (FI_NONE: none left in this sweep) is known: publish the move for the apply
-// launch, advance the cursor, close the sweep (reference src/heuristics.c:476-496).  One thread.
+// The search kernel's last block (several GPUs) / fi_finish_kernel: publish the move for the apply launch, then the bookkeeping.
 __device__ __forceinline__ void fi_finish(const InstDev &I, const TourDev &T, unsigned long long f, int i0, int j0) {
     Ctl *ctl = T.ctl;
-    const int n = T.n;
-    int ci = 0, cj = 0;
-    bool sweep_end = false;
     if (f != FI_NONE) {
-        const int i = (int)(f / (unsigned long long)n), j = (int)(f % (unsigned long long)n);
+        const int i = (int)(f >> 32), j = (int)(f & 0xffffffffull);
         const long long delta = move_delta_nodes(I, T, i, j);
         if (delta >= 0) ctl->error = 1;  // cannot happen: the searching thread saw delta < 0
-        publish_move(T, i, j, delta);    // reference heuristics.c:476-486; applied by the next two launches
-        ctl->sweep_moves += 1;
-        const long long gap = (long long)(f - ((unsigned long long)i0 * n + j0)) + 1;
-        ctl->pairs_swept += gap;
-        ctl->fi_shard = gap > ctl->fi_shard_min_gap;
-        ci = i;
-        cj = j + 1;
-        if (cj >= n) { ci = i + 1; cj = ci + 1; }
-        if (ci >= n - 1) sweep_end = true;
-    } else {
-        sweep_end = true;
-        ctl->ap_valid = 0;
-        const long long gap = (long long)((unsigned long long)(n - 1) * n - ((unsigned long long)i0 * n + j0));
-        ctl->pairs_swept += gap;
-        ctl->fi_shard = gap > ctl->fi_shard_min_gap;
+        publish_move(T, i, j, delta);    // reference heuristics.c:476-486; applied by the next launch
     }
-    ctl->launches += 1;
-    if (sweep_end) {
-        ctl->passes += 1;
-        if (ctl->sweep_moves == 0) {  // reference heuristics.c:492: the sweep brought no gain
-            ctl->done = 1;
-            ctl->done_reason = DONE_OPTIMUM;
-        }
-        ctl->sweep_moves = 0;
-        ci = 0;
-        cj = 1;
-    }
-    if (ctl->max_moves >= 0 && ctl->moves >= ctl->max_moves && !ctl->done) {  // a capped run may be continued later
-        ctl->done = 1;
-        ctl->done_reason = DONE_CAP;
-    }
-    ctl->cur_i = ci;
-    ctl->cur_j = cj;
+    fi_advance(T, f, i0, j0);
     ctl->fi_found = FI_NONE;
-    ctl->fi_seg = 0;
     ctl->ticket = 0;
 }
 
@@ -127,6 +90,14 @@ __global__ void __launch_bounds__(FI_THREADS) fi_search_kernel(const InstDev I, 
     // search itself; every rank then searches alone — same pair, same tour — and the ranks only share the work of the long
     // searches of the late sweeps (ctl->fi_shard, set by fi_finish from the length of the previous search).
     const bool shard = S.world > 1 && *((volatile int *)&ctl->fi_shard) != 0;
+    unsigned long long *found = S.late ? &ctl->fi_sel[S.late - 1] : &ctl->fi_found;
+    if (S.late && blockIdx.x == 0 && threadIdx.x == 0) {  // the position entry the previous apply launch parked (nobody reads pos[] here)
+        const int pn = *((volatile int *)&ctl->fi_pend_node);
+        if (pn >= 0) {
+            T.pos[pn] = ctl->fi_pend_pos;
+            ctl->fi_pend_node = -1;
+        }
+    }
     const int s_rank = shard ? S.rank : 0, s_world = shard ? S.world : 1;
     if (done) {
         // a capped run stops right after publishing a move: make sure later apply launches are no-ops
@@ -146,14 +117,14 @@ __global__ void __launch_bounds__(FI_THREADS) fi_search_kernel(const InstDev I, 
             // dense the launch ends in the first round); the following ones are drawn from the counter
             s_seg = first ? (int)blockIdx.x : (int)gridDim.x + (int)atomicAdd(&ctl->fi_seg, 1u);
             s_minhit = 0x7fffffff;
-            s_found = first ? FI_NONE : *((volatile unsigned long long *)&ctl->fi_found);  // one read per block: the exit below must be uniform
+            s_found = first ? FI_NONE : *((volatile unsigned long long *)found);  // one read per block: the exit below must be uniform
         }
         __syncthreads();
         const long long Abase = A0 + ((long long)s_rank + (long long)s_world * (long long)s_seg) * SEG;
         if (Abase >= total) break;  // past the end of the sweep
         int rb, jb;
         fi_locate(Abase, n, rb, jb);
-        if (s_found < (unsigned long long)rb * (unsigned long long)n + (unsigned long long)jb) break;  // an earlier pair already won
+        if (s_found < fi_key(rb, jb)) break;  // an earlier pair already won
         // this thread's first pair of the segment (tid pairs behind the segment's first one); its further pairs follow at a
         // stride of 256
         long long A = Abase + tid;
@@ -168,8 +139,8 @@ __global__ void __launch_bounds__(FI_THREADS) fi_search_kernel(const InstDev I, 
         for (int c = 0; c < FI_SEG_CHUNKS && !stop; ++c) {
             // thread 0: has another block meanwhile published a hit in front of this chunk?  (requested with the chunk's loads)
             unsigned long long f_now = FI_NONE;
-            const unsigned long long chunk_first = (unsigned long long)row * (unsigned long long)n + (unsigned long long)j;
-            if (tid == 0) f_now = *((volatile unsigned long long *)&ctl->fi_found);
+            const unsigned long long chunk_first = fi_key(row, j);
+            if (tid == 0) f_now = *((volatile unsigned long long *)found);
             int rows[FI_U], js[FI_U];
             float4 ri[FI_U], rj[FI_U];
             float2 li[FI_U], lj[FI_U];  // {ds, succ}
@@ -231,13 +202,14 @@ __global__ void __launch_bounds__(FI_THREADS) fi_search_kernel(const InstDev I, 
             if (tid == 0 && s_minhit != 0x7fffffff) {
                 int hr, hj;
                 fi_locate(Abase + s_minhit, n, hr, hj);
-                atomicMin(&ctl->fi_found, (unsigned long long)hr * (unsigned long long)n + (unsigned long long)hj);
+                atomicMin(found, fi_key(hr, hj));
             }
             break;
         }
         __syncthreads();  // s_seg / s_minhit are rewritten by the next round
     }
 
+    if (S.late) return;  // the apply launch reads ctl->fi_sel[parity] itself
     // ---- last block: exchange (several GPUs), then publish the winning move / close the sweep ---------------
     __syncthreads();
     if (tid == 0) {
@@ -280,12 +252,26 @@ __global__ void fi_finish_kernel(const InstDev I, const TourDev T) {
     fi_finish(I, T, ctl->fi_found, ctl->cur_i, ctl->cur_j);
 }
 
+// end of a late-selection run: store the position entry the last apply launch parked
+__global__ void fi_flush_kernel(const TourDev T) {
+    Ctl *ctl = T.ctl;
+    if (ctl->fi_pend_node >= 0) {
+        T.pos[ctl->fi_pend_node] = ctl->fi_pend_pos;
+        ctl->fi_pend_node = -1;
+    }
+}
+
+cudaError_t launch_fi_flush(const TourDev &T, cudaStream_t st) {
+    fi_flush_kernel<<<1, 1, 0, st>>>(T);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_fi_finish(const InstDev &I, const TourDev &T, cudaStream_t st) {
     fi_finish_kernel<<<1, 1, 0, st>>>(I, T);
     return cudaGetLastError();
 }
 
-cudaError_t launch_fi_search(const InstDev &I, const TourDev &T, int rank, int world, const XchgDev *xchg, int grid, bool pdl,
+cudaError_t launch_fi_search(const InstDev &I, const TourDev &T, int rank, int world, const XchgDev *xchg, int late, int grid, bool pdl,
                              cudaStream_t st) {
     const bool att = (I.metric == M_ATT);
     const bool ex = I.exact32 != 0;
@@ -294,6 +280,7 @@ cudaError_t launch_fi_search(const InstDev &I, const TourDev &T, int rank, int w
     S.rank = rank;
     S.world = world;
     S.finish_here = (world == 1 || xchg != nullptr) ? 1 : 0;
+    S.late = late;
     if (xchg) S.xchg = *xchg;
     if (!I.fp32_ok) return launch_maybe_pdl(fi_search_kernel<false, false, false>, g, b, 0, st, pdl, I, T, S);
     if (att && ex) return launch_maybe_pdl(fi_search_kernel<true, true, true>, g, b, 0, st, pdl, I, T, S);

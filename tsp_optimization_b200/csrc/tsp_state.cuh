@@ -66,6 +66,14 @@ struct Ctl {
     // 0 = every rank searches alone from the cursor (identical results, no exchange).  Decided after every search from the
     // number of pairs it had to sweep — the same number on every rank — so all ranks always agree.
     int fi_shard;
+    // single GPU ("late selection"): the search kernels only fold their hits into fi_sel[parity of the launch]; the apply
+    // launch that follows reads the winner itself, applies it and does the bookkeeping, so the search kernel has no
+    // "last block" tail.  The other parity's word is reset by that apply launch for the next search.
+    unsigned long long fi_sel[2];
+    // ... every thread of that apply launch reads pos[b] to find the range, so the ONE position entry the launch itself would
+    // overwrite under their eyes — pos[b], written by swap 0 — is parked here and stored by the next search launch (which never
+    // reads pos[]) or by fi_flush_kernel at the end of the run.
+    int fi_pend_node, fi_pend_pos;   // fi_pend_node < 0: nothing parked
     long long fi_shard_min_gap;     // pairs swept by the last search above which the next one is sharded
     // exact tile pruning: this rank's live tiles of the coming pass, built by tile_filter_kernel
     unsigned live_count;            // entries in TourDev::live
@@ -136,8 +144,12 @@ __device__ __forceinline__ void node_flip(const TourDev &T, int k) {
     T.npxy[k] = make_float2(r.z, r.w);
 }
 
+// delta_out (may be null): the thread of swap 0 — global thread 0 — stores the exact delta of the move it applied,
+// d(a,b) + d(a1,b1) - d(a,a1) - d(b,b1), from the edge lengths it reads and writes anyway.
+// park_pos_b (may be null): swap 0 does NOT store pos[b]; the thread gets {b, new position of b} back instead (see Ctl::fi_pend_*).
 template <bool NODE>
-__device__ __forceinline__ void apply_swap_range(const InstDev &I, const TourDev &T, int pa, int pb, int gtid, int gthreads) {
+__device__ __forceinline__ void apply_swap_range(const InstDev &I, const TourDev &T, int pa, int pb, int gtid, int gthreads,
+                                                 long long *delta_out = nullptr, int2 *park_pos_b = nullptr) {
     const int n = T.n;
     float4 *rec = T.rec;
     int s = pa + 1;
@@ -186,7 +198,8 @@ __device__ __forceinline__ void apply_swap_range(const InstDev &I, const TourDev
             rec[A].z = zc;
             rec[Bm].z = za;
         }
-        T.pos[kb] = A;
+        if (park_pos_b && t == 0) *park_pos_b = make_int2(kb, A);
+        else T.pos[kb] = A;
         T.pos[ka] = B;
         if (A == 0) {  // rec[n] mirrors rec[0] (wrap-around successor of position n-1)
             *reinterpret_cast<float2 *>(&rec[n].x) = xb;
@@ -213,6 +226,7 @@ __device__ __forceinline__ void apply_swap_range(const InstDev &I, const TourDev
             }
             const float dab = (float)dist_nodes(I, na, kb);
             const float da1b1 = (float)dist_nodes(I, ka, nb1);
+            if (delta_out) *delta_out = (long long)dab + (long long)da1b1 - (long long)rec[pa].z - (long long)rec[pb].z;  // nobody else writes these two
             rec[pa].z = dab;
             rec[pb].z = da1b1;
             if (NODE) {
@@ -300,6 +314,56 @@ __device__ __forceinline__ void seed_hint_from_candidates(const InstDev &I, cons
     if (t >= ctl->ncand) return;
     const long long delta = legal_move_delta_cg(I, T, ctl->cand[t]);
     if (delta < 0) atomicMin(&ctl->hint, (int)delta);
+}
+
+// ---- first improvement: what follows a search (shared by the search kernel's last block and the apply launch) --------
+// The first improving pair travels as (i << 32) | j: the same order as the reference's row-major enumeration.
+__device__ __forceinline__ unsigned long long fi_key(int i, int j) { return ((unsigned long long)(unsigned)i << 32) | (unsigned)j; }
+// number of pairs (i<j) in rows 0..r-1 of the row-major enumeration: sum_{q<r} (n-1-q)
+__device__ __forceinline__ long long fi_pairs_before_row(long long r, long long n) { return r * (n - 1) - r * (r - 1) / 2; }
+
+// Counters, cursor and sweep end once the first improving pair f at or after the cursor (i0, j0) is known (FI_NONE: none left
+// in this sweep), reference src/heuristics.c:476-496.  One thread.  The move itself is published / applied by the caller.
+__device__ __forceinline__ void fi_advance(const TourDev &T, unsigned long long f, int i0, int j0) {
+    Ctl *ctl = T.ctl;
+    const int n = T.n;
+    int ci = 0, cj = 0;
+    bool sweep_end = false;
+    const long long A0 = fi_pairs_before_row(i0, n) + (j0 - i0 - 1);
+    long long gap;
+    if (f != FI_NONE) {
+        const int i = (int)(f >> 32), j = (int)(f & 0xffffffffull);
+        ctl->sweep_moves += 1;
+        gap = fi_pairs_before_row(i, n) + (j - i - 1) - A0 + 1;
+        ci = i;
+        cj = j + 1;
+        if (cj >= n) { ci = i + 1; cj = ci + 1; }
+        if (ci >= n - 1) sweep_end = true;
+    } else {
+        sweep_end = true;
+        ctl->ap_valid = 0;
+        gap = (long long)n * (n - 1) / 2 - A0;
+    }
+    ctl->pairs_swept += gap;
+    ctl->fi_shard = gap > ctl->fi_shard_min_gap;
+    ctl->launches += 1;
+    if (sweep_end) {
+        ctl->passes += 1;
+        if (ctl->sweep_moves == 0) {  // reference heuristics.c:492: the sweep brought no gain
+            ctl->done = 1;
+            ctl->done_reason = DONE_OPTIMUM;
+        }
+        ctl->sweep_moves = 0;
+        ci = 0;
+        cj = 1;
+    }
+    if (ctl->max_moves >= 0 && ctl->moves >= ctl->max_moves && !ctl->done) {  // a capped run may be continued later
+        ctl->done = 1;
+        ctl->done_reason = DONE_CAP;
+    }
+    ctl->cur_i = ci;
+    ctl->cur_j = cj;
+    ctl->fi_seg = 0;
 }
 
 // ---- kernel argument blocks shared by the kernel translation units and engine.cu ----------------------

@@ -381,7 +381,7 @@ def main():
     gpu_ms, launches, moves, done_passes = maxr(st.gpu_ms), st.launches, st.moves, st.passes
     value = done_passes * pairs / (gpu_ms * 1e-3)
     # the tile shape / grid `value` was measured with (later legs — pruned runs, other sizes — re-plan the tiles)
-    shape_value = {k: eng.info(k) for k in ("block_threads", "rows_per_thread", "tile_cols", "grid_bi", "ntiles")}
+    shape_value = {k: eng.info(k) for k in ("block_threads", "rows_per_thread", "tile_cols", "grid_bi", "ntiles", "row_shuffle", "tile_rows")}
     tour_after, _ = eng.tour_download()
     chk_value = fixture.check_after_passes(tour_after, args.warmup + done_passes)
     clocks = sampler.stop(t_region0, t_region1)
@@ -554,15 +554,17 @@ def main():
     ncu = {}
     if os.path.exists(NCU_KEYED):
         with open(NCU_KEYED) as f:
-            ncu = json.load(f).get(f"{T}x{R}x{TJ}", {})
+            ncu = json.load(f).get(f"{T}x{R}x{TJ}" + ("s" if shape_value["row_shuffle"] else ""), {})
     ipe = ncu.get("thread_instr_per_eval")
     roofline = {"bound": "sfu_sqrt", "achieved": per_gpu / 1e12, "peak": sqrt_peak / 1e12, "unit": "T sqrt/s (= T evals/s)",
                 "frac": per_gpu / sqrt_peak, "traffic": ncu.get("dram_bytes_per_launch"), "kernel": "bi_scan_kernel",
-                "per_unit": f"1 MUFU.SQRT per evaluated move (algorithmic minimum: every distance serves two moves); the kernel "
-                            f"issues (R+1)/R = {(R + 1) / R:.4f} with R = {R} rows per thread",
+                "per_unit": "1 MUFU.SQRT per evaluated move (algorithmic minimum: every distance serves two moves); the kernel issues " +
+                            (f"32R/(32R-1) = {32 * R / (32 * R - 1):.4f} (R = {R} rows per thread; the distance below a lane's rows comes "
+                             f"from the next lane by shuffle, a warp owns 32R-1 rows)" if shape_value["row_shuffle"]
+                             else f"(R+1)/R = {(R + 1) / R:.4f} with R = {R} rows per thread"),
                 "peak_source": f"{num_sms} SMs x 16 MUFU/clk x {sm_mhz:.0f} MHz ({clock_src}); MEASURED_PEAKS.json ({peaks_src}) "
                                f"holds HBM and bf16 figures only, neither bounds this kernel",
-                "ncu": ncu if ncu else f"no ncu capture committed for tile shape {T}x{R}x{TJ} (profiles/ncu_by_tile_shape.json)",
+                "ncu": ncu if ncu else f"no ncu capture committed for tile shape {T}x{R}x{TJ}{'s' if shape_value['row_shuffle'] else ''} (profiles/ncu_by_tile_shape.json)",
                 "fp32_issue_view": {"survey_per_unit": FP32_INSTR_PER_EVAL,
                                     "frac_vs_survey_18_instr_model": per_gpu * FP32_INSTR_PER_EVAL / fp32_peak,
                                     "executed_thread_instr_per_eval": ipe,
@@ -598,7 +600,8 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": gpu_ms / max(1, done_passes), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": cfg,
-            "engine": {"block_threads": T, "rows_per_thread": R, "tile_cols": TJ, "grid": shape_value["grid_bi"], "tiles": shape_value["ntiles"],
+            "engine": {"block_threads": T, "rows_per_thread": R, "tile_cols": TJ, "tile_rows": shape_value["tile_rows"],
+                       "row_shuffle": shape_value["row_shuffle"], "grid": shape_value["grid_bi"], "tiles": shape_value["ntiles"],
                        "sharding": ("tiles round-robin over ranks; per pass each rank's 8-byte argmin key is " +
                                     ("stored into every peer's slots over NVLink by the scan kernel (CUDA IPC peer memory)"
                                      if eng.info("exchange_p2p") else "min-allreduced by NCCL")) if world > 1 else "single GPU",

@@ -20,13 +20,15 @@ def _sass(mangled: str) -> str:
     return r.stdout
 
 
-@pytest.mark.parametrize("shape", ["ILi64ELi8ELb0ELb1ELb0", "ILi64ELi8ELb0ELb0ELb0", "ILi64ELi8ELb1ELb1ELb0", "ILi128ELi8ELb0ELb1ELb0",
-                                   "ILi128ELi16ELb0ELb1ELb0"])
+@pytest.mark.parametrize("shape", ["ILi64ELi8ELb0ELb1ELb0ELb0", "ILi64ELi8ELb0ELb0ELb0ELb0", "ILi64ELi8ELb1ELb1ELb0ELb0", "ILi128ELi8ELb0ELb1ELb0ELb0",
+                                   "ILi128ELi16ELb0ELb1ELb0ELb0", "ILi64ELi8ELb0ELb1ELb0ELb1", "ILi64ELi8ELb0ELb0ELb0ELb1", "ILi64ELi8ELb1ELb1ELb0ELb1"])
 def test_exhaustive_scan_hot_loop_stays_in_the_uniform_datapath(shape):
-    """bi_scan_kernel<T, R, ATT, EXACT32, PRUNED=false>: the column records are read with LDS.128 [UR + imm] (uniform
+    """bi_scan_kernel<T, R, ATT, EXACT32, PRUNED=false, SHUF>: the column records are read with LDS.128 [UR + imm] (uniform
     address register), the packed FP32x2 pipe and MUFU.SQRT are in use, and the TMA bulk copy is there.  With vector
     addressing (LDS.128 [R + imm] only) the same kernel measured 5 % slower on a B200 (1470 vs 1389 us per pass at
     n = 100 000): see the s_tile comment in csrc/kernels_bi.cu."""
     sass = _sass(f"_ZN4tspb14bi_scan_kernel{shape}EEEvNS_6BiArgsE")
     assert len(re.findall(r"LDS\.128 R\d+, \[UR", sass)) >= 4
     assert "MUFU.SQRT" in sass and "FFMA2" in sass and "FADD2" in sass and "UBLKCP" in sass
+    if shape.endswith("ELb1"):  # the shuffle variant: R square roots per column (no scalar (R+1)-th one), one SHFL.DOWN instead
+        assert "SHFL.DOWN" in sass

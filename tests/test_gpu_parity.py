@@ -287,6 +287,30 @@ def test_bi_tile_shapes(engine, oracle, T, R, TJ, fuse):
         engine.set_option("fuse_apply", -1)
 
 
+@pytest.mark.parametrize("T,R,TJ", [(64, 8, 256), (64, 8, 88), (64, 4, 64), (64, 2, 32)])
+@pytest.mark.parametrize("shuffle", [0, 1])
+def test_bi_row_shuffle_variant_equals_plain_variant(engine, oracle, T, R, TJ, shuffle):
+    """bi_scan_kernel<..., SHUF>: a warp owns 32 R - 1 rows and takes the distance below a lane's rows from the next lane
+    (csrc/kernels_bi.cu); the plain variant computes it.  Same move log, exhaustive and pruned, from an NN start and from a
+    random start (wrap-around reversals), tile rows 32 R - 1 per warp vs 32 R."""
+    xy = uniform_instance(2300)
+    engine.set_option("block_threads", T)
+    engine.set_option("rows_per_thread", R)
+    engine.set_option("tile_cols", TJ)
+    engine.set_option("row_shuffle", shuffle)
+    try:
+        succ, _ = oracle.nn_tour(xy, 0, 0)
+        _check_bi(engine, oracle, xy, 0, succ, max_passes=30)
+        assert engine.info("row_shuffle") == shuffle and engine.info("tile_rows") == ((T // 32) * (32 * R - 1) if shuffle else T * R)
+        rnd = order_to_succ(np.random.default_rng(17).permutation(len(xy)))
+        _check_bi(engine, oracle, xy, 0, rnd, max_passes=12)
+    finally:
+        engine.set_option("block_threads", 0)
+        engine.set_option("rows_per_thread", 0)
+        engine.set_option("tile_cols", 0)
+        engine.set_option("row_shuffle", -1)
+
+
 def test_bi_random_start_and_wraparound_reversals(engine, oracle):
     """random permutations: most moves have pos[a] > pos[b] for some step, i.e. the reversed forward path wraps."""
     rng = np.random.default_rng(5)

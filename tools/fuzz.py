@@ -60,6 +60,8 @@ while time.time() - t0 < budget:
     eng.set_option("single_block", route)
     eng.set_option("prune", int(rng.choice([-1, 0, 1, 1])))          # exact tile pruning must not change a single move
     eng.set_option("batch_kernel", int(rng.integers(0, 2)))          # one-block BI: position-space / node-space kernel
+    eng.set_option("row_shuffle", int(rng.choice([-1, 0, 1])))       # scan kernel: row below a lane's rows computed / shuffled from the next lane
+    eng.set_option("fi_late", int(rng.integers(0, 2)))               # first improvement: winner selected by the apply launch / by the search kernel's tail
     eng.set_option("grid", int(rng.choice([0, 0, 1, 3, 17, 64])))  # few blocks -> many rounds of dynamically drawn tiles
     eng.set_instance(xy, wt)
     use_matrix = wt in (1, 2, 4) or rng.random() < 0.15

@@ -22,6 +22,8 @@ namespace tspb {
 // ---- launchers implemented in the kernel translation units ---------------------------------------------
 cudaError_t launch_bi_scan(const BiArgs &a, int threads, int rows_per_thread, int grid, bool pdl, cudaStream_t st);
 bool bi_shape_supported(int threads, int rows_per_thread);
+int bi_tile_rows(int threads, int rows_per_thread, int row_shuffle);
+bool bi_shuffle_supported(int threads, int rows_per_thread);
 cudaError_t launch_bi_scan_exact(const InstDev &inst, const TourDev &tour, int rank, int world, int fuse_apply, int grid,
                                  cudaStream_t st);
 cudaError_t launch_bi_scan_tabu(const InstDev &inst, const TourDev &tour, int *skip, int iter, int tenure, long long *zl,
@@ -215,6 +217,8 @@ struct tspb200_ctx {
     void *peer_mapped[XCHG_MAX_WORLD] = {};
     std::string xchg_note;
     int opt_exchange = 0;  // 0 = peer memory when available, 1 = NCCL allreduce
+    int opt_row_shuffle = -1;         // best-improvement scan: distance below a lane's rows by shuffle (-1 auto = on where built, 0 off, 1 on)
+    int row_shuffle = 0;              // what the current tile plan was made for
     int opt_fi_late = 1;              // first improvement on one GPU: the apply launch selects the winner itself (no search-kernel tail)
     unsigned long long fi_parity = 0; // launches of the late-selection search so far in this run (its hit word alternates)
     long long opt_fi_shard_min_gap = 4000000;  // first improvement on several GPUs: searches longer than this many pairs are followed by a sharded one
@@ -391,6 +395,10 @@ int tspb200_set_option(tspb200_ctx *ctx, const char *key, int64_t value) {
     } else if (k == "timing") {
         if (value < 0 || value > 2) return fail(ctx, TSPB200_E_ARG, "timing must be 0, 1 or 2");
         ctx->opt_timing = (int)value;
+    } else if (k == "row_shuffle") {
+        if (value < -1 || value > 1) return fail(ctx, TSPB200_E_ARG, "row_shuffle must be -1 (auto), 0 or 1");
+        ctx->opt_row_shuffle = (int)value;
+        ctx->has_tour = false;  // the tile plan depends on it
     } else if (k == "fi_late") {
         ctx->opt_fi_late = value ? 1 : 0;
     } else if (k == "fi_shard_min_gap") {
@@ -433,6 +441,8 @@ int64_t tspb200_get_info(const tspb200_ctx *ctx, const char *key) {
     if (k == "rows_per_thread") return ctx->R;
     if (k == "block_threads") return ctx->T;
     if (k == "tile_cols") return ctx->TJ;
+    if (k == "row_shuffle") return ctx->row_shuffle;
+    if (k == "tile_rows") return bi_tile_rows(ctx->T, ctx->R, ctx->row_shuffle);
     if (k == "grid_bi") return ctx->grid_bi;
     if (k == "ntiles") return ctx->ntiles;
     if (k == "exact32") return ctx->inst.exact32;
@@ -672,9 +682,11 @@ static long long tile_plan(int n, int TI, int TJ, std::vector<int> *row_start, s
 // instructions per move than their sqrt count alone says.
 static int bi_blocks_per_sm(int t, int r) { return r >= 16 ? (t == 256 ? 1 : 384 / t) : 512 / t; }
 
-static void choose_tile_shape(int n, int num_sms, int world, int opt_T, int opt_R, int opt_TJ, int *T, int *R, int *TJ) {
-    struct Shape { int t, r; double penalty; };
-    const Shape cand[] = {{64, 8, 1.0}, {128, 16, 1.04}, {128, 8, 1.015}, {256, 8, 1.05}, {64, 4, 1.15}, {64, 2, 1.3}};
+// With the row shuffle (64-thread shapes) a thread issues R instead of R + 1 square roots per column and a tile has
+// (T/32)(32R - 1) rows; the factors of those shapes are the measured ones of the shuffle variant (64 x 4: 1435 vs 1288 us).
+static void choose_tile_shape(int n, int num_sms, int world, int opt_T, int opt_R, int opt_TJ, bool shuffle, int *T, int *R, int *TJ) {
+    struct Shape { int t, r; double penalty, penalty_shuffle; };
+    const Shape cand[] = {{64, 8, 1.0, 1.0}, {128, 16, 1.04, 0}, {128, 8, 1.015, 0}, {256, 8, 1.05, 0}, {64, 4, 1.15, 1.11}, {64, 2, 1.3, 1.25}};
     const double OV = 16.0;
     double best = 1e300;
     int bt = 64, br = 2, btj = 32;
@@ -685,11 +697,12 @@ static void choose_tile_shape(int n, int num_sms, int world, int opt_T, int opt_
         const long long slots = (long long)num_sms * bps;
         for (int tj = 32; tj <= 256; tj += 8) {
             const int tjj = opt_TJ ? opt_TJ : tj;
-            const long long nt = tile_plan(n, t * r, tjj, nullptr, nullptr);
+            const bool sh = shuffle && bi_shuffle_supported(t, r);
+            const long long nt = tile_plan(n, bi_tile_rows(t, r, sh ? 1 : 0), tjj, nullptr, nullptr);
             const long long per_rank = (nt + world - 1) / world;
             const double rounds = per_rank <= slots ? 1.0 : (double)per_rank / (double)slots + 1.0;
             if (r >= 16 && rounds < 4.0 && !opt_R) continue;  // 12 warps per SM hide the per-tile prologue only over several rounds
-            const double cost = rounds * (bps * t) * (tjj + OV) * (r + 1) * c.penalty;
+            const double cost = rounds * (bps * t) * (tjj + OV) * (sh ? r * (c.penalty_shuffle > 0 ? c.penalty_shuffle : c.penalty) : (r + 1) * c.penalty);
             if (cost < best) { best = cost; bt = t; br = r; btj = tjj; }
             if (opt_TJ) break;
         }
@@ -706,9 +719,9 @@ static bool prune_wanted(const tspb200_ctx *ctx) {
 static void plan_tiles(tspb200_ctx *ctx, std::vector<int> &row_start, std::vector<int> &row_j0) {
     const int world_eff = ctx->opt_debug_shard ? (ctx->opt_debug_shard >> 8) : ctx->world;
     // the shape search costs ~0.2 ms of host time: remembered per (n, ranks, options)
-    const long long key[6] = {ctx->n, world_eff, ctx->opt_T, ctx->opt_R, ctx->opt_TJ, ctx->num_sms};
+    const long long key[6] = {ctx->n, world_eff * 4 + (ctx->opt_row_shuffle + 1), ctx->opt_T, ctx->opt_R, ctx->opt_TJ, ctx->num_sms};
     if (memcmp(key, ctx->shape_key, sizeof key) != 0) {
-        choose_tile_shape(ctx->n, ctx->num_sms, world_eff, ctx->opt_T, ctx->opt_R, ctx->opt_TJ, &ctx->shape_T, &ctx->shape_R, &ctx->shape_TJ);
+        choose_tile_shape(ctx->n, ctx->num_sms, world_eff, ctx->opt_T, ctx->opt_R, ctx->opt_TJ, ctx->opt_row_shuffle != 0, &ctx->shape_T, &ctx->shape_R, &ctx->shape_TJ);
         memcpy(ctx->shape_key, key, sizeof key);
     }
     ctx->T = ctx->shape_T; ctx->R = ctx->shape_R; ctx->TJ = ctx->shape_TJ;
@@ -724,7 +737,8 @@ static void plan_tiles(tspb200_ctx *ctx, std::vector<int> &row_start, std::vecto
         if (!bi_shape_supported(ctx->T, ctx->R)) { ctx->T = 64; ctx->R = 4; }
     }
     const int slots = ctx->num_sms * bi_blocks_per_sm(ctx->T, ctx->R);
-    ctx->ntiles = (int)tile_plan(ctx->n, ctx->T * ctx->R, ctx->TJ, &row_start, &row_j0);
+    ctx->row_shuffle = (ctx->opt_row_shuffle != 0 && bi_shuffle_supported(ctx->T, ctx->R)) ? 1 : 0;
+    ctx->ntiles = (int)tile_plan(ctx->n, bi_tile_rows(ctx->T, ctx->R, ctx->row_shuffle), ctx->TJ, &row_start, &row_j0);
     ctx->ntr = (int)row_j0.size();
     long long per_rank = (ctx->ntiles + world_eff - 1) / world_eff;
     int grid = ctx->opt_grid > 0 ? ctx->opt_grid : slots;
@@ -752,7 +766,7 @@ int tspb200_debug_tile_plan(int n, int T, int R, int TJ, int num_sms, int world,
                             int *row_start, int *row_j0, int cap, int *ntr) {
     if (n < 1 || num_sms < 1 || world < 1) return TSPB200_E_ARG;
     int t = T, r = R, tj = TJ;
-    if (t == 0 || r == 0 || tj == 0) choose_tile_shape(n, num_sms, world, T, R, TJ, &t, &r, &tj);
+    if (t == 0 || r == 0 || tj == 0) choose_tile_shape(n, num_sms, world, T, R, TJ, false, &t, &r, &tj);
     if (!bi_shape_supported(t, r)) return TSPB200_E_ARG;
     std::vector<int> rs, rj;
     tile_plan(n, t * r, tj, &rs, &rj);
@@ -790,8 +804,8 @@ int tspb200_tour_upload(tspb200_ctx *ctx, const int32_t *succ, int64_t log_cap) 
     }
     std::vector<int> row_start, row_j0;
     plan_tiles(ctx, row_start, row_j0);
-    const int TI = ctx->T * ctx->R;
-    const int alloc = ((n + TI - 1) / TI) * TI + TI + 1024 + 16;
+    const int TI = ctx->T * ctx->R;  // (an upper bound of the tile height when the shuffle variant is planned)
+    const int alloc = ((n + TI - 1) / TI) * TI + 2 * TI + 1024 + 16;
     if (n > ctx->tour_cap_n || alloc > ctx->tour_cap_rec || log_cap > ctx->tour_cap_log) {
         free_tour(ctx);
         CK(cudaMalloc(&ctx->tour.rec, sizeof(float4) * (size_t)alloc));
@@ -992,6 +1006,7 @@ int tspb200_bi_run(tspb200_ctx *ctx, int64_t max_passes, tspb200_stats *st) {
     // exact tile pruning: same moves, fewer evaluated pairs (the throughput benchmarks switch it off: "prune" = 0)
     const bool prune = path == 0 && !ctx->tabu_on && ctx->ntr > 0 && prune_wanted(ctx);
     a.pruned = prune ? 1 : 0;
+    a.row_shuffle = ctx->row_shuffle;
     // multi-GPU: keys travel as NVLink peer stores from the scan kernel (path 0) unless NCCL was asked for
     const bool use_xchg = ctx->world > 1 && path == 0 && ctx->xchg.enabled && ctx->opt_exchange == 0;
     a.xchg = ctx->xchg;
@@ -1054,7 +1069,7 @@ int tspb200_bi_run(tspb200_ctx *ctx, int64_t max_passes, tspb200_stats *st) {
                 CK(cudaEventRecord(ctx->pass_events[2 * q], ctx->stream));
             }
             if (prune) {
-                CK(launch_tile_prune(a, ctx->T * ctx->R, ctx->grid_bi, pdl, ctx->stream));
+                CK(launch_tile_prune(a, bi_tile_rows(ctx->T, ctx->R, ctx->row_shuffle), ctx->grid_bi, pdl, ctx->stream));
                 host_launches += 2;
             }
             if (ctx->tabu_on)

@@ -353,9 +353,10 @@ cudaError_t launch_two_opt_batch(const InstDev &I, int mode, int *succ, const in
 
 // ---- best improvement in POSITION space (the grid kernel's evaluator, one thread block per tour) ----------------------------
 // The node-space evaluator above needs two fresh distances per pair; in position space every distance D[p][q] serves the two
-// moves (p,q) and (p-1,q-1), a lane owns R consecutive rows and marches along the columns: (R+1)/R square roots per move,
+// moves (p,q) and (p-1,q-1), a lane owns R consecutive rows and marches along the columns; the distance of the row below them
+// is the next lane's: one square root per move (a warp covers 32 R - 1 rows),
 // packed FP32x2 arithmetic, one filter test per warp and 4 columns, hits resolved by the whole warp in FP64 — exactly
-// bi_scan_kernel, with the tour records {x, y, ds, node} in shared memory instead of L2.  A warp covers 32*R rows; the
+// bi_scan_kernel, with the tour records {x, y, ds, node} in shared memory instead of L2.  A warp covers 32 R - 1 rows; the
 // (row tile, column) space of the upper triangle is cut into equal contiguous shares, one per warp, so a warp loads its
 // rows at most twice per pass.  Result = reference src/tabusearch.c:107-178 bit for bit (same (delta, i, j) argmin, same
 // forward-path reversal), for GA offspring repair / multi-start / VNS and tabu restarts on EUC_2D / CEIL_2D / ATT instances.
@@ -399,10 +400,12 @@ __device__ __noinline__ MoveKey bpos_cold_warp(const InstDev I, const float4 *re
     return key_warp_min(best);
 }
 
-// distances from the lane's R+1 rows to one column point (rows in packed pairs, the successor row scalar)
-template <int R, bool ATT>
-__device__ __forceinline__ void bpos_column(const f32x2 (&xr2)[R / 2], const f32x2 (&yr2)[R / 2], float xrl, float yrl, float cx,
-                                            float cy, float (&D)[R + 1]) {
+// distances from the lane's R rows to one column point (rows in packed pairs); D[R], the distance from the row below them —
+// the next lane's first row: a warp owns 32 R - 1 consecutive rows — comes from that lane by one shuffle when NEXT is set
+// (R square roots per column instead of R + 1; lane 31's last row, whose lower neighbour lives in another warp's share,
+// is masked out by the caller and scanned as the first row of the next row tile)
+template <int R, bool ATT, bool NEXT>
+__device__ __forceinline__ void bpos_column(const f32x2 (&xr2)[R / 2], const f32x2 (&yr2)[R / 2], float cx, float cy, float (&D)[R + 1]) {
     const f32x2 cxx = f2pack(cx, cx), cyy = f2pack(cy, cy);
 #pragma unroll
     for (int k = 0; k < R / 2; ++k) {
@@ -412,10 +415,10 @@ __device__ __forceinline__ void bpos_column(const f32x2 (&xr2)[R / 2], const f32
         D[2 * k] = sqrt_approx(f2lo(s));
         D[2 * k + 1] = sqrt_approx(f2hi(s));
     }
-    D[R] = bt_dist32<ATT>(xrl, yrl, cx, cy);
+    D[R] = NEXT ? __shfl_down_sync(0xffffffffu, D[0], 1) : 0.f;
 }
 
-// One warp scans rows [p0w, p0w + 32 R) x columns [qb, qe) (qb, qe multiples of 4) of the shared-memory tour.
+// One warp scans rows [p0w, p0w + 32 R - 1) x columns [qb, qe) (qb, qe multiples of 4) of the shared-memory tour.
 template <int R, bool ATT, bool EXACT32, bool DIAG>
 __device__ __forceinline__ void bpos_scan(const InstDev &I, const float4 *rec, int n, int p0w, int qb, int qe, float W,
                                           volatile int *s_hint, MoveKey &best, unsigned long long &colds) {
@@ -430,14 +433,14 @@ __device__ __forceinline__ void bpos_scan(const InstDev &I, const float4 *rec, i
         yr2[k] = f2add(f2pack(v0.y, v1.y), zero2);
         cp2[k] = f2sub(zero2, f2pack(v0.z, v1.z));  // padding rows: ds = -BIG -> +BIG -> never a candidate
     }
-    const float xrl = rec[p0 + R].x, yrl = rec[p0 + R].y;
+    if (lane == 31) cp2[R / 2 - 1] = f2pack(f2lo(cp2[R / 2 - 1]), TSPB_BIG);  // its lower neighbour is not in this warp: next row tile's first row
     float thr = (float)(*s_hint) + W;
     float4 c0 = rec[qb];
     float4 cnext = rec[qb + 1];
     f32x2 U2[R / 2];
     {
         float D0[R + 1];
-        bpos_column<R, ATT>(xr2, yr2, xrl, yrl, c0.x, c0.y, D0);
+        bpos_column<R, ATT, false>(xr2, yr2, c0.x, c0.y, D0);
 #pragma unroll
         for (int k = 0; k < R / 2; ++k) U2[k] = f2add(f2pack(D0[2 * k], D0[2 * k + 1]), cp2[k]);
     }
@@ -449,7 +452,7 @@ __device__ __forceinline__ void bpos_scan(const InstDev &I, const float4 *rec, i
             const float4 c1 = cnext;
             cnext = rec[q4 + c + 2];
             float Dn[R + 1];
-            bpos_column<R, ATT>(xr2, yr2, xrl, yrl, c1.x, c1.y, Dn);
+            bpos_column<R, ATT, true>(xr2, yr2, c1.x, c1.y, Dn);
             float m = TSPB_BIG;
 #pragma unroll
             for (int r = 0; r < R; ++r) {
@@ -493,7 +496,7 @@ __global__ void __launch_bounds__(BPOS_THREADS) two_opt_batch_bi_kernel(const In
     __shared__ MoveKey s_win;
     __shared__ long long s_cost[BPOS_THREADS / 32];
     constexpr int NW = BPOS_THREADS / 32;
-    constexpr int NR = 32 * R;  // rows per warp tile
+    constexpr int NR = 32 * R - 1;  // rows (moves) per warp tile: the 32nd lane's last row overlaps the next tile's first
     const int n = I.n;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     float4 *rec = reinterpret_cast<float4 *>(smem_raw);
@@ -643,7 +646,7 @@ __global__ void __launch_bounds__(BPOS_THREADS) two_opt_batch_bi_kernel(const In
 template <int R, bool ATT, bool EXACT32>
 static cudaError_t launch_bpos_t(const InstDev &I, int *succ, const int *slots, long long *obj, long long *counters, int batch,
                                  int num_sms, cudaStream_t st, int *launched, MoveRec *log, long long log_cap) {
-    constexpr int NR = 32 * R;
+    constexpr int NR = 32 * R - 1;
     const int n = I.n;
     const int ntr = n >= 4 ? (n - 2 + NR - 1) / NR : 0;
     int alloc = ntr * NR + R + 1;

@@ -31,7 +31,10 @@ __device__ __forceinline__ float dist32(float ax, float ay, float bx, float by) 
 
 
 // distances from R+1 consecutive rows to one column point: rows 0..R-1 in R/2 packed pairs, row R scalar
-template <int R, bool ATT>
+// LAST: how D[R] — the distance from the row just below this thread's rows, i.e. the first row of the next lane — is
+// obtained: 1 = computed here (scalar, the (R+1)-th square root of the column), 2 = taken from the next lane with one
+// shuffle (SHUF kernels: the lanes of a warp own adjacent row groups, so that distance is lane+1's D[0]), 0 = not needed.
+template <int R, bool ATT, int LAST>
 __device__ __forceinline__ void column_dists(const f32x2 (&xr2)[R / 2], const f32x2 (&yr2)[R / 2], float xrl, float yrl,
                                              float cx, float cy, float (&D)[R + 1]) {
     const f32x2 cxx = f2pack(cx, cx), cyy = f2pack(cy, cy);
@@ -44,7 +47,9 @@ __device__ __forceinline__ void column_dists(const f32x2 (&xr2)[R / 2], const f3
         D[2 * k] = sqrt_approx(f2lo(s));
         D[2 * k + 1] = sqrt_approx(f2hi(s));
     }
-    D[R] = dist32<ATT>(xrl, yrl, cx, cy);
+    if (LAST == 1) D[R] = dist32<ATT>(xrl, yrl, cx, cy);
+    else if (LAST == 2) D[R] = __shfl_down_sync(0xffffffffu, D[0], 1);
+    else D[R] = 0.f;
 }
 
 // ---- cold path ------------------------------------------------------------------------------------------
@@ -100,7 +105,12 @@ __device__ __noinline__ MoveKey bi_cold_warp(const InstDev I, const float4 *rec,
 // Shared memory per block (dynamic): two column buffers (TJ+2 records) filled by TMA bulk copies, one mbarrier per stage,
 // plus the tile tables.  Row records go straight from L2 into registers: a thread's R+1 rows are 16*(R+1) contiguous bytes,
 // and reading them through shared memory would put all lanes of a quarter-warp on the same banks (stride 16*R bytes).
-template <int BI_THREADS, int R, bool ATT, bool EXACT32, bool PRUNED>
+//
+// SHUF: a warp owns 32 R - 1 consecutive rows instead of 32 R: lane L holds rows p0 .. p0+R-1 with p0 = warp base + L R, the
+// distance of the row below its last one is lane L+1's first distance of the same column (one SHFL instead of a square root
+// and four FP32 instructions), and lane 31's last row — whose lower neighbour lives in another warp — is masked out and
+// scanned again as the first row of the next warp.  R square roots per R moves (minus 1/32R): the algorithmic minimum.
+template <int BI_THREADS, int R, bool ATT, bool EXACT32, bool PRUNED, bool SHUF>
 __global__ void __launch_bounds__(BI_THREADS, (R >= 16 ? (BI_THREADS == 256 ? 1 : 384 / BI_THREADS) : 512 / BI_THREADS)) bi_scan_kernel(const BiArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long bars[2];
@@ -116,7 +126,7 @@ __global__ void __launch_bounds__(BI_THREADS, (R >= 16 ? (BI_THREADS == 256 ? 1 
     pdl_launch_dependents();
     const int n = A.inst.n;
     const int TJ = A.TJ;
-    constexpr int TI = BI_THREADS * R;
+    constexpr int TI = SHUF ? (BI_THREADS / 32) * (32 * R - 1) : BI_THREADS * R;  // rows (moves) of a tile
     const float W = A.inst.W;
     const float4 *rec = A.tour.rec;
     float4 *scols0 = reinterpret_cast<float4 *>(smem_raw);
@@ -261,7 +271,7 @@ __global__ void __launch_bounds__(BI_THREADS, (R >= 16 ? (BI_THREADS == 256 ? 1 
         if (tid == 0) draw(buf ^ 1, false);
 
         // rows of this thread: p0 .. p0+R-1 in packed pairs (+ successor row p0+R, scalar)
-        const int p0 = P0 + tid * R;
+        const int p0 = SHUF ? P0 + (tid >> 5) * (32 * R - 1) + (tid & 31) * R : P0 + tid * R;
         f32x2 xr2[R / 2], yr2[R / 2], cp2[R / 2];
         float xrl, yrl;
 #pragma unroll
@@ -274,10 +284,14 @@ __global__ void __launch_bounds__(BI_THREADS, (R >= 16 ? (BI_THREADS == 256 ? 1 
             yr2[k] = f2add(f2pack(v0.y, v1.y), zero2);
             cp2[k] = f2sub(zero2, f2pack(v0.z, v1.z));  // padding rows carry ds = -BIG -> cp = +BIG -> never a candidate
         }
-        {
+        if (!SHUF) {
             const float4 v = __ldg(&rec[p0 + R]);
             xrl = v.x;
             yrl = v.y;
+        } else {
+            xrl = yrl = 0.f;
+            // lane 31's last row has its lower neighbour in another warp: never a candidate here (it is the next warp's first row)
+            if ((tid & 31) == 31) cp2[R / 2 - 1] = f2pack(f2lo(cp2[R / 2 - 1]), TSPB_BIG);
         }
         thr = fminf(thr, (float)(*((volatile int *)&s_hint)) + W);
 
@@ -295,7 +309,7 @@ __global__ void __launch_bounds__(BI_THREADS, (R >= 16 ? (BI_THREADS == 256 ? 1 
         c0 = sc[(JB)];                                                                                 \
         cnext = sc[(JB) + 1];                                                                          \
         float D0[R + 1];                                                                               \
-        column_dists<R, ATT>(xr2, yr2, xrl, yrl, c0.x, c0.y, D0);                                      \
+        column_dists<R, ATT, SHUF ? 0 : 1>(xr2, yr2, xrl, yrl, c0.x, c0.y, D0);                        \
         _Pragma("unroll") for (int k = 0; k < R / 2; ++k) U2[k] = f2add(f2pack(D0[2 * k], D0[2 * k + 1]), cp2[k]); \
     }
 #define UU(r_) (((r_) & 1) ? f2hi(U2[(r_) >> 1]) : f2lo(U2[(r_) >> 1]))
@@ -307,7 +321,7 @@ __global__ void __launch_bounds__(BI_THREADS, (R >= 16 ? (BI_THREADS == 256 ? 1 
         const float4 c1 = cnext;                                                                       \
         cnext = sc[(jj_) + 2]; /* prefetched one column ahead */                                       \
         float Dn[R + 1];                                                                               \
-        column_dists<R, ATT>(xr2, yr2, xrl, yrl, c1.x, c1.y, Dn);                                      \
+        column_dists<R, ATT, SHUF ? 2 : 1>(xr2, yr2, xrl, yrl, c1.x, c1.y, Dn);                        \
         float m = TSPB_BIG;                                                                            \
         _Pragma("unroll") for (int r = 0; r < R; ++r) {                                                \
             float qv = UU(r) + Dn[r + 1];                                                              \
@@ -329,7 +343,7 @@ __global__ void __launch_bounds__(BI_THREADS, (R >= 16 ? (BI_THREADS == 256 ? 1 
         while (hits) {                                                                                 \
             const int L = __ffs(hits) - 1;                                                             \
             const float thrL = __shfl_sync(0xffffffffu, thr, L);                                       \
-            const MoveKey nb = bi_cold_warp<R, ATT, EXACT32>(A.inst, rec, sc, n, P0 + ((tid & ~31) + L) * R, Q0, jj, thrL); \
+            const MoveKey nb = bi_cold_warp<R, ATT, EXACT32>(A.inst, rec, sc, n, p0 + (L - (tid & 31)) * R, Q0, jj, thrL); \
             if ((tid & 31) == L) {                                                                     \
                 atomicAdd(&ctl->cold_calls, 1ull);                                                     \
                 if (key_less(nb, best)) {                                                              \
@@ -924,7 +938,7 @@ __global__ void __launch_bounds__(256) bi_scan_exact_kernel(const InstDev inst, 
 }
 
 // ---- host-side launchers -----------------------------------------------------------------------------
-template <int T, int R>
+template <int T, int R, bool SHUF>
 static cudaError_t launch_bi_tr(const BiArgs &a, int grid, bool pdl, cudaStream_t st) {
     const size_t smem = (size_t)2 * (a.TJ + 2) * sizeof(float4) + (size_t)(2 * a.ntr + 2) * sizeof(int);
     const bool att = (a.inst.metric == M_ATT);
@@ -951,15 +965,24 @@ static cudaError_t launch_bi_tr(const BiArgs &a, int grid, bool pdl, cudaStream_
         return cudaLaunchKernelEx(&cfg, kern, a);
     };
     if (a.pruned) {
-        if (att && ex) return go(bi_scan_kernel<T, R, true, true, true>);
-        if (att) return go(bi_scan_kernel<T, R, true, false, true>);
-        if (ex) return go(bi_scan_kernel<T, R, false, true, true>);
-        return go(bi_scan_kernel<T, R, false, false, true>);
+        if (att && ex) return go(bi_scan_kernel<T, R, true, true, true, SHUF>);
+        if (att) return go(bi_scan_kernel<T, R, true, false, true, SHUF>);
+        if (ex) return go(bi_scan_kernel<T, R, false, true, true, SHUF>);
+        return go(bi_scan_kernel<T, R, false, false, true, SHUF>);
     }
-    if (att && ex) return go(bi_scan_kernel<T, R, true, true, false>);
-    if (att) return go(bi_scan_kernel<T, R, true, false, false>);
-    if (ex) return go(bi_scan_kernel<T, R, false, true, false>);
-    return go(bi_scan_kernel<T, R, false, false, false>);
+    if (att && ex) return go(bi_scan_kernel<T, R, true, true, false, SHUF>);
+    if (att) return go(bi_scan_kernel<T, R, true, false, false, SHUF>);
+    if (ex) return go(bi_scan_kernel<T, R, false, true, false, SHUF>);
+    return go(bi_scan_kernel<T, R, false, false, false, SHUF>);
+}
+
+// rows (moves) of one tile for a block of `threads` threads with `rows_per_thread` rows each
+int bi_tile_rows(int threads, int rows_per_thread, int row_shuffle) {
+    return row_shuffle ? (threads / 32) * (32 * rows_per_thread - 1) : threads * rows_per_thread;
+}
+// the shuffle variant is built for the 64-thread shapes (the ones the shape model picks)
+bool bi_shuffle_supported(int threads, int rows_per_thread) {
+    return threads == 64 && (rows_per_thread == 2 || rows_per_thread == 4 || rows_per_thread == 8);
 }
 
 // supported (threads, rows per thread) shapes; anything else is rejected by tspb200_set_option
@@ -972,19 +995,25 @@ bool bi_shape_supported(int threads, int rows_per_thread) {
 
 cudaError_t launch_bi_scan(const BiArgs &a, int threads, int rows_per_thread, int grid, bool pdl, cudaStream_t st) {
     const int R = rows_per_thread;
+    if (a.row_shuffle) {
+        if (threads == 64 && R == 8) return launch_bi_tr<64, 8, true>(a, grid, pdl, st);
+        if (threads == 64 && R == 4) return launch_bi_tr<64, 4, true>(a, grid, pdl, st);
+        if (threads == 64 && R == 2) return launch_bi_tr<64, 2, true>(a, grid, pdl, st);
+        return cudaErrorInvalidValue;
+    }
     if (threads == 256) {
-        if (R == 16) return launch_bi_tr<256, 16>(a, grid, pdl, st);
-        if (R == 8) return launch_bi_tr<256, 8>(a, grid, pdl, st);
-        if (R == 4) return launch_bi_tr<256, 4>(a, grid, pdl, st);
-        if (R == 2) return launch_bi_tr<256, 2>(a, grid, pdl, st);
+        if (R == 16) return launch_bi_tr<256, 16, false>(a, grid, pdl, st);
+        if (R == 8) return launch_bi_tr<256, 8, false>(a, grid, pdl, st);
+        if (R == 4) return launch_bi_tr<256, 4, false>(a, grid, pdl, st);
+        if (R == 2) return launch_bi_tr<256, 2, false>(a, grid, pdl, st);
     } else if (threads == 128) {
-        if (R == 16) return launch_bi_tr<128, 16>(a, grid, pdl, st);
-        if (R == 8) return launch_bi_tr<128, 8>(a, grid, pdl, st);
-        if (R == 4) return launch_bi_tr<128, 4>(a, grid, pdl, st);
+        if (R == 16) return launch_bi_tr<128, 16, false>(a, grid, pdl, st);
+        if (R == 8) return launch_bi_tr<128, 8, false>(a, grid, pdl, st);
+        if (R == 4) return launch_bi_tr<128, 4, false>(a, grid, pdl, st);
     } else if (threads == 64) {
-        if (R == 8) return launch_bi_tr<64, 8>(a, grid, pdl, st);
-        if (R == 4) return launch_bi_tr<64, 4>(a, grid, pdl, st);
-        if (R == 2) return launch_bi_tr<64, 2>(a, grid, pdl, st);
+        if (R == 8) return launch_bi_tr<64, 8, false>(a, grid, pdl, st);
+        if (R == 4) return launch_bi_tr<64, 4, false>(a, grid, pdl, st);
+        if (R == 2) return launch_bi_tr<64, 2, false>(a, grid, pdl, st);
     }
     return cudaErrorInvalidValue;
 }

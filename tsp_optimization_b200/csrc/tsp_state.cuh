@@ -453,6 +453,7 @@ struct BiArgs {
     int seed_hint;   // 0 = none, 1 = this block's previous winner re-evaluated at the start of the scan, 2 = also runner-ups
     int packed_tail; // 1: blocks fold their key into ctl->pass_min with one 64-bit atomicMin (n <= 2^17, seed_hint < 2)
     int pruned;      // 1: tiles come from the live list built by tile_filter_kernel (exact tile pruning)
+    int row_shuffle; // 1: SHUF kernels (a warp owns 32 R - 1 rows, the distance below a lane's rows comes from the next lane)
     int timing;      // 1: accumulate the per-pass breakdown in ctl->tm_acc; 2: also dump per-block {start, end} stamps
     unsigned long long *dbg;        // timing == 2: [gridDim.x][2] globaltimer stamps of the last pass
     XchgDev xchg;    // fuse_apply == 0: how this rank's key reaches the other ranks (enabled = 0 -> NCCL allreduce of ctl->packed)

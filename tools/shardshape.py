@@ -8,6 +8,7 @@ eng.set_instance(uniform_instance(n), 0)
 succ, _ = eng.nn_tour(0)
 world = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 eng.set_option("debug_shard", (world << 8) | 0)
+eng.set_option("prune", 0)  # exhaustive passes: this is about the throughput shapes
 shapes = [(0, 0, 0)] + [(64, 8, tj) for tj in (64, 96, 128, 160, 192, 224, 256)] + [(64, 4, tj) for tj in (128, 256)] + \
          [(128, 16, tj) for tj in (128, 192)] + [(128, 8, tj) for tj in (128, 256)]  # (64 x R: row-shuffle variant unless row_shuffle = 0)
 for T, R, TJ in shapes:

@@ -680,7 +680,9 @@ static long long tile_plan(int n, int TI, int TJ, std::vector<int> *row_start, s
 // The per-shape factors are measured on B200 at n = 100 000 (tools/shardshape.py): 64-thread blocks (8 per SM, 16 warps)
 // hide latency best; R = 16 (1.0625 sqrt per move) pays with 150 registers, i.e. 12 warps per SM; R = 4 and 2 spend more
 // instructions per move than their sqrt count alone says.
-static int bi_blocks_per_sm(int t, int r) { return r >= 16 ? (t == 256 ? 1 : 384 / t) : 512 / t; }
+static int bi_blocks_per_sm(int t, int r, bool pruned = false) {  // 64 threads, exhaustive scan: TSPB_BI_MINBLOCKS64 (kernels_bi.cu)
+    return r >= 16 ? (t == 256 ? 1 : 384 / t) : (t == 64 && !pruned ? 10 : 512 / t);
+}
 
 // With the row shuffle (64-thread shapes) a thread issues R instead of R + 1 square roots per column and a tile has
 // (T/32)(32R - 1) rows; the factors of those shapes are the measured ones of the shuffle variant (64 x 4: 1435 vs 1288 us).
@@ -736,7 +738,8 @@ static void plan_tiles(tspb200_ctx *ctx, std::vector<int> &row_start, std::vecto
         if (!ctx->opt_TJ) ctx->TJ = ctx->n < 40000 ? 32 : 64;
         if (!bi_shape_supported(ctx->T, ctx->R)) { ctx->T = 64; ctx->R = 4; }
     }
-    const int slots = ctx->num_sms * bi_blocks_per_sm(ctx->T, ctx->R);
+    const bool pruned_plan = prune_wanted(ctx) && ctx->inst.fp32_ok && ctx->opt_force_path <= 0 && ctx->n >= PRUNE_AUTO_MIN_N;
+    const int slots = ctx->num_sms * bi_blocks_per_sm(ctx->T, ctx->R, pruned_plan);
     ctx->row_shuffle = (ctx->opt_row_shuffle != 0 && bi_shuffle_supported(ctx->T, ctx->R)) ? 1 : 0;
     ctx->ntiles = (int)tile_plan(ctx->n, bi_tile_rows(ctx->T, ctx->R, ctx->row_shuffle), ctx->TJ, &row_start, &row_j0);
     ctx->ntr = (int)row_j0.size();
@@ -957,6 +960,7 @@ static int prepare_run(tspb200_ctx *ctx, bool reset_fi_cursor, long long max_mov
     h->max_moves = max_moves_abs;
     h->fi_shard_min_gap = ctx->opt_fi_shard_min_gap;
     h->fi_pend_node = -1;
+    h->fi_mode[0] = h->fi_mode[1] = 0;
     h->fi_sel[0] = h->fi_sel[1] = FI_NONE;  // both hit words of the late-selection search start clean, parity 0 first
     ctx->fi_parity = 0;
     if (reset_fi_cursor || ctx->opt_fi_shard_min_gap == 0) h->fi_shard = ctx->opt_fi_shard_min_gap == 0 ? 1 : 0;
@@ -1193,7 +1197,8 @@ int tspb200_fi_run(tspb200_ctx *ctx, int64_t max_moves, tspb200_stats *st) {
         while (!done) {
             for (long long q = 0; q < batch; ++q) {
                 // one GPU: the search only folds its hits into ctl->fi_sel[parity]; the apply launch takes the winner from there
-                const int late = (ctx->world == 1 && ctx->opt_fi_late) ? 1 + (int)(ctx->fi_parity++ & 1) : 0;
+                const bool late_ok = ctx->opt_fi_late && (ctx->world == 1 || use_xchg);  // (the NCCL exchange keeps the published-move path)
+                const int late = late_ok ? 1 + (int)(ctx->fi_parity++ & 1) : 0;
                 CK(launch_fi_search(I, ctx->tour, ctx->rank, ctx->world, use_xchg ? &xd : nullptr, late, grid, pdl, ctx->stream));
                 host_launches++;
                 if (ctx->world > 1 && !use_xchg) {
@@ -1223,7 +1228,7 @@ int tspb200_fi_run(tspb200_ctx *ctx, int64_t max_moves, tspb200_stats *st) {
             }
         }
         if (done && cap >= 0 && ctx->h_ctl->moves >= cap) status = TSPB200_STOPPED_BY_CAP;
-        if (ctx->world == 1 && ctx->opt_fi_late) CK(launch_fi_flush(ctx->tour, ctx->stream));  // the last apply's parked pos[] entry
+        if (ctx->opt_fi_late && (ctx->world == 1 || use_xchg)) CK(launch_fi_flush(ctx->tour, ctx->stream));  // the last apply's parked pos[] entry
     }
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));

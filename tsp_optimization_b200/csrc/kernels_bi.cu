@@ -110,8 +110,16 @@ __device__ __noinline__ MoveKey bi_cold_warp(const InstDev I, const float4 *rec,
 // distance of the row below its last one is lane L+1's first distance of the same column (one SHFL instead of a square root
 // and four FP32 instructions), and lane 31's last row — whose lower neighbour lives in another warp — is masked out and
 // scanned again as the first row of the next warp.  R square roots per R moves (minus 1/32R): the algorithmic minimum.
+#ifndef TSPB_BI_MINBLOCKS64
+// Resident 64-thread blocks per SM the compiler must leave room for (register cap 65536 / (64 x this)).  Measured on B200,
+// 64 x 8 x 256 row-shuffle kernel at n = 100 000 (profiles/r2_blocks_per_sm_ab.jsonl): 8 blocks (100 registers) 1288 us per
+// pass, 10 blocks (94 registers, no spills) 1276 us — and 184 vs 189 us for one rank's share of eight —, 12 blocks (80
+// registers, spills) 1321 us.  engine.cu (bi_blocks_per_sm) sizes the grid to match.  The pruned variants (more live state: they
+// would spill under the lower cap) keep 8.
+#define TSPB_BI_MINBLOCKS64 10
+#endif
 template <int BI_THREADS, int R, bool ATT, bool EXACT32, bool PRUNED, bool SHUF>
-__global__ void __launch_bounds__(BI_THREADS, (R >= 16 ? (BI_THREADS == 256 ? 1 : 384 / BI_THREADS) : 512 / BI_THREADS)) bi_scan_kernel(const BiArgs A) {
+__global__ void __launch_bounds__(BI_THREADS, (R >= 16 ? (BI_THREADS == 256 ? 1 : 384 / BI_THREADS) : (BI_THREADS == 64 && !PRUNED ? TSPB_BI_MINBLOCKS64 : 512 / BI_THREADS))) bi_scan_kernel(const BiArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long bars[2];
     __shared__ int s_hint;
@@ -568,7 +576,7 @@ __global__ void bi_decode_packed_kernel(const TourDev tour) {
 // Grid-wide application of the published move (see apply_swap_range).
 // seed: number of block_best[] entries (the scan's grid size) to re-evaluate as seeds of the next pass's filter, 0 = none
 // NODE: also keep the node-space view of the first-improvement search current (see apply_swap_range)
-// fi_late (first improvement on one GPU): 1 + parity — nobody has published a move; every thread reads the search's winner
+// fi_late (first improvement, searches that were not sharded): 1 + parity — nobody has published a move; every thread reads the search's winner
 // ctl->fi_sel[parity] = (i << 32) | j and the two positions itself (two round trips, one more than reading a published
 // move, instead of the search kernel's whole "last block" tail), global thread 0 — which applies swap 0 and therefore
 // holds the four edge lengths of the move — logs it and advances the sweep.
@@ -578,7 +586,9 @@ __global__ void __launch_bounds__(256) apply_move_kernel(const InstDev inst, con
     Ctl *ctl = tour.ctl;
     pdl_launch_dependents();
     pdl_wait();
-    if (NODE && fi_late) {
+    // (a sharded search — several GPUs, ctl->fi_mode — has published its move itself: the classic path below)
+    if (NODE && fi_late && blockIdx.x == 0 && threadIdx.x == 0) ctl->fi_sel[(fi_late - 1) ^ 1] = FI_NONE;  // the next search's word
+    if (NODE && fi_late && *((volatile int *)&ctl->fi_mode[fi_late - 1]) == 0) {
         const int gtid = blockIdx.x * 256 + threadIdx.x;
         const unsigned long long f = *((volatile unsigned long long *)&ctl->fi_sel[fi_late - 1]);
         int done = 0, i0 = 0, j0 = 0;
@@ -614,9 +624,8 @@ __global__ void __launch_bounds__(256) apply_move_kernel(const InstDev inst, con
             ctl->ap_valid = 0;
             fi_advance(tour, f, i0, j0);
         }
-        // The next search's word; this launch's own word is reset by the next apply launch — also by the no-op launches that
-        // follow a finished run inside a batch, or the launch after them would find this move again.
-        if (gtid == 0) ctl->fi_sel[(fi_late - 1) ^ 1] = FI_NONE;
+        // (This launch's own word is reset by the next apply launch — also by the no-op launches that follow a finished run
+        // inside a batch, or the launch after them would find this move again.)
         return;
     }
     if (!ctl->ap_valid) return;

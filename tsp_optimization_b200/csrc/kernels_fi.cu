@@ -90,8 +90,13 @@ __global__ void __launch_bounds__(FI_THREADS) fi_search_kernel(const InstDev I, 
     // search itself; every rank then searches alone — same pair, same tour — and the ranks only share the work of the long
     // searches of the late sweeps (ctl->fi_shard, set by fi_finish from the length of the previous search).
     const bool shard = S.world > 1 && *((volatile int *)&ctl->fi_shard) != 0;
-    unsigned long long *found = S.late ? &ctl->fi_sel[S.late - 1] : &ctl->fi_found;
-    if (S.late && blockIdx.x == 0 && threadIdx.x == 0) {  // the position entry the previous apply launch parked (nobody reads pos[] here)
+    // late selection (S.late = 1 + parity): unless this search is sharded — then its last block exchanges the winner with the
+    // other ranks and publishes the move as before — the hits go to ctl->fi_sel[parity] and the kernel has no tail
+    const bool late_now = S.late != 0 && !shard;
+    unsigned long long *found = late_now ? &ctl->fi_sel[S.late - 1] : &ctl->fi_found;
+    if (S.late && blockIdx.x == 0 && threadIdx.x == 0) {
+        ctl->fi_mode[S.late - 1] = shard ? 1 : 0;  // tells the apply launch which of the two this search was
+        // the position entry the previous apply launch parked (nobody reads pos[] before this kernel's last block)
         const int pn = *((volatile int *)&ctl->fi_pend_node);
         if (pn >= 0) {
             T.pos[pn] = ctl->fi_pend_pos;
@@ -209,7 +214,7 @@ __global__ void __launch_bounds__(FI_THREADS) fi_search_kernel(const InstDev I, 
         __syncthreads();  // s_seg / s_minhit are rewritten by the next round
     }
 
-    if (S.late) return;  // the apply launch reads ctl->fi_sel[parity] itself
+    if (late_now) return;  // the apply launch reads ctl->fi_sel[parity] itself
     // ---- last block: exchange (several GPUs), then publish the winning move / close the sweep ---------------
     __syncthreads();
     if (tid == 0) {

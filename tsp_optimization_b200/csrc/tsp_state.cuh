@@ -74,6 +74,7 @@ struct Ctl {
     // overwrite under their eyes — pos[b], written by swap 0 — is parked here and stored by the next search launch (which never
     // reads pos[]) or by fi_flush_kernel at the end of the run.
     int fi_pend_node, fi_pend_pos;   // fi_pend_node < 0: nothing parked
+    int fi_mode[2];                  // per launch parity: 1 = that search was sharded and published its move itself (several GPUs)
     long long fi_shard_min_gap;     // pairs swept by the last search above which the next one is sharded
     // exact tile pruning: this rank's live tiles of the coming pass, built by tile_filter_kernel
     unsigned live_count;            // entries in TourDev::live

@@ -22,3 +22,17 @@ python tools/ncu_summary.py full gpurun_out/prof.ncu-rep > gpurun_out/ncu_full.t
 # multi-GPU (gpurun --gpus N): python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29513 \
 #     bench.py --gpus N --steps 100 --warmup 5            -> profiles/r1_bench_nN.json
 #   ... tools/mgpu_check.py 20000 40 / tools/batch_mgpu.py FI  (parity of the sharded paths, profiles/r1_ga_batch_1_and_2_gpus.jsonl)
+
+# ---- round 2 (files profiles/r2_*) ----------------------------------------------------------------------------------------
+python bench.py --steps 20 --warmup 5 > gpurun_out/bench_r2_g1.json                            # profiles/r2_bench_n1.json
+python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_r2_ref.json           # profiles/r2_bench_reference_arm.json
+bash tools/gpu_profiles_r2.sh                                                                  # r2_launches_bench.txt, r2_ncu_full_*.txt, r2_*_hotspots.txt
+python tools/prune_probe.py 10000 20000 > gpurun_out/prune_probe.jsonl                         # r2_prune_probe_n10k_n20k.jsonl (PRUNE_SHAPES=... for r2_prune_probe_small_tiles.jsonl)
+python tools/prune_probe.py 100000 > gpurun_out/prune_probe_100k.jsonl                         # r2_prune_probe_n100k.jsonl
+python tools/r2_probe.py b c d > gpurun_out/r2_probe.jsonl                                     # r2_fi_latency.jsonl, r2_pruned_pass_phases_n10k.jsonl, r2_nn_grid_walk.jsonl
+python tools/shuf_ab.py > gpurun_out/shuf_ab.jsonl                                             # r2_row_shuffle_ab.jsonl
+python tools/occ_ab.py > gpurun_out/occ_ab.jsonl                                               # r2_blocks_per_sm_ab.jsonl (second build: make OUT=../lib_alt EXTRA=-DTSPB_BI_MINBLOCKS64=8, TSPB200_LIB=...)
+for w in 8 4 2; do python tools/shardshape.py $w; done > gpurun_out/shardshape.jsonl           # r2_shard_shapes_row_shuffle.jsonl
+python tools/tail_probe.py > gpurun_out/tail_probe.jsonl; python tools/tj_sweep.py > gpurun_out/tj_sweep.jsonl   # r2_tail_probe.jsonl, r2_tile_width_sweep.jsonl
+python tools/fuzz.py 150 21 > gpurun_out/fuzz.jsonl                                            # r2_fuzz.jsonl (one line per run)
+# multi-GPU (gpurun --gpus 2 / 8): bash tools/gpu_round2.sh, bash tools/gpu_round8.sh         -> r2_bench_n2/4/8.json, r2_mgpu_check.txt

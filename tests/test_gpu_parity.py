@@ -469,6 +469,48 @@ def test_errors_are_loud(engine):
         engine.set_option("rows_per_thread", 3)
 
 
+def test_upload_ranks_the_successor_array_on_the_device(engine, oracle):
+    """tour upload: visiting order from the successor array by pointer jumping on the device (csrc/kernels_misc.cu
+    launch_succ_to_order, default for n >= 2048) == the host walk: same state, same 2-opt run; and the same loud rejection of
+    everything that is not one Hamiltonian cycle."""
+    rng = np.random.default_rng(3)
+    for n in (5, 64, 1000, 2049, 5000):
+        xy = np.floor(rng.random((n, 2)) * 3000.0)
+        engine.set_instance(xy, 0)
+        succ = order_to_succ(rng.permutation(n).astype(np.int32))
+        res = {}
+        for mode in (0, 1):
+            engine.set_option("upload_rank", mode)
+            engine.tour_upload(succ, log_cap=16)
+            s0, c0 = engine.tour_download()
+            engine.bi_run(5)
+            res[mode] = (s0, c0, engine.tour_log(16).tolist(), engine.tour_download())
+        assert (res[0][0] == succ).all() and (res[1][0] == succ).all() and res[0][1] == res[1][1] == oracle.succ_cost(xy, 0, succ), n
+        assert res[0][2] == res[1][2] and (res[0][3][0] == res[1][3][0]).all() and res[0][3][1] == res[1][3][1], n
+    n = 3000
+    engine.set_instance(np.floor(rng.random((n, 2)) * 3000.0), 0)
+    good = order_to_succ(rng.permutation(n).astype(np.int32))
+    two_cycles = good.copy()                      # cut the cycle in two: swap the successors of two nodes
+    a, b = 17, int(good[good[good[17]]])
+    two_cycles[a], two_cycles[b] = good[b], good[a]
+    out_of_range = good.copy(); out_of_range[5] = n
+    negative = good.copy(); negative[7] = -1
+    not_a_permutation = good.copy(); not_a_permutation[9] = good[11]
+    self_loops = np.arange(n, dtype=np.int32)
+    try:
+        for mode in (0, 1):
+            engine.set_option("upload_rank", mode)
+            for bad in (two_cycles, out_of_range, negative, not_a_permutation, self_loops):
+                with pytest.raises(eng.TspB200Error):
+                    engine.tour_upload(bad)
+                with pytest.raises(eng.TspB200Error):
+                    engine.bi_run(1)          # nothing resident after a rejected upload
+            engine.tour_upload(good)
+            assert (engine.tour_download()[0] == good).all()
+    finally:
+        engine.set_option("upload_rank", -1)
+
+
 # ---- tabu-masked best improvement (reference src/tabusearch.c:83-92,137-149) ---------------------------------
 @pytest.mark.parametrize("n,wt,density,iter_,tenure", [(60, 0, 0.2, 30, 12), (200, 0, 0.05, 100, 20), (299, 5, 0.3, 50, 49),
                                                        (150, 4, 0.1, 40, 5), (120, 3, 0.5, 10, -1), (500, 0, 0.02, 1000, 50)])

@@ -41,6 +41,7 @@ cudaError_t launch_fi_finish(const InstDev &I, const TourDev &T, cudaStream_t st
 cudaError_t launch_dist_matrix(const InstDev &I, int *out, long long ld, int row_begin, int row_end, bool fast,
                                unsigned long long *geo_near, cudaStream_t st);
 cudaError_t launch_build_state(const InstDev &I, const TourDev &T, const int *order, cudaStream_t st);
+cudaError_t launch_succ_to_order(const int *succ, int n, void *work, int *order, int *err, cudaStream_t st);
 cudaError_t launch_export_state(const TourDev &T, int *succ, unsigned long long *cost, cudaStream_t st);
 cudaError_t launch_tour_cost(const InstDev &I, const int *tours, const int *slots, int as_order, long long *out, int batch,
                              cudaStream_t st);
@@ -217,6 +218,7 @@ struct tspb200_ctx {
     void *peer_mapped[XCHG_MAX_WORLD] = {};
     std::string xchg_note;
     int opt_exchange = 0;  // 0 = peer memory when available, 1 = NCCL allreduce
+    int opt_upload_rank = -1;         // successor array -> visiting order at tour upload: -1 auto (device for n >= 2048), 0 host walk, 1 device
     int opt_row_shuffle = -1;         // best-improvement scan: distance below a lane's rows by shuffle (-1 auto = on where built, 0 off, 1 on)
     int row_shuffle = 0;              // what the current tile plan was made for
     int opt_fi_late = 1;              // first improvement on one GPU: the apply launch selects the winner itself (no search-kernel tail)
@@ -395,6 +397,9 @@ int tspb200_set_option(tspb200_ctx *ctx, const char *key, int64_t value) {
     } else if (k == "timing") {
         if (value < 0 || value > 2) return fail(ctx, TSPB200_E_ARG, "timing must be 0, 1 or 2");
         ctx->opt_timing = (int)value;
+    } else if (k == "upload_rank") {
+        if (value < -1 || value > 1) return fail(ctx, TSPB200_E_ARG, "upload_rank must be -1 (auto), 0 or 1");
+        ctx->opt_upload_rank = (int)value;
     } else if (k == "row_shuffle") {
         if (value < -1 || value > 1) return fail(ctx, TSPB200_E_ARG, "row_shuffle must be -1 (auto), 0 or 1");
         ctx->opt_row_shuffle = (int)value;
@@ -792,9 +797,11 @@ int tspb200_tour_upload(tspb200_ctx *ctx, const int32_t *succ, int64_t log_cap) 
     if (!(ctx->dist_bound < 16777216.0))
         return fail(ctx, TSPB200_E_UNSUPPORTED, "2-opt keeps edge lengths as exact integers in FP32 words: distances up to %.0f "
                     "(>= 2^24) are not supported", ctx->dist_bound);
-    // successor array -> visiting order from node 0 (also validates that succ is one Hamiltonian cycle)
-    std::vector<int> order((size_t)n);
-    {
+    // successor array -> visiting order from node 0 (also validates that succ is one Hamiltonian cycle): by pointer jumping
+    // on the device for big tours (kernels_misc.cu launch_succ_to_order), by a walk on the host for small ones
+    const bool rank_on_device = ctx->opt_upload_rank >= 0 ? ctx->opt_upload_rank == 1 : n >= 2048;
+    std::vector<int> order(rank_on_device ? 0 : (size_t)n);
+    if (!rank_on_device) {
         std::vector<unsigned char> seen((size_t)n, 0);
         int at = 0;
         for (int p = 0; p < n; ++p) {
@@ -871,7 +878,16 @@ int tspb200_tour_upload(tspb200_ctx *ctx, const int32_t *succ, int64_t log_cap) 
     CK(cudaMemcpyAsync(ctx->d_tile_row_start, row_start.data(), sizeof(int) * row_start.size(), cudaMemcpyHostToDevice, ctx->stream));
     if (!row_j0.empty())
         CK(cudaMemcpyAsync(ctx->d_tile_row_j0, row_j0.data(), sizeof(int) * row_j0.size(), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->d_order, order.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    int *d_rank_err = nullptr;
+    if (rank_on_device) {
+        SCRATCH(d_work, unsigned char *, 19, sizeof(int2) * 2 * (size_t)n + sizeof(int) * ((size_t)n + 4));
+        d_rank_err = reinterpret_cast<int *>(d_work + sizeof(int2) * 2 * (size_t)n + sizeof(int) * (size_t)n);
+        CK(cudaMemcpyAsync(ctx->d_succ, succ, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemsetAsync(ctx->d_order, 0, sizeof(int) * (size_t)n, ctx->stream));  // a rejected succ[] leaves holes: keep them valid node ids
+        CK(launch_succ_to_order(ctx->d_succ, n, d_work, ctx->d_order, d_rank_err, ctx->stream));
+    } else {
+        CK(cudaMemcpyAsync(ctx->d_order, order.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    }
     Ctl c0;
     memset(&c0, 0, sizeof c0);
     c0.cur_i = 0; c0.cur_j = 1;
@@ -888,7 +904,13 @@ int tspb200_tour_upload(tspb200_ctx *ctx, const int32_t *succ, int64_t log_cap) 
     CK(cudaMemsetAsync(ctx->tour.block_best, 0, sizeof(MoveKey) * 4096, ctx->stream));  // delta 0 = "no previous winner"
     InstDev I = inst_for_path(ctx, select_path(ctx));
     CK(launch_build_state(I, ctx->tour, ctx->d_order, ctx->stream));
+    int rank_err = 0;
+    if (rank_on_device) CK(cudaMemcpyAsync(&rank_err, d_rank_err, sizeof rank_err, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    if (rank_err) {  // (the state built from a bogus order is never used: has_tour stays false)
+        ctx->has_tour = false;
+        return fail(ctx, TSPB200_E_ARG, "succ[] is not a single cycle over %d nodes", n);
+    }
     ctx->has_tour = true;
     return TSPB200_OK;
 }

@@ -252,6 +252,66 @@ __global__ void rebuild_node_space_kernel(const TourDev T) {
     }
 }
 
+// ---- successor array -> visiting order on the device (tour upload) ------------------------------------------------------
+// The reference's tours are successor arrays (edges[k].j); the position-space state needs the visiting order from node 0.
+// Walking succ[] on the host is n dependent cache misses (0.35 ms at n = 100 000, a third of the fixed cost of a
+// host-buffer 2-opt call); here: list ranking by pointer jumping.  The cycle is cut in front of node 0 (tail = the node whose
+// successor is 0); a[i] = {next, distance to next}; every round replaces next by next's next and adds the distances, so after
+// ceil(log2 n) rounds a[i] = {tail, distance to the tail} and position(i) = n-1 - distance.  Validation = what the host walk
+// checked: every successor in range and hit exactly once (a permutation) and every node reaches the tail (one cycle).
+__global__ void __launch_bounds__(256) rank_init_kernel(const int *succ, int n, int2 *a, int *indeg, int *err) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const int s = succ[i];
+    if (s < 0 || s >= n) {
+        atomicOr(err, 1);
+        a[i] = make_int2(i, 0);
+        return;
+    }
+    atomicAdd(&indeg[s], 1);
+    a[i] = s == 0 ? make_int2(i, 0) : make_int2(s, 1);
+}
+
+__global__ void __launch_bounds__(256) rank_jump_kernel(const int2 *a, int2 *b, int n) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const int2 me = a[i];
+    const int2 nx = a[me.x];
+    b[i] = make_int2(nx.x, me.y + nx.y);
+}
+
+__global__ void __launch_bounds__(256) rank_finish_kernel(const int *succ, const int2 *a, const int *indeg, int n, int *order, int *err) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const int2 me = a[i];
+    // the tail is its own successor in the cut list; everybody must have arrived there, with a distance that is a position
+    const bool at_tail = me.x >= 0 && me.x < n && succ[me.x] == 0;
+    if (indeg[i] != 1 || !at_tail || me.y < 0 || me.y > n - 1) {
+        atomicOr(err, 2);
+        return;
+    }
+    order[n - 1 - me.y] = i;
+}
+
+// order[p] = node at position p of the tour succ[] started at node 0; *err != 0 afterwards: succ[] is not one Hamiltonian cycle.
+// work: 2 n int2 + n int + 1 int (device).
+cudaError_t launch_succ_to_order(const int *succ, int n, void *work, int *order, int *err, cudaStream_t st) {
+    int2 *a = static_cast<int2 *>(work), *b = a + n;
+    int *indeg = reinterpret_cast<int *>(b + n);
+    cudaError_t e = cudaMemsetAsync(indeg, 0, sizeof(int) * (size_t)n, st);
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(err, 0, sizeof(int), st);
+    if (e != cudaSuccess) return e;
+    const int grid = (n + 255) / 256;
+    rank_init_kernel<<<grid, 256, 0, st>>>(succ, n, a, indeg, err);
+    for (long long span = 1; span < n; span <<= 1) {
+        rank_jump_kernel<<<grid, 256, 0, st>>>(a, b, n);
+        int2 *t = a; a = b; b = t;
+    }
+    rank_finish_kernel<<<grid, 256, 0, st>>>(succ, a, indeg, n, order, err);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_rebuild_node_space(const TourDev &T, cudaStream_t st) {
     int grid = (T.n + 255) / 256;
     if (grid > 1184) grid = 1184;

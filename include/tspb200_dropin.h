@@ -99,6 +99,8 @@ int HEU_extramileage(tspb200_ref_instance *inst);
 int tspb200_dropin_layout(long long *out, int cap);
 /* Releases the cached device contexts (optional; they are also released at process exit). */
 void tspb200_dropin_reset(void);
+/* Number of instances currently resident on the device (the drop-in keeps up to four, least recently used first to go). */
+int tspb200_dropin_resident(void);
 
 #ifdef __cplusplus
 }

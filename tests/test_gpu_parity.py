@@ -1086,3 +1086,40 @@ def test_dropin_calc_dist_beyond_the_host_mirror_and_after_in_place_edits(oracle
     for i, j in ((3, 9), (0, 399), (17, 250)):
         assert L.calc_dist(i, j, C.byref(inst2.c)) == oracle.dist(moved, 0, i, j)
     L.tspb200_dropin_reset()
+
+
+def test_dropin_keeps_several_instances_resident(oracle):
+    """a caller that alternates between instances (csrc/dropin.cpp: up to four resident contexts, least recently used first to
+    go): every call is answered for the right instance, coming back to an instance does not evict the others, a fifth one
+    replaces the least recently used, and alg_2opt on an instance still sees that instance's coordinates."""
+    L = C.CDLL(eng.DROPIN_PATH)
+    L.calc_dist.restype = C.c_double
+    L.calc_dist.argtypes = [C.c_int, C.c_int, C.c_void_p]
+    L.alg_2opt.argtypes = [C.c_void_p]
+    L.tspb200_dropin_reset()
+    rng = np.random.default_rng(11)
+    insts = []
+    for k, (n, wt) in enumerate(((300, 0), (300, 0), (450, 3), (200, 5), (350, 0))):
+        xy = np.floor(rng.random((n, 2)) * 5000.0) + k
+        succ, cost = oracle.nn_tour(xy, wt, 0)
+        insts.append((xy, wt, RefInstance(xy, wt, succ, cost), succ, cost))
+    for rounds in range(3):
+        for k in (0, 1, 2, 3, 0, 2, 1, 3):
+            xy, wt, ri, _, _ = insts[k]
+            i, j = int(rng.integers(0, len(xy))), int(rng.integers(0, len(xy)))
+            assert L.calc_dist(i, j, C.byref(ri.c)) == oracle.dist(xy, wt, i, j), (rounds, k)
+        assert L.tspb200_dropin_resident() == 4
+    xy, wt, ri, succ, cost = insts[4]                      # a fifth problem: replaces the least recently used (instance 0)
+    assert L.alg_2opt(C.byref(ri.c)) == 0
+    es, eobj, _, _ = oracle.two_opt_fi(xy, wt, succ, cost)
+    assert (ri.succ() == es).all() and ri.c.solution.obj_best == eobj and L.tspb200_dropin_resident() == 4
+    for k in (3, 1, 2, 0):                                 # instance 0 comes back (evicting another one): still the right answers
+        xy, wt, ri, succ, cost = insts[k]
+        assert L.calc_dist(1, 7, C.byref(ri.c)) == oracle.dist(xy, wt, 1, 7)
+    xy, wt, ri, succ, cost = insts[2]
+    assert L.alg_2opt(C.byref(ri.c)) == 0
+    es, eobj, _, _ = oracle.two_opt_fi(xy, wt, succ, cost)
+    assert (ri.succ() == es).all() and ri.c.solution.obj_best == eobj
+    L.tspb200_dropin_reset()
+    assert L.tspb200_dropin_resident() == 0
+

@@ -6,7 +6,8 @@
 // whichever of u,v is the smaller index, and
 //     delta = D[p][q] + D[p+1][q+1] - ds[p] - ds[q],      D[p][q] = d(node(p), node(q)).
 // Each D value is therefore used by two pairs, (p,q) and (p-1,q-1): a thread owns R consecutive rows
-// and marches along the columns, so it needs R+1 fresh distances per R evaluated moves.
+// and marches along the columns, so it needs R+1 distances per R evaluated moves — R of its own and
+// the first one of the thread below, which the SHUF variants fetch from the next lane with a shuffle.
 //
 // Arithmetic: FP32 (2 FADD, FMUL, FFMA, MUFU.SQRT per distance) as a FILTER: Q = D1 + D2 - ds_p is
 // compared with thr + ds_q where thr = (best exact delta so far) + W.  W bounds the worst FP32/rounding

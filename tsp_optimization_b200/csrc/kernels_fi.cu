@@ -3,8 +3,8 @@
 // The reference sweeps node-index pairs (i<j) row-major and applies EVERY improving move at once, then
 // carries on from (i, j+1) with the modified tour; sweeps repeat until one brings no gain (:492).
 // Exact replay on a GPU: one launch = "find the first pair at or after the cursor, in that same order,
-// whose exact delta is negative" (a grid-wide min over the linear index i*n+j), apply it, advance the
-// cursor.  The scan is in NODE space (nrec/nds/nsucc) because the order that matters
+// whose exact delta is negative" (a grid-wide min over the word (i << 32) | j), apply it, advance the
+// cursor.  The scan is in NODE space (nrec/nlnk, doubly linked: tsp_state.cuh) because the order that matters
 // is the node-index order.  FP32 filter + FP64 exact check exactly as in the BI kernel.
 #include "tsp_state.cuh"
 
@@ -26,8 +26,8 @@ __device__ __forceinline__ float fi_dist32(float ax, float ay, float bx, float b
 // FI_SEG_CHUNKS x FI_CHUNK consecutive pairs (crossing row ends).  Blocks draw segments in increasing order from an atomic
 // counter; a block scans its segment chunk by chunk — FI_CHUNK = 256 threads x FI_U pairs, every thread's FI_U pairs are
 // loaded before the first one is evaluated so that their L2 round trips overlap — and after every chunk the block votes:
-// a hit inside the chunk (the smallest offset is the first one in order) is published with atomicMin on the (row*n + j)
-// index and ends the block; so does a hit that ANOTHER block has published in the meantime at a pair in front of this
+// a hit inside the chunk (the smallest offset is the first one in order) is published with atomicMin on the (row << 32 | j)
+// word and ends the block; so does a hit that ANOTHER block has published in the meantime at a pair in front of this
 // chunk (thread 0 polls ctl->fi_found along with its own loads).  Blocks whose next segment starts behind a published hit
 // stop as well.  Every segment before the winning one has been scanned to its end without a hit, so the minimum is exactly
 // the reference's "first improving pair at or after the cursor"; the work past the hit is bounded by one chunk per block

@@ -291,7 +291,7 @@ def test_bi_tile_shapes(engine, oracle, T, R, TJ, fuse):
 @pytest.mark.parametrize("shuffle", [0, 1])
 def test_bi_row_shuffle_variant_equals_plain_variant(engine, oracle, T, R, TJ, shuffle):
     """bi_scan_kernel<..., SHUF>: a warp owns 32 R - 1 rows and takes the distance below a lane's rows from the next lane
-    (csrc/kernels_bi.cu); the plain variant computes it.  Same move log, exhaustive and pruned, from an NN start and from a
+    (csrc/kernels_bi_scan.cuh); the plain variant computes it.  Same move log, exhaustive and pruned, from an NN start and from a
     random start (wrap-around reversals), tile rows 32 R - 1 per warp vs 32 R."""
     xy = uniform_instance(2300)
     engine.set_option("block_threads", T)

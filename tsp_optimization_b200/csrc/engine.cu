@@ -685,7 +685,7 @@ static long long tile_plan(int n, int TI, int TJ, std::vector<int> *row_start, s
 // The per-shape factors are measured on B200 at n = 100 000 (tools/shardshape.py): 64-thread blocks (8 per SM, 16 warps)
 // hide latency best; R = 16 (1.0625 sqrt per move) pays with 150 registers, i.e. 12 warps per SM; R = 4 and 2 spend more
 // instructions per move than their sqrt count alone says.
-static int bi_blocks_per_sm(int t, int r, bool pruned = false) {  // 64 threads, exhaustive scan: TSPB_BI_MINBLOCKS64 (kernels_bi.cu)
+static int bi_blocks_per_sm(int t, int r, bool pruned = false) {  // 64 threads, exhaustive scan: TSPB_BI_MINBLOCKS64 (kernels_bi_scan.cuh)
     return r >= 16 ? (t == 256 ? 1 : 384 / t) : (t == 64 && !pruned ? 10 : 512 / t);
 }
 

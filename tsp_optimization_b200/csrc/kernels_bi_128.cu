@@ -1,0 +1,13 @@
+// kernels_bi_128.cu — bi_scan_kernel<128, R, ...>
+#include "kernels_bi_scan.cuh"
+
+namespace tspb {
+
+cudaError_t launch_bi_scan_128(const BiArgs &a, int R, int grid, bool pdl, cudaStream_t st) {
+    if (R == 16) return launch_bi_tr<128, 16, false>(a, grid, pdl, st);
+    if (R == 8) return launch_bi_tr<128, 8, false>(a, grid, pdl, st);
+    if (R == 4) return launch_bi_tr<128, 4, false>(a, grid, pdl, st);
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace tspb

@@ -226,6 +226,10 @@ int tspb200_comm_destroy(tspb200_ctx *ctx);
  * sharding tests. */
 int tspb200_debug_tile_plan(int n, int T, int R, int TJ, int num_sms, int world, int *out_T, int *out_R, int *out_TJ,
                             int *row_start, int *row_j0, int cap, int *ntr);
+/* The same with the row-shuffle variant of the scan kernel taken into account (row_shuffle != 0: a tile-row of a 64-thread
+ * shape is (T/32)(32R - 1) positions, *out_tile_rows; the shape model knows about it), i.e. the plan tspb200_tour_upload makes. */
+int tspb200_debug_tile_plan_ex(int n, int T, int R, int TJ, int num_sms, int world, int row_shuffle, int *out_T, int *out_R,
+                               int *out_TJ, int *out_tile_rows, int *row_start, int *row_j0, int cap, int *ntr);
 
 /* Timing experiments: device-side debug buffers ("block_times": [grid][2] uint64 %globaltimer stamps {start, end} of every
  * block of the last best-improvement pass run with option "timing" = 2). */

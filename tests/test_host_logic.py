@@ -2,7 +2,7 @@
 import numpy as np
 import pytest
 
-from tsp_optimization_b200.engine import key_pack, key_unpack, tile_plan
+from tsp_optimization_b200.engine import key_pack, key_unpack, tile_plan, tile_plan_ex
 from tsp_optimization_b200.instances import (is_tour, order_to_succ, random_tours, succ_to_order,
                                              uniform_instance)
 
@@ -39,6 +39,31 @@ def test_tile_plan_covers_every_pair_exactly_once(n, T, R, TJ):
     want[0, n - 1] = 0
     assert (cover == want).all()
     assert int(want.sum()) == n * (n - 3) // 2
+
+
+@pytest.mark.parametrize("n,R,TJ", [(130, 2, 32), (700, 2, 64), (1500, 4, 64), (2100, 8, 128), (513, 8, 64), (1021, 8, 88), (1275, 4, 32)])
+def test_row_shuffle_tile_plan_covers_every_pair_exactly_once(n, R, TJ):
+    """the row-shuffle variant (csrc/kernels_bi_scan.cuh): a warp owns 32R - 1 rows — lane L the rows [L R, L R + R) of the warp's
+    range, lane 31's last row is masked and belongs to the next warp — so a 64-thread tile-row is 2 (32R - 1) positions; with
+    that height the plan must still cover every non-adjacent pair exactly once, and the lanes' rows must tile the tile-row."""
+    T = 64
+    t, r, tj, ti, rs, rj = tile_plan_ex(n, R, TJ, threads=T, row_shuffle=1)
+    assert (t, r, tj, ti) == (T, R, TJ, (T // 32) * (32 * R - 1))
+    owned = []
+    for warp in range(T // 32):
+        for lane in range(32):
+            rows = list(range(warp * (32 * R - 1) + lane * R, warp * (32 * R - 1) + lane * R + R))
+            owned += rows[:-1] if lane == 31 else rows
+    assert sorted(owned) == list(range(ti))          # every row of the tile-row exactly once
+    cover = covered_pairs(n, ti, TJ, rs, rj)
+    want = np.zeros((n, n), dtype=np.int32)
+    for p in range(n):
+        want[p, p + 2:] = 1
+    want[0, n - 1] = 0
+    assert (cover == want).all()
+    # the plain plan of the same shape is a different one (taller tile-rows): the option really changes the plan
+    assert tile_plan_ex(n, R, TJ, threads=T, row_shuffle=0)[3] == T * R
+    assert tile_plan_ex(100000)[:4] == (64, 8, 256, 510)
 
 
 def test_tile_plan_round_robin_sharding_partitions_the_tiles():

@@ -770,14 +770,16 @@ int tspb200_debug_fetch(tspb200_ctx *ctx, const char *what, void *out, int64_t b
 
 // Host-only helper (no device needed): the tile plan for (n, T, R, TJ); T, R or TJ == 0 -> automatic choice for
 // `num_sms` SMs and `world` ranks. row_start gets ntr+1 entries, row_j0 ntr entries.
-int tspb200_debug_tile_plan(int n, int T, int R, int TJ, int num_sms, int world, int *out_T, int *out_R, int *out_TJ,
-                            int *row_start, int *row_j0, int cap, int *ntr) {
+int tspb200_debug_tile_plan_ex(int n, int T, int R, int TJ, int num_sms, int world, int row_shuffle, int *out_T, int *out_R,
+                               int *out_TJ, int *out_tile_rows, int *row_start, int *row_j0, int cap, int *ntr) {
     if (n < 1 || num_sms < 1 || world < 1) return TSPB200_E_ARG;
     int t = T, r = R, tj = TJ;
-    if (t == 0 || r == 0 || tj == 0) choose_tile_shape(n, num_sms, world, T, R, TJ, false, &t, &r, &tj);
+    if (t == 0 || r == 0 || tj == 0) choose_tile_shape(n, num_sms, world, T, R, TJ, row_shuffle != 0, &t, &r, &tj);
     if (!bi_shape_supported(t, r)) return TSPB200_E_ARG;
+    const int sh = (row_shuffle && bi_shuffle_supported(t, r)) ? 1 : 0;  // what plan_tiles() does with the option
+    const int TI = bi_tile_rows(t, r, sh);
     std::vector<int> rs, rj;
-    tile_plan(n, t * r, tj, &rs, &rj);
+    tile_plan(n, TI, tj, &rs, &rj);
     if ((int)rs.size() > cap) return TSPB200_E_ARG;
     for (size_t k = 0; k < rs.size(); ++k) row_start[k] = rs[k];
     for (size_t k = 0; k < rj.size(); ++k) row_j0[k] = rj[k];
@@ -785,7 +787,13 @@ int tspb200_debug_tile_plan(int n, int T, int R, int TJ, int num_sms, int world,
     if (out_T) *out_T = t;
     if (out_R) *out_R = r;
     if (out_TJ) *out_TJ = tj;
+    if (out_tile_rows) *out_tile_rows = TI;
     return TSPB200_OK;
+}
+
+int tspb200_debug_tile_plan(int n, int T, int R, int TJ, int num_sms, int world, int *out_T, int *out_R, int *out_TJ,
+                            int *row_start, int *row_j0, int cap, int *ntr) {
+    return tspb200_debug_tile_plan_ex(n, T, R, TJ, num_sms, world, 0, out_T, out_R, out_TJ, nullptr, row_start, row_j0, cap, ntr);
 }
 
 int tspb200_tour_upload(tspb200_ctx *ctx, const int32_t *succ, int64_t log_cap) {

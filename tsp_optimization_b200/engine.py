@@ -32,7 +32,7 @@ ABI_SYMBOLS = [
     "tspb200_dist_matrix_free", "tspb200_dist_row", "tspb200_tour_upload", "tspb200_tour_download", "tspb200_tour_log",
     "tspb200_bi_run", "tspb200_fi_run", "tspb200_two_opt", "tspb200_two_opt_tabu", "tspb200_two_opt_batch", "tspb200_nn_tour", "tspb200_nn_tour_batch", "tspb200_extra_mileage",
     "tspb200_tour_costs", "tspb200_comm_unique_id", "tspb200_comm_init", "tspb200_comm_destroy",
-    "tspb200_debug_tile_plan", "tspb200_debug_fetch",
+    "tspb200_debug_tile_plan", "tspb200_debug_tile_plan_ex", "tspb200_debug_fetch",
     "tspb200_tour_cost", "tspb200_tour_save", "tspb200_tour_restore", "tspb200_vns_kick",
     "tspb200_tabu_begin", "tspb200_tabu_run", "tspb200_tabu_kick", "tspb200_tabu_end",
     "tspb200_population_upload", "tspb200_population_download", "tspb200_population_costs", "tspb200_population_two_opt",
@@ -155,6 +155,22 @@ def tile_plan(n: int, rows_per_thread: int = 0, tile_cols: int = 0, threads: int
     if rc:
         raise TspB200Error(rc, "tile plan failed")
     return t.value, r.value, tj.value, rs[:ntr.value + 1].copy(), rj[:ntr.value].copy()
+
+
+def tile_plan_ex(n: int, rows_per_thread: int = 0, tile_cols: int = 0, threads: int = 0, num_sms: int = 148, world: int = 1,
+                 row_shuffle: int = 1):
+    """Host-only: the plan tspb200_tour_upload makes, row-shuffle variant included -> (T, R, TJ, tile_rows, row_start, row_j0)."""
+    L = load_library()
+    cap = n // 32 + 8
+    rs = np.zeros(cap, dtype=np.int32)
+    rj = np.zeros(cap, dtype=np.int32)
+    t, r, tj, ti, ntr = C.c_int32(0), C.c_int32(0), C.c_int32(0), C.c_int32(0), C.c_int32(0)
+    L.tspb200_debug_tile_plan_ex.argtypes = [C.c_int] * 7 + [C.POINTER(C.c_int32)] * 4 + [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int32)]
+    rc = L.tspb200_debug_tile_plan_ex(n, threads, rows_per_thread, tile_cols, num_sms, world, row_shuffle, C.byref(t), C.byref(r),
+                                      C.byref(tj), C.byref(ti), rs.ctypes.data, rj.ctypes.data, cap, C.byref(ntr))
+    if rc:
+        raise TspB200Error(rc, "tile plan failed")
+    return t.value, r.value, tj.value, ti.value, rs[:ntr.value + 1].copy(), rj[:ntr.value].copy()
 
 
 def key_pack(delta: int, i: int, j: int) -> int:

@@ -8,8 +8,9 @@ nearest-neighbour start tour built on the GPU, best-improvement 2-opt with on-th
 One STEP = one best-improvement pass = all n(n-3)/2 move deltas evaluated + argmin + move applied.
   value   = passes * n(n-3)/2 / device time, tour resident in HBM, EXHAUSTIVE scan (exact tile pruning off), every pass
             preceded by an L2 flush and timed by its own CUDA event pair on the engine's stream
-  e2e     = the same through the host-buffer C-ABI call tspb200_two_opt(): coordinates + tour uploaded from
-            pinned host memory, K passes, tour downloaded, wall clock around the call
+  e2e     = the same through the host-buffer C-ABI calls tspb200_set_instance() + tspb200_two_opt(): the tour uploaded
+            from pinned host memory (the coordinates are a constant of the job: compared on the host, re-sent only when
+            they change), K passes, tour and cost downloaded, wall clock around the calls
   N > 1   : the pair tiles are dealt round-robin over the ranks (strong scaling, same instance); per pass every rank's
             packed argmin key is stored into every peer's slots over NVLink by the scan kernel itself (CUDA IPC peer
             memory; NCCL only bootstraps the handles and is the fallback); max over ranks of the device time.

@@ -82,10 +82,12 @@ def test_sharded_argmin_equals_reference_moves(tmp_path, oracle):
     assert m0.tolist() == log.tolist()
 
 
-def _fi_worker(rank, world, port, out_dir):
+def _fi_worker(rank, world, port, out_dir, min_gap=0):
     """first improvement, sharded like csrc/kernels_fi.cu: the row-major pair order from the cursor is cut into segments of SEG
     pairs, rank r scans the segments r, r + world, ... and stops at ITS first improving pair; the min over the ranks of the
-    linear index i * n + j is the reference's next move."""
+    linear index i * n + j is the reference's next move.  min_gap > 0 is the adaptive rule (Ctl::fi_shard): a search is
+    sharded (and exchanged) only if the previous one had to sweep more than min_gap pairs — a number every rank has —,
+    otherwise every rank searches the whole range alone and NO collective is entered (all ranks must agree on that)."""
     import sys
     sys.path.insert(0, ROOT)
     from oracle.oracle import Oracle
@@ -103,9 +105,12 @@ def _fi_worker(rank, world, port, out_dir):
     moves = []
     cursor, sweep_moves = 0, 0
     NONE = 1 << 40
+    shard = min_gap == 0
+    exchanges = 0
     while len(moves) < 60:
         found = NONE
-        seg = rank
+        seg = rank if shard else 0
+        step = world if shard else 1
         while cursor + seg * SEG < len(pairs):
             lo = cursor + seg * SEG
             for k in range(lo, min(lo + SEG, len(pairs))):
@@ -118,15 +123,22 @@ def _fi_worker(rank, world, port, out_dir):
                     break
             if found != NONE:
                 break
-            seg += world
-        t = torch.tensor([found], dtype=torch.int64)
-        dist.all_reduce(t, op=dist.ReduceOp.MIN)
-        f = int(t.item())
+            seg += step
+        f = found
+        if shard:
+            t = torch.tensor([found], dtype=torch.int64)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            f = int(t.item())
+            exchanges += 1
         if f == NONE:  # end of the sweep (heuristics.c:492-496)
+            if min_gap:
+                shard = len(pairs) - cursor > min_gap
             if sweep_moves == 0:
                 break
             cursor, sweep_moves = 0, 0
             continue
+        if min_gap:  # the next search's mode, from the length of this one (csrc/tsp_state.cuh fi_advance)
+            shard = pairs.index(divmod(f, n)) - cursor + 1 > min_gap
         i, j = divmod(f, n)
         a1, b1 = int(succ[i]), int(succ[j])
         moves.append((i, j, int(D[i, j] + D[a1, b1] - D[i, a1] - D[j, b1])))
@@ -137,7 +149,7 @@ def _fi_worker(rank, world, port, out_dir):
         orc.L.orc_reverse_path(n, succ, j, a1, prev)
         sweep_moves += 1
         cursor = pairs.index((i, j)) + 1
-    np.save(os.path.join(out_dir, f"fi_moves_{rank}.npy"), np.array(moves, dtype=np.int64))
+    np.save(os.path.join(out_dir, f"fi_moves_{rank}_{min_gap}.npy"), np.array(moves + [(exchanges, 0, 0)], dtype=np.int64))
     dist.destroy_process_group()
 
 
@@ -149,7 +161,14 @@ def test_sharded_first_improvement_equals_reference_moves(tmp_path, oracle):
     xy = uniform_instance(220)
     succ, cost = oracle.nn_tour(xy, 0, 0)
     _, _, _, log = oracle.two_opt_fi(xy, 0, succ, cost, max_moves=60, log_cap=60)
-    m0 = np.load(tmp_path / "fi_moves_0.npy")
-    m1 = np.load(tmp_path / "fi_moves_1.npy")
+    m0 = np.load(tmp_path / "fi_moves_0_0.npy")
+    m1 = np.load(tmp_path / "fi_moves_1_0.npy")
     assert (m0 == m1).all()
-    assert m0.tolist() == log.tolist()
+    assert m0[:-1].tolist() == log.tolist()
+    # adaptive sharding: same moves, the ranks agree on when to exchange, and they exchange less often than every search
+    port = _free_port()
+    mp.spawn(_fi_worker, args=(world, port, str(tmp_path), 300), nprocs=world, join=True)
+    a0 = np.load(tmp_path / "fi_moves_0_300.npy")
+    a1 = np.load(tmp_path / "fi_moves_1_300.npy")
+    assert (a0 == a1).all() and a0[:-1].tolist() == log.tolist()
+    assert 0 < a0[-1][0] < m0[-1][0]
